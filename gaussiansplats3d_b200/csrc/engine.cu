@@ -1,0 +1,598 @@
+// engine.cu -- host side of libgsplat_b200.so: the C ABI declared in include/gsplat_b200.h.
+//
+// One gs_engine = the device-resident state of one sort Worker (src/worker/SortWorker.js) plus one SplatMesh
+// (src/splatmesh/SplatMesh.js) on one B200: persistent centres, splat data, scratch, one CUDA stream.
+// There is no CPU implementation of any stage in this library: without a device every entry fails.
+#include "../../include/gsplat_b200.h"
+#include "common.cuh"
+#include "sort_kernels.cuh"
+#include "raster_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+using namespace gs;
+
+// ---------------------------------------------------------------------------------------------------------------
+thread_local char g_gs_err[512] = "";
+#define g_err g_gs_err
+static int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CU(call)                                                                                                  \
+    do {                                                                                                          \
+        cudaError_t _e = (call);                                                                                  \
+        if (_e != cudaSuccess) return fail(GS_ERR_CUDA, "%s -> %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+extern "C" int gs_abi_version(void) { return GS_ABI_VERSION; }
+extern "C" const char *gs_last_error_message(void) { return g_err; }
+extern "C" const char *gs_status_string(int s) {
+    switch (s) {
+        case GS_OK: return "ok";
+        case GS_ERR_BAD_ARG: return "bad argument";
+        case GS_ERR_NO_DEVICE: return "no CUDA device";
+        case GS_ERR_CUDA: return "CUDA error";
+        case GS_ERR_DEGENERATE: return "all distances equal";
+        case GS_ERR_BUCKET_RANGE: return "bucket index out of range";
+        case GS_ERR_NOT_READY: return "not ready";
+        case GS_ERR_CAPACITY: return "capacity exceeded";
+        default: return "unknown";
+    }
+}
+extern "C" int gs_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T> struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    int ensure(size_t count) {
+        if (count <= n) return GS_OK;
+        if (p) cudaFree(p);
+        p = nullptr; n = 0;
+        cudaError_t e = cudaMalloc((void **)&p, std::max<size_t>(count, 1) * sizeof(T));
+        if (e != cudaSuccess) return fail(GS_ERR_CUDA, "cudaMalloc(%zu bytes) -> %s", count * sizeof(T), cudaGetErrorString(e));
+        n = count;
+        return GS_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+template <typename T> struct PinBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    int ensure(size_t count) {
+        if (count <= n) return GS_OK;
+        if (p) cudaFreeHost(p);
+        p = nullptr; n = 0;
+        cudaError_t e = cudaHostAlloc((void **)&p, std::max<size_t>(count, 1) * sizeof(T), cudaHostAllocDefault);
+        if (e != cudaSuccess) return fail(GS_ERR_CUDA, "cudaHostAlloc(%zu bytes) -> %s", count * sizeof(T), cudaGetErrorString(e));
+        n = count;
+        return GS_OK;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; n = 0; }
+};
+
+enum { EV_SORT0, EV_DEPTH, EV_BUCKET, EV_SORT1, EV_R0, EV_PROJECT, EV_BIN, EV_R1, EV_H2D0, EV_H2D1, EV_D2H0, EV_D2H1, EV_COUNT };
+
+struct gs_engine {
+    gs_config cfg{};
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[EV_COUNT]{};
+    int sm_count = 148;
+    int key_bits = 16;
+
+    // --- sorter state (SortWorker.js:125-178 memory regions, device side) ---
+    DevBuf<int4> centers;            // int32x4 or f32x4 per splat
+    DevBuf<uint32_t> scene_idx;      // dynamic mode
+    DevBuf<uint32_t> indexes;        // indexesToSort
+    DevBuf<uint32_t> precomputed;    // precomputedDistances (i32 or f32 bits)
+    DevBuf<int32_t> dist;            // mappedDistances
+    DevBuf<uint32_t> keys[2];        // radix keys ping/pong (u16 or u32 elements, sized in u32 words)
+    DevBuf<uint32_t> vals[2];        // radix values ping/pong
+    DevBuf<uint32_t> sorted;         // sortedIndexes
+    DevBuf<float> transforms;        // 32 x mat4
+    DevBuf<SortControl> ctl;
+    DevBuf<uint32_t> lookback;
+    DevBuf<uint32_t> freq;           // scratch reproduction for gs_sort_indexes
+    uint32_t uploaded_splats = 0;    // 'uploadedSplatCount' SortWorker.js:97
+    uint32_t last_render_count = 0;
+    bool have_sorted = false;
+
+    // pinned staging (the shared-memory views of SortWorker.js:180-191)
+    PinBuf<uint32_t> h_indexes, h_sorted;
+    PinBuf<uint32_t> h_ctl;
+    PinBuf<unsigned char> h_frame;
+
+    // --- rasteriser state ---
+    RasterState rs;
+
+    gs_timings tm{};
+};
+
+static int check_engine(gs_engine *e) {
+    if (!e) return fail(GS_ERR_BAD_ARG, "null engine");
+    cudaError_t ce = cudaSetDevice(e->cfg.device);
+    if (ce != cudaSuccess) return fail(GS_ERR_CUDA, "cudaSetDevice(%d) -> %s", e->cfg.device, cudaGetErrorString(ce));
+    return GS_OK;
+}
+
+extern "C" int gs_create(const gs_config *cfg, gs_engine **out) {
+    if (!cfg || !out) return fail(GS_ERR_BAD_ARG, "gs_create: null argument");
+    *out = nullptr;
+    gs_config c{};
+    memcpy(&c, cfg, std::min<size_t>(cfg->struct_size ? cfg->struct_size : sizeof(gs_config), sizeof(gs_config)));
+    if (c.distance_map_range == 0) c.distance_map_range = 1u << 16; // Constants.DefaultSplatSortDistanceMapPrecision
+    if (c.distance_map_range < 2 || c.distance_map_range > (1u << 24)) return fail(GS_ERR_BAD_ARG, "distance_map_range %u outside [2, 2^24]", c.distance_map_range);
+    if (c.world_size == 0) { c.world_size = 1; c.rank = 0; }
+    if (c.rank >= c.world_size) return fail(GS_ERR_BAD_ARG, "rank %u >= world_size %u", c.rank, c.world_size);
+    int ndev = gs_device_count();
+    if (ndev <= 0) return fail(GS_ERR_NO_DEVICE, "no CUDA device visible: libgsplat_b200 has no CPU path");
+    if (c.device < 0 || c.device >= ndev) return fail(GS_ERR_BAD_ARG, "device %d not in [0,%d)", c.device, ndev);
+    CU(cudaSetDevice(c.device));
+    gs_engine *e = new (std::nothrow) gs_engine();
+    if (!e) return fail(GS_ERR_BAD_ARG, "out of host memory");
+    e->cfg = c;
+    cudaDeviceProp prop{};
+    CU(cudaGetDeviceProperties(&prop, c.device));
+    e->sm_count = prop.multiProcessorCount;
+    CU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    for (int i = 0; i < EV_COUNT; ++i) CU(cudaEventCreate(&e->ev[i]));
+    int kb = 0;
+    while ((1u << kb) < c.distance_map_range) ++kb;
+    e->key_bits = kb;
+    int rc = GS_OK;
+    const size_t n = std::max<uint32_t>(c.max_splat_count, 1);
+    if ((rc = e->centers.ensure(n)) || (rc = e->indexes.ensure(n)) || (rc = e->dist.ensure(n)) || (rc = e->sorted.ensure(n)) ||
+        (rc = e->vals[0].ensure(n)) || (rc = e->vals[1].ensure(n)) || (rc = e->keys[0].ensure(n)) || (rc = e->keys[1].ensure(n)) ||
+        (rc = e->ctl.ensure(1)) || (rc = e->transforms.ensure(16 * GS_MAX_SCENES)) || (rc = e->h_ctl.ensure(sizeof(SortControl) / 4 + 64))) {
+        gs_destroy(e);
+        return rc;
+    }
+    if (c.dynamic_mode && (rc = e->scene_idx.ensure(n))) { gs_destroy(e); return rc; }
+    cudaMemsetAsync(e->scene_idx.p, 0, e->scene_idx.n * 4, e->stream);
+    {   // identity transforms until the caller provides some
+        std::vector<float> id(16 * GS_MAX_SCENES, 0.f);
+        for (int s = 0; s < GS_MAX_SCENES; ++s) id[16 * s] = id[16 * s + 5] = id[16 * s + 10] = id[16 * s + 15] = 1.f;
+        CU(cudaMemcpy(e->transforms.p, id.data(), id.size() * 4, cudaMemcpyHostToDevice));
+    }
+    rc = raster_init(e->rs, c, e->sm_count);
+    if (rc) { gs_destroy(e); return fail(rc, "raster_init failed: %s", g_err); }
+    CU(cudaStreamSynchronize(e->stream));
+    *out = e;
+    return GS_OK;
+}
+
+extern "C" void gs_destroy(gs_engine *e) {
+    if (!e) return;
+    cudaSetDevice(e->cfg.device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    e->centers.release(); e->scene_idx.release(); e->indexes.release(); e->precomputed.release(); e->dist.release();
+    e->keys[0].release(); e->keys[1].release(); e->vals[0].release(); e->vals[1].release(); e->sorted.release();
+    e->transforms.release(); e->ctl.release(); e->lookback.release(); e->freq.release();
+    e->h_indexes.release(); e->h_sorted.release(); e->h_ctl.release(); e->h_frame.release();
+    raster_release(e->rs);
+    for (int i = 0; i < EV_COUNT; ++i) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+extern "C" int gs_upload_centers(gs_engine *e, const void *centers, const uint32_t *sceneIndexes, uint32_t from, uint32_t count) {
+    int rc = check_engine(e);
+    if (rc) return rc;
+    if (!centers && count) return fail(GS_ERR_BAD_ARG, "gs_upload_centers: null centers");
+    if ((uint64_t)from + count > e->cfg.max_splat_count) return fail(GS_ERR_CAPACITY, "centres [%u,%u) exceed max_splat_count %u", from, from + count, e->cfg.max_splat_count);
+    if (count) CU(cudaMemcpyAsync(e->centers.p + from, centers, (size_t)count * 16, cudaMemcpyHostToDevice, e->stream));
+    if (e->cfg.dynamic_mode && sceneIndexes && count)
+        CU(cudaMemcpyAsync(e->scene_idx.p + from, sceneIndexes, (size_t)count * 4, cudaMemcpyHostToDevice, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    e->uploaded_splats = from + count; // SortWorker.js:97
+    return GS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+template <int MODE>
+static void launch_depth(bool identity, int blocks, cudaStream_t st, const uint32_t *idx, const void *centers, const void *pre,
+                         const uint32_t *scene, const float *tr, const DepthParams &P, uint32_t s0, uint32_t rc, int32_t *dist, SortControl *ctl) {
+    if (identity) k_depth<MODE, true><<<blocks, kDepthThreads, 0, st>>>(idx, centers, pre, scene, tr, P, s0, rc, dist, ctl);
+    else k_depth<MODE, false><<<blocks, kDepthThreads, 0, st>>>(idx, centers, pre, scene, tr, P, s0, rc, dist, ctl);
+}
+
+// The sort proper, everything already on the device.  d_indexes == nullptr: identity.
+static int sort_on_device(gs_engine *e, const uint32_t *d_indexes, const float *mvp, uint32_t sort_count, uint32_t render_count,
+                          bool use_pre, bool write_buckets) {
+    if (sort_count > render_count) return fail(GS_ERR_BAD_ARG, "sortCount %u > renderCount %u", sort_count, render_count);
+    if (render_count > e->cfg.max_splat_count) return fail(GS_ERR_CAPACITY, "renderCount %u > max_splat_count %u", render_count, e->cfg.max_splat_count);
+    cudaStream_t st = e->stream;
+    const uint32_t s0 = render_count - sort_count, n = sort_count;
+    const PassPlan pl = make_plan_bits(e->key_bits);
+    uint32_t launches = 0;
+    int rc = e->lookback.ensure(radix_lookback_words(std::max(n, 1u), pl.npasses));
+    if (rc) return rc;
+    CU(cudaEventRecord(e->ev[EV_SORT0], st));
+    k_sort_init<<<std::max(1, e->sm_count), 256, 0, st>>>(e->ctl.p, e->lookback.p, radix_lookback_words(std::max(n, 1u), pl.npasses));
+    ++launches;
+    if (s0 > 0) { k_copy_head<<<std::min<uint32_t>((s0 + 255) / 256, e->sm_count * 8), 256, 0, st>>>(d_indexes, e->sorted.p, s0); ++launches; }
+    if (n > 0) {
+        DepthParams P{};
+        memcpy(P.mvp, mvp, 64);
+        P.irow[0] = (int32_t)((double)mvp[2] * 1000.0);   // sorter.cpp:64 -- f64 product, truncation toward zero
+        P.irow[1] = (int32_t)((double)mvp[6] * 1000.0);
+        P.irow[2] = (int32_t)((double)mvp[10] * 1000.0);
+        P.irow[3] = 1;
+        P.frow[0] = mvp[2]; P.frow[1] = mvp[6]; P.frow[2] = mvp[10]; P.frow[3] = 0.f;
+        const bool integer = e->cfg.integer_based_sort, dyn = e->cfg.dynamic_mode;
+        const int mode = use_pre ? (integer ? kIntPrecomputed : kFloatPrecomputed)
+                                 : (integer ? (dyn ? kIntDynamic : kIntStatic) : (dyn ? kFloatDynamic : kFloatStatic));
+        const int dblocks = (int)std::min<uint64_t>(((uint64_t)n + kDepthThreads * kDepthItems - 1) / (kDepthThreads * kDepthItems), (uint64_t)e->sm_count * 8);
+        const bool identity = (d_indexes == nullptr);
+        const void *pre = e->precomputed.p;
+        switch (mode) {
+            case kIntStatic: launch_depth<kIntStatic>(identity, dblocks, st, d_indexes, e->centers.p, pre, e->scene_idx.p, e->transforms.p, P, s0, render_count, e->dist.p, e->ctl.p); break;
+            case kIntDynamic: launch_depth<kIntDynamic>(identity, dblocks, st, d_indexes, e->centers.p, pre, e->scene_idx.p, e->transforms.p, P, s0, render_count, e->dist.p, e->ctl.p); break;
+            case kIntPrecomputed: launch_depth<kIntPrecomputed>(identity, dblocks, st, d_indexes, e->centers.p, pre, e->scene_idx.p, e->transforms.p, P, s0, render_count, e->dist.p, e->ctl.p); break;
+            case kFloatStatic: launch_depth<kFloatStatic>(identity, dblocks, st, d_indexes, e->centers.p, pre, e->scene_idx.p, e->transforms.p, P, s0, render_count, e->dist.p, e->ctl.p); break;
+            case kFloatDynamic: launch_depth<kFloatDynamic>(identity, dblocks, st, d_indexes, e->centers.p, pre, e->scene_idx.p, e->transforms.p, P, s0, render_count, e->dist.p, e->ctl.p); break;
+            default: launch_depth<kFloatPrecomputed>(identity, dblocks, st, d_indexes, e->centers.p, pre, e->scene_idx.p, e->transforms.p, P, s0, render_count, e->dist.p, e->ctl.p); break;
+        }
+        ++launches;
+        CU(cudaEventRecord(e->ev[EV_DEPTH], st));
+        const int bblocks = (int)std::min<uint64_t>(((uint64_t)n + kBucketThreads * kBucketItems - 1) / (kBucketThreads * kBucketItems), (uint64_t)e->sm_count * 8);
+        const uint32_t R = e->cfg.distance_map_range;
+        const uint32_t *vsrc = identity ? nullptr : d_indexes + s0;
+        const int vmode = identity ? kValIotaReversed : kValArrayReversed;
+        if (e->key_bits <= 16) {
+            k_bucket<uint16_t><<<bblocks, kBucketThreads, 0, st>>>(e->dist.p, (uint16_t *)e->keys[0].p, s0, render_count, R, pl, write_buckets ? 1 : 0, e->ctl.p);
+            ++launches;
+            CU(cudaEventRecord(e->ev[EV_BUCKET], st));
+            radix_sort_pairs<uint16_t>((uint16_t *)e->keys[0].p, (uint16_t *)e->keys[1].p, vsrc, render_count - 1u, vmode, e->vals[0].p, e->vals[1].p,
+                                       e->sorted.p + s0, n, nullptr, 0ull, pl, e->ctl.p, e->lookback.p, false, st, launches);
+        } else {
+            k_bucket<uint32_t><<<bblocks, kBucketThreads, 0, st>>>(e->dist.p, e->keys[0].p, s0, render_count, R, pl, write_buckets ? 1 : 0, e->ctl.p);
+            ++launches;
+            CU(cudaEventRecord(e->ev[EV_BUCKET], st));
+            radix_sort_pairs<uint32_t>(e->keys[0].p, e->keys[1].p, vsrc, render_count - 1u, vmode, e->vals[0].p, e->vals[1].p, e->sorted.p + s0, n,
+                                       nullptr, 0ull, pl, e->ctl.p, e->lookback.p, false, st, launches);
+        }
+    } else {
+        CU(cudaEventRecord(e->ev[EV_DEPTH], st));
+        CU(cudaEventRecord(e->ev[EV_BUCKET], st));
+    }
+    CU(cudaEventRecord(e->ev[EV_SORT1], st));
+    CU(cudaGetLastError());
+    e->tm.kernel_launches = launches;
+    e->last_render_count = render_count;
+    e->have_sorted = true;
+    return GS_OK;
+}
+
+// after a stream sync: fold the device-side error bits and stage timings into the engine
+static int finish_sort(gs_engine *e, float *sort_time_ms) {
+    CU(cudaMemcpyAsync(e->h_ctl.p, e->ctl.p, 12, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    float ms = 0.f;
+    cudaEventElapsedTime(&e->tm.depth_ms, e->ev[EV_SORT0], e->ev[EV_DEPTH]);
+    cudaEventElapsedTime(&e->tm.bucket_ms, e->ev[EV_DEPTH], e->ev[EV_BUCKET]);
+    cudaEventElapsedTime(&e->tm.scatter_ms, e->ev[EV_BUCKET], e->ev[EV_SORT1]);
+    cudaEventElapsedTime(&ms, e->ev[EV_SORT0], e->ev[EV_SORT1]);
+    e->tm.sort_total_ms = ms;
+    if (sort_time_ms) *sort_time_ms = ms;
+    const uint32_t err = e->h_ctl.p[2];
+    if (err & kErrBucketRange) return fail(GS_ERR_BUCKET_RANGE, "a bucket index fell outside [0,%u): distances overflow the int32/f32 range map", e->cfg.distance_map_range);
+    return GS_OK;
+}
+
+static int stage_sort_inputs(gs_engine *e, const gs_sort_params *p, const uint32_t **d_indexes) {
+    cudaStream_t st = e->stream;
+    *d_indexes = nullptr;
+    CU(cudaEventRecord(e->ev[EV_H2D0], st));
+    if (p->indexes_to_sort_dev) *d_indexes = p->indexes_to_sort_dev;
+    else if (p->indexes_to_sort) {
+        CU(cudaMemcpyAsync(e->indexes.p, p->indexes_to_sort, (size_t)p->render_count * 4, cudaMemcpyHostToDevice, st));
+        *d_indexes = e->indexes.p;
+    }
+    if (e->cfg.dynamic_mode && p->transforms) CU(cudaMemcpyAsync(e->transforms.p, p->transforms, 16 * GS_MAX_SCENES * 4, cudaMemcpyHostToDevice, st));
+    if (p->use_precomputed_distances) {
+        if (!p->precomputed_distances) return fail(GS_ERR_BAD_ARG, "use_precomputed_distances without precomputed_distances");
+        int rc = e->precomputed.ensure(e->cfg.max_splat_count);
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(e->precomputed.p, p->precomputed_distances, (size_t)e->uploaded_splats * 4, cudaMemcpyHostToDevice, st));
+    }
+    CU(cudaEventRecord(e->ev[EV_H2D1], st));
+    return GS_OK;
+}
+
+extern "C" int gs_sort(gs_engine *e, const gs_sort_params *p, uint32_t *sorted_out, float *sort_time_ms) {
+    int rc = check_engine(e);
+    if (rc) return rc;
+    if (!p) return fail(GS_ERR_BAD_ARG, "gs_sort: null params");
+    // SortWorker.js:99-100: counts are clamped to what has been uploaded
+    gs_sort_params q = *p;
+    q.render_count = std::min(q.render_count, e->uploaded_splats);
+    q.sort_count = std::min(q.sort_count, e->uploaded_splats);
+    if (q.sort_count > q.render_count) return fail(GS_ERR_BAD_ARG, "sortCount %u > renderCount %u", q.sort_count, q.render_count);
+    const uint32_t *d_idx = nullptr;
+    if ((rc = stage_sort_inputs(e, &q, &d_idx))) return rc;
+    if ((rc = sort_on_device(e, d_idx, q.model_view_proj, q.sort_count, q.render_count, q.use_precomputed_distances != 0, false))) return rc;
+    CU(cudaEventRecord(e->ev[EV_D2H0], e->stream));
+    if (sorted_out && q.render_count) CU(cudaMemcpyAsync(sorted_out, e->sorted.p, (size_t)q.render_count * 4, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaEventRecord(e->ev[EV_D2H1], e->stream));
+    rc = finish_sort(e, sort_time_ms);
+    cudaEventElapsedTime(&e->tm.h2d_ms, e->ev[EV_H2D0], e->ev[EV_H2D1]);
+    cudaEventElapsedTime(&e->tm.d2h_ms, e->ev[EV_D2H0], e->ev[EV_D2H1]);
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Stateless drop-in (sorter.cpp:17-22).  A private engine per (device 0, splatCount, mode, range) is cached so repeated
+// calls do not re-allocate; inputs are uploaded on every call like a non-shared-memory worker copies them
+// (SortWorker.js:35-51).
+static gs_engine *g_dropin = nullptr;
+
+extern "C" int gs_sort_indexes(const uint32_t *indexes, const void *centers, const void *precomputedDistances, int32_t *mappedDistances,
+                               uint32_t *frequencies, const float *modelViewProj, uint32_t *indexesOut, const uint32_t *sceneIndexes,
+                               const float *transforms, uint32_t distanceMapRange, uint32_t sortCount, uint32_t renderCount,
+                               uint32_t splatCount, bool usePrecomputedDistances, bool useIntegerSort, bool dynamicMode) {
+    if (!indexes || !modelViewProj || !indexesOut) return fail(GS_ERR_BAD_ARG, "gs_sort_indexes: null indexes/modelViewProj/indexesOut");
+    if (!usePrecomputedDistances && !centers) return fail(GS_ERR_BAD_ARG, "gs_sort_indexes: null centers");
+    if (usePrecomputedDistances && !precomputedDistances) return fail(GS_ERR_BAD_ARG, "gs_sort_indexes: null precomputedDistances");
+    if (dynamicMode && !usePrecomputedDistances && (!sceneIndexes || !transforms)) return fail(GS_ERR_BAD_ARG, "gs_sort_indexes: dynamic mode needs sceneIndexes and transforms");
+    if (sortCount > renderCount || renderCount > splatCount) return fail(GS_ERR_BAD_ARG, "need sortCount <= renderCount <= splatCount");
+    if (distanceMapRange < 2 || distanceMapRange > (1u << 24)) return fail(GS_ERR_BAD_ARG, "distanceMapRange %u outside [2, 2^24]", distanceMapRange);
+    gs_engine *e = g_dropin;
+    if (!e || e->cfg.max_splat_count < splatCount || e->cfg.distance_map_range != distanceMapRange ||
+        (bool)e->cfg.integer_based_sort != useIntegerSort || (bool)e->cfg.dynamic_mode != dynamicMode) {
+        if (e) gs_destroy(e);
+        g_dropin = nullptr;
+        gs_config c{};
+        c.struct_size = sizeof(c);
+        c.device = 0;
+        c.max_splat_count = std::max(splatCount, 1u);
+        c.distance_map_range = distanceMapRange;
+        c.integer_based_sort = useIntegerSort;
+        c.dynamic_mode = dynamicMode;
+        int rc = gs_create(&c, &e);
+        if (rc) return rc;
+        g_dropin = e;
+    }
+    int rc = check_engine(e);
+    if (rc) return rc;
+    cudaStream_t st = e->stream;
+    if (centers && splatCount) CU(cudaMemcpyAsync(e->centers.p, centers, (size_t)splatCount * 16, cudaMemcpyHostToDevice, st));
+    if (dynamicMode && sceneIndexes && splatCount) CU(cudaMemcpyAsync(e->scene_idx.p, sceneIndexes, (size_t)splatCount * 4, cudaMemcpyHostToDevice, st));
+    if (dynamicMode && transforms) CU(cudaMemcpyAsync(e->transforms.p, transforms, 16 * GS_MAX_SCENES * 4, cudaMemcpyHostToDevice, st));
+    if (usePrecomputedDistances) {
+        if ((rc = e->precomputed.ensure(e->cfg.max_splat_count))) return rc;
+        CU(cudaMemcpyAsync(e->precomputed.p, precomputedDistances, (size_t)splatCount * 4, cudaMemcpyHostToDevice, st));
+    }
+    if (renderCount) CU(cudaMemcpyAsync(e->indexes.p, indexes, (size_t)renderCount * 4, cudaMemcpyHostToDevice, st));
+    e->uploaded_splats = splatCount;
+    const bool want_scratch = (mappedDistances != nullptr) || (frequencies != nullptr);
+    if ((rc = sort_on_device(e, e->indexes.p, modelViewProj, sortCount, renderCount, usePrecomputedDistances, want_scratch))) return rc;
+    // wasm-trap emulation: results are only written back when the device reported no range error
+    std::vector<uint32_t> out_stage;
+    if ((rc = finish_sort(e, nullptr))) return rc;
+    if (renderCount) CU(cudaMemcpyAsync(indexesOut, e->sorted.p, (size_t)renderCount * 4, cudaMemcpyDeviceToHost, st));
+    const uint32_t s0 = renderCount - sortCount;
+    if (mappedDistances && sortCount) CU(cudaMemcpyAsync(mappedDistances + s0, e->dist.p + s0, (size_t)sortCount * 4, cudaMemcpyDeviceToHost, st));
+    if (frequencies) {
+        if ((rc = e->freq.ensure(distanceMapRange))) return rc;
+        CU(cudaMemsetAsync(e->freq.p, 0, (size_t)distanceMapRange * 4, st));
+        if (sortCount) k_bucket_counts<<<std::min<uint32_t>((sortCount + 255) / 256, e->sm_count * 8), 256, 0, st>>>(e->dist.p, s0, renderCount, e->freq.p);
+        k_exclusive_scan_single_block<<<1, 1024, 0, st>>>(e->freq.p, distanceMapRange);
+        CU(cudaMemcpyAsync(frequencies, e->freq.p, (size_t)distanceMapRange * 4, cudaMemcpyDeviceToHost, st));
+    }
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    return GS_OK;
+}
+
+extern "C" void sortIndexes(unsigned int *indexes, void *centers, void *precomputedDistances, int *mappedDistances,
+                            unsigned int *frequencies, float *modelViewProj, unsigned int *indexesOut, unsigned int *sceneIndexes,
+                            float *transforms, unsigned int distanceMapRange, unsigned int sortCount, unsigned int renderCount,
+                            unsigned int splatCount, bool usePrecomputedDistances, bool useIntegerSort, bool dynamicMode) {
+    (void)gs_sort_indexes(indexes, centers, precomputedDistances, mappedDistances, frequencies, modelViewProj, indexesOut, sceneIndexes,
+                          transforms, distanceMapRange, sortCount, renderCount, splatCount, usePrecomputedDistances, useIntegerSort, dynamicMode);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// D1: SplatMesh.computeDistancesOnGPU.  mvp is f64 because three.js Matrix4 elements are JS numbers and the integer rows
+// are Math.round(element * 1000) on those doubles (SplatMesh.js:2057-2064).
+extern "C" int gs_compute_distances(gs_engine *e, const double *mvp, const double *scene_transforms, uint32_t count, void *out) {
+    int rc = check_engine(e);
+    if (rc) return rc;
+    if (!mvp || !out) return fail(GS_ERR_BAD_ARG, "gs_compute_distances: null argument");
+    if (count > e->uploaded_splats) return fail(GS_ERR_CAPACITY, "count %u > uploaded splats %u", count, e->uploaded_splats);
+    const bool integer = e->cfg.integer_based_sort, dyn = e->cfg.dynamic_mode;
+    if (dyn && !scene_transforms) return fail(GS_ERR_BAD_ARG, "dynamic mode needs scene_transforms (f64[16*32])");
+    std::vector<int32_t> irows(4 * GS_MAX_SCENES, 0);
+    std::vector<float> frows(4 * GS_MAX_SCENES, 0.f);
+    auto jsround = [](double v) { return (int32_t)std::floor(v + 0.5); }; // Math.round
+    for (int s = 0; s < (dyn ? GS_MAX_SCENES : 1); ++s) {
+        double m[16];
+        if (dyn) { // tempMatrix = mvp * transform_s (three.js Matrix4.multiply, f64)   SplatMesh.js:1722-1724
+            const double *t = scene_transforms + 16 * s;
+            for (int c = 0; c < 4; ++c)
+                for (int r = 0; r < 4; ++r) m[4 * c + r] = mvp[r] * t[4 * c] + mvp[4 + r] * t[4 * c + 1] + mvp[8 + r] * t[4 * c + 2] + mvp[12 + r] * t[4 * c + 3];
+        } else memcpy(m, mvp, sizeof(m));
+        for (int k = 0; k < 4; ++k) {
+            irows[4 * s + k] = jsround(m[2 + 4 * k] * 1000.0);
+            frows[4 * s + k] = (float)m[2 + 4 * k];
+        }
+    }
+    DevBuf<int32_t> d_ir; DevBuf<float> d_fr;
+    if ((rc = d_ir.ensure(irows.size())) || (rc = d_fr.ensure(frows.size()))) return rc;
+    cudaStream_t st = e->stream;
+    CU(cudaMemcpyAsync(d_ir.p, irows.data(), irows.size() * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_fr.p, frows.data(), frows.size() * 4, cudaMemcpyHostToDevice, st));
+    if ((rc = e->precomputed.ensure(e->cfg.max_splat_count))) return rc;
+    const int blocks = std::max(1, (int)std::min<uint32_t>((count + 255) / 256, e->sm_count * 8));
+    if (integer && dyn) k_distances_splat_order<true, true><<<blocks, 256, 0, st>>>(e->centers.p, e->scene_idx.p, d_ir.p, d_fr.p, count, e->precomputed.p);
+    else if (integer) k_distances_splat_order<true, false><<<blocks, 256, 0, st>>>(e->centers.p, e->scene_idx.p, d_ir.p, d_fr.p, count, e->precomputed.p);
+    else if (dyn) k_distances_splat_order<false, true><<<blocks, 256, 0, st>>>(e->centers.p, e->scene_idx.p, d_ir.p, d_fr.p, count, e->precomputed.p);
+    else k_distances_splat_order<false, false><<<blocks, 256, 0, st>>>(e->centers.p, e->scene_idx.p, d_ir.p, d_fr.p, count, e->precomputed.p);
+    CU(cudaMemcpyAsync(out, e->precomputed.p, (size_t)count * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    d_ir.release(); d_fr.release();
+    return GS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int gs_upload_splat_data(gs_engine *e, const gs_splat_data *d) {
+    int rc = check_engine(e);
+    if (rc) return rc;
+    if (!d) return fail(GS_ERR_BAD_ARG, "gs_upload_splat_data: null");
+    rc = raster_upload(e->rs, e->cfg, *d, e->stream);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(e->stream));
+    return GS_OK;
+}
+
+static int render_on_device(gs_engine *e, const gs_uniforms *u, const gs_render_params *p, const uint32_t *d_order) {
+    cudaStream_t st = e->stream;
+    CU(cudaEventRecord(e->ev[EV_R0], st));
+    int rc = raster_render(e->rs, e->cfg, *u, *p, d_order, st, e->ev[EV_PROJECT], e->ev[EV_BIN], e->tm);
+    if (rc) return rc;
+    CU(cudaEventRecord(e->ev[EV_R1], st));
+    CU(cudaGetLastError());
+    return GS_OK;
+}
+
+static size_t frame_bytes(const gs_render_params *p) { return (size_t)p->width * p->height * (p->frame_format == GS_FRAME_RGBA8 ? 4 : 16); }
+
+static int finish_render(gs_engine *e, const gs_render_params *p, void *frame_out) {
+    cudaStream_t st = e->stream;
+    CU(cudaEventRecord(e->ev[EV_D2H0], st));
+    if (frame_out) CU(cudaMemcpyAsync(frame_out, raster_frame_ptr(e->rs, p->frame_format), frame_bytes(p), cudaMemcpyDeviceToHost, st));
+    CU(cudaEventRecord(e->ev[EV_D2H1], st));
+    CU(cudaMemcpyAsync(e->h_ctl.p + 16, e->rs.rctl.p, sizeof(RasterControl), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    cudaEventElapsedTime(&e->tm.project_ms, e->ev[EV_R0], e->ev[EV_PROJECT]);
+    cudaEventElapsedTime(&e->tm.bin_ms, e->ev[EV_PROJECT], e->ev[EV_BIN]);
+    cudaEventElapsedTime(&e->tm.blend_ms, e->ev[EV_BIN], e->ev[EV_R1]);
+    cudaEventElapsedTime(&e->tm.render_total_ms, e->ev[EV_R0], e->ev[EV_R1]);
+    cudaEventElapsedTime(&e->tm.d2h_ms, e->ev[EV_D2H0], e->ev[EV_D2H1]);
+    RasterControl rc;
+    memcpy(&rc, e->h_ctl.p + 16, sizeof(rc));
+    e->tm.tile_instances = rc.total_instances;
+    e->tm.visible_splats = rc.visible;
+    if (rc.overflow) return fail(GS_ERR_CAPACITY, "tile-instance buffer overflow: %llu instances needed, capacity %llu (raise GS_INSTANCE_FACTOR)",
+                                 (unsigned long long)rc.total_instances, (unsigned long long)e->rs.instance_capacity);
+    return GS_OK;
+}
+
+static int stage_order(gs_engine *e, const gs_render_params *p, const uint32_t **d_order) {
+    *d_order = nullptr;
+    if (p->render_count > e->cfg.max_splat_count) return fail(GS_ERR_CAPACITY, "render_count %u > max_splat_count %u", p->render_count, e->cfg.max_splat_count);
+    if (p->sorted_indexes_dev) *d_order = p->sorted_indexes_dev;
+    else if (p->sorted_indexes) { // SplatMesh.updateRenderIndexes: upload of the splatIndex attribute
+        CU(cudaMemcpyAsync(e->sorted.p, p->sorted_indexes, (size_t)p->render_count * 4, cudaMemcpyHostToDevice, e->stream));
+        *d_order = e->sorted.p;
+        e->have_sorted = true;
+        e->last_render_count = p->render_count;
+    } else {
+        if (!e->have_sorted || e->last_render_count < p->render_count) return fail(GS_ERR_NOT_READY, "gs_render without sorted indexes: call gs_sort first or pass sorted_indexes");
+        *d_order = e->sorted.p;
+    }
+    return GS_OK;
+}
+
+extern "C" int gs_render(gs_engine *e, const gs_uniforms *u, const gs_render_params *p, void *frame_out) {
+    int rc = check_engine(e);
+    if (rc) return rc;
+    if (!u || !p) return fail(GS_ERR_BAD_ARG, "gs_render: null argument");
+    const uint32_t *d_order = nullptr;
+    if ((rc = stage_order(e, p, &d_order))) return rc;
+    if ((rc = render_on_device(e, u, p, d_order))) return rc;
+    return finish_render(e, p, frame_out);
+}
+
+extern "C" int gs_frame(gs_engine *e, const gs_sort_params *s, const gs_uniforms *u, const gs_render_params *p, uint32_t *sorted_out, void *frame_out) {
+    int rc = check_engine(e);
+    if (rc) return rc;
+    if (!s || !u || !p) return fail(GS_ERR_BAD_ARG, "gs_frame: null argument");
+    gs_sort_params q = *s;
+    q.render_count = std::min(q.render_count, e->uploaded_splats);
+    q.sort_count = std::min(q.sort_count, e->uploaded_splats);
+    const uint32_t *d_idx = nullptr;
+    if ((rc = stage_sort_inputs(e, &q, &d_idx))) return rc;
+    if ((rc = sort_on_device(e, d_idx, q.model_view_proj, q.sort_count, q.render_count, q.use_precomputed_distances != 0, false))) return rc;
+    const uint32_t sort_launches = e->tm.kernel_launches;
+    gs_render_params rp = *p;
+    rp.sorted_indexes = nullptr; rp.sorted_indexes_dev = nullptr;
+    rp.render_count = std::min(rp.render_count, q.render_count);
+    if ((rc = render_on_device(e, u, &rp, e->sorted.p))) return rc;
+    e->tm.kernel_launches += sort_launches;
+    if (sorted_out && q.render_count) CU(cudaMemcpyAsync(sorted_out, e->sorted.p, (size_t)q.render_count * 4, cudaMemcpyDeviceToHost, e->stream));
+    int rc2 = finish_render(e, &rp, frame_out);
+    rc = finish_sort(e, nullptr);
+    cudaEventElapsedTime(&e->tm.h2d_ms, e->ev[EV_H2D0], e->ev[EV_H2D1]);
+    return rc ? rc : rc2;
+}
+
+extern "C" int gs_read_projected(gs_engine *e, gs_projected_splat *out, uint32_t count) {
+    int rc = check_engine(e);
+    if (rc) return rc;
+    if (!out) return fail(GS_ERR_BAD_ARG, "gs_read_projected: null");
+    rc = raster_read_projected(e->rs, out, count, e->stream);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(e->stream));
+    return GS_OK;
+}
+
+extern "C" int gs_buffer_dev(gs_engine *e, int id, void **ptr, size_t *bytes) {
+    if (!e || !ptr) return fail(GS_ERR_BAD_ARG, "gs_buffer_dev: null");
+    size_t b = 0;
+    switch (id) {
+        case GS_BUF_SORTED_INDEXES: *ptr = e->sorted.p; b = e->sorted.n * 4; break;
+        case GS_BUF_FRAME: *ptr = raster_frame_ptr(e->rs, e->rs.last_format); b = e->rs.last_frame_bytes; break;
+        case GS_BUF_CENTERS: *ptr = e->centers.p; b = e->centers.n * 16; break;
+        case GS_BUF_DISTANCES: *ptr = e->dist.p; b = e->dist.n * 4; break;
+        case GS_BUF_SPLAT_RECORDS: *ptr = e->rs.records.p; b = e->rs.records.n * sizeof(SplatRecord); break;
+        case GS_BUF_INDEXES_TO_SORT: *ptr = e->indexes.p; b = e->indexes.n * 4; break;
+        default: return fail(GS_ERR_BAD_ARG, "unknown buffer id %d", id);
+    }
+    if (bytes) *bytes = b;
+    return GS_OK;
+}
+extern "C" int gs_stream(gs_engine *e, void **s) {
+    if (!e || !s) return fail(GS_ERR_BAD_ARG, "gs_stream: null");
+    *s = (void *)e->stream;
+    return GS_OK;
+}
+extern "C" int gs_synchronize(gs_engine *e) {
+    int rc = check_engine(e);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(e->stream));
+    return GS_OK;
+}
+extern "C" int gs_last_timings(gs_engine *e, gs_timings *t) {
+    if (!e || !t) return fail(GS_ERR_BAD_ARG, "gs_last_timings: null");
+    *t = e->tm;
+    return GS_OK;
+}
+
+// pinned host memory for callers (the SharedArrayBuffer views a shared-memory worker hands out, SortWorker.js:180-191)
+extern "C" int gs_host_alloc(void **ptr, size_t bytes) {
+    if (!ptr) return fail(GS_ERR_BAD_ARG, "gs_host_alloc: null");
+    if (gs_device_count() <= 0) return fail(GS_ERR_NO_DEVICE, "no CUDA device");
+    CU(cudaHostAlloc(ptr, std::max<size_t>(bytes, 1), cudaHostAllocDefault));
+    return GS_OK;
+}
+extern "C" int gs_host_free(void *ptr) {
+    if (ptr) CU(cudaFreeHost(ptr));
+    return GS_OK;
+}

@@ -1,0 +1,783 @@
+// raster_kernels.cuh -- tile-binned forward rasteriser (sm_100a) replacing the reference's WebGL path:
+//   k_project     : vertex shader, once per splat (not x4)    SplatMaterial.js:112-341, SplatMaterial3D.js:83-216
+//   k_tile_count  : per draw-rank tile counts + exclusive scan (decoupled look-back)
+//   k_tile_emit   : (tile, splat) instances in DRAW order + radix digit histograms
+//   k_radix_pass  : stable sort of the instances by tile id (sort_kernels.cuh) -> per-tile lists in draw order
+//   k_blend       : fragment shader + blend, front-to-back      SplatMaterial3D.js:234-252, :65-75
+// Draw order is the reference's (sorted_indexes[0] first = farthest).  We composite front-to-back over the REVERSED
+// list with a transmittance accumulator, which is algebraically the same "over" chain.
+#pragma once
+#include "common.cuh"
+#include "sort_kernels.cuh"
+#include "../../include/gsplat_b200.h"
+#include <cuda_fp16.h>
+
+namespace gs {
+
+constexpr int kTile = 16;              // tile edge in pixels
+constexpr int kTileShift = 4;
+constexpr float kTransmittanceCutoff = 1.0f / 4096.0f; // stop compositing a pixel below this (stated deviation)
+
+struct __align__(16) SplatRecord {     // 48 bytes, read as 3 x 16 B
+    float cx, cy;                      // quad centre in pixels, GL window coordinates (y up)
+    float g1x, g1y;                    // g1 = B1 / |B1|^2 : u = dot(d, g1) is the quad-local coordinate in [-1,1]
+    float g2x, g2y;                    // g2 = B2 / |B2|^2
+    float ndc_z, a;
+    float r, g, b;
+    uint32_t valid;
+};
+
+struct RasterControl {
+    unsigned long long total_instances;
+    uint32_t overflow;
+    uint32_t visible;
+    uint32_t scan_ticket;
+    uint32_t pad[3];
+};
+
+struct ProjParams {
+    float mv[16], proj[16];
+    float cam[3];
+    float focal[2], viewport[2];
+    float inv_focal_adj, ortho_zoom;
+    int orthographic;
+    float splat_scale;
+    int point_cloud, sh_degree, antialiased;
+    float kernel2d, max_size;
+    int fade_in_complete;
+    float scene_center[3], fade_start;
+    int dynamic, optional_effects, scene_count;
+    int tiles_x, tiles_y;
+    uint32_t rank, world;
+    int width, height;
+};
+
+struct DynamicUniforms {               // only read in dynamic / optional-effects / 8-bit SH modes
+    float view[16];
+    float transforms[16 * GS_MAX_SCENES_DEV];
+    float sh8_min[GS_MAX_SCENES_DEV], sh8_max[GS_MAX_SCENES_DEV];
+    float opacity[GS_MAX_SCENES_DEV];
+    int visibility[GS_MAX_SCENES_DEV];
+};
+
+// number of tile rows in [ty0, ty1] owned by `rank` under row-interleaved ownership (row % world == rank)
+__host__ __device__ __forceinline__ int owned_rows(int ty0, int ty1, uint32_t rank, uint32_t world) {
+    if (ty1 < ty0) return 0;
+    if (world == 1) return ty1 - ty0 + 1;
+    // first owned row >= ty0
+    int r = ty0 + (int)(((int)rank - (ty0 % (int)world) + (int)world) % (int)world);
+    if (r > ty1) return 0;
+    return (ty1 - r) / (int)world + 1;
+}
+
+__device__ __forceinline__ void mat4_mul_dev(const float *a, const float *b, float *o) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+            o[4 * c + r] = a[r] * b[4 * c] + a[4 + r] * b[4 * c + 1] + a[8 + r] * b[4 * c + 2] + a[12 + r] * b[4 * c + 3];
+}
+__device__ inline void mat4_inverse_dev(const float *m, float *o) {
+    float inv[16];
+    inv[0] = m[5] * m[10] * m[15] - m[5] * m[11] * m[14] - m[9] * m[6] * m[15] + m[9] * m[7] * m[14] + m[13] * m[6] * m[11] - m[13] * m[7] * m[10];
+    inv[4] = -m[4] * m[10] * m[15] + m[4] * m[11] * m[14] + m[8] * m[6] * m[15] - m[8] * m[7] * m[14] - m[12] * m[6] * m[11] + m[12] * m[7] * m[10];
+    inv[8] = m[4] * m[9] * m[15] - m[4] * m[11] * m[13] - m[8] * m[5] * m[15] + m[8] * m[7] * m[13] + m[12] * m[5] * m[11] - m[12] * m[7] * m[9];
+    inv[12] = -m[4] * m[9] * m[14] + m[4] * m[10] * m[13] + m[8] * m[5] * m[14] - m[8] * m[6] * m[13] - m[12] * m[5] * m[10] + m[12] * m[6] * m[9];
+    inv[1] = -m[1] * m[10] * m[15] + m[1] * m[11] * m[14] + m[9] * m[2] * m[15] - m[9] * m[3] * m[14] - m[13] * m[2] * m[11] + m[13] * m[3] * m[10];
+    inv[5] = m[0] * m[10] * m[15] - m[0] * m[11] * m[14] - m[8] * m[2] * m[15] + m[8] * m[3] * m[14] + m[12] * m[2] * m[11] - m[12] * m[3] * m[10];
+    inv[9] = -m[0] * m[9] * m[15] + m[0] * m[11] * m[13] + m[8] * m[1] * m[15] - m[8] * m[3] * m[13] - m[12] * m[1] * m[11] + m[12] * m[3] * m[9];
+    inv[13] = m[0] * m[9] * m[14] - m[0] * m[10] * m[13] - m[8] * m[1] * m[14] + m[8] * m[2] * m[13] + m[12] * m[1] * m[10] - m[12] * m[2] * m[9];
+    inv[2] = m[1] * m[6] * m[15] - m[1] * m[7] * m[14] - m[5] * m[2] * m[15] + m[5] * m[3] * m[14] + m[13] * m[2] * m[7] - m[13] * m[3] * m[6];
+    inv[6] = -m[0] * m[6] * m[15] + m[0] * m[7] * m[14] + m[4] * m[2] * m[15] - m[4] * m[3] * m[14] - m[12] * m[2] * m[7] + m[12] * m[3] * m[6];
+    inv[10] = m[0] * m[5] * m[15] - m[0] * m[7] * m[13] - m[4] * m[1] * m[15] + m[4] * m[3] * m[13] + m[12] * m[1] * m[7] - m[12] * m[3] * m[5];
+    inv[14] = -m[0] * m[5] * m[14] + m[0] * m[6] * m[13] + m[4] * m[1] * m[14] - m[4] * m[2] * m[13] - m[12] * m[1] * m[6] + m[12] * m[2] * m[5];
+    inv[3] = -m[1] * m[6] * m[11] + m[1] * m[7] * m[10] + m[5] * m[2] * m[11] - m[5] * m[3] * m[10] - m[9] * m[2] * m[7] + m[9] * m[3] * m[6];
+    inv[7] = m[0] * m[6] * m[11] - m[0] * m[7] * m[10] - m[4] * m[2] * m[11] + m[4] * m[3] * m[10] + m[8] * m[2] * m[7] - m[8] * m[3] * m[6];
+    inv[11] = -m[0] * m[5] * m[11] + m[0] * m[7] * m[9] + m[4] * m[1] * m[11] - m[4] * m[3] * m[9] - m[8] * m[1] * m[7] + m[8] * m[3] * m[5];
+    inv[15] = m[0] * m[5] * m[10] - m[0] * m[6] * m[9] - m[4] * m[1] * m[10] + m[4] * m[2] * m[9] + m[8] * m[1] * m[6] - m[8] * m[2] * m[5];
+    const float det = m[0] * inv[0] + m[1] * inv[4] + m[2] * inv[8] + m[3] * inv[12];
+    const float id = 1.0f / det;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) o[i] = inv[i] * id;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Projection: one thread per splat, splat order (coalesced 16 B + 24 B + SH loads).
+//   COVF16: covariances stored as 6 halfs;  SHFMT: gs_sh_format
+constexpr int kProjThreads = 128;
+
+template <bool COVF16, int SHFMT>
+__global__ void __launch_bounds__(kProjThreads)
+k_project(const uint4 *__restrict__ cc, const void *__restrict__ cov, const void *__restrict__ sh, int sh_data_degree,
+          const uint32_t *__restrict__ scene_idx, const DynamicUniforms *__restrict__ dyn, ProjParams P, uint32_t count,
+          SplatRecord *__restrict__ rec, ushort4 *__restrict__ rects, RasterControl *rctl) {
+    const uint32_t s = blockIdx.x * kProjThreads + threadIdx.x;
+    uint32_t visible = 0;
+    if (s < count) {
+        SplatRecord o;
+        o.cx = o.cy = o.g1x = o.g1y = o.g2x = o.g2y = o.ndc_z = o.a = o.r = o.g = o.b = 0.f;
+        o.valid = 0;
+        ushort4 rect = make_ushort4(1, 1, 0, 0); // empty
+        const int4 c4 = ld_nc_v4(cc + s);
+        const float cx = __int_as_float(c4.y), cy = __int_as_float(c4.z), cz = __int_as_float(c4.w);
+        uint32_t scene = 0;
+        if (P.scene_count > 1 && scene_idx) scene = scene_idx[s] & (GS_MAX_SCENES_DEV - 1);
+        bool alive = true;
+        if (P.optional_effects) alive = !(dyn->opacity[scene] <= 0.01f || dyn->visibility[scene] == 0);
+
+        float mvd[16];
+        const float *mv = P.mv;
+        if (P.dynamic) { mat4_mul_dev(dyn->view, dyn->transforms + 16 * scene, mvd); mv = mvd; }
+        float view[4], clip[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) view[r] = mv[r] * cx + mv[4 + r] * cy + mv[8 + r] * cz + mv[12 + r];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) clip[r] = P.proj[r] * view[0] + P.proj[4 + r] * view[1] + P.proj[8 + r] * view[2] + P.proj[12 + r] * view[3];
+        const float lim = 1.2f * clip[3];
+        if (clip[2] < -lim || clip[0] < -lim || clip[0] > lim || clip[1] < -lim || clip[1] > lim) alive = false;
+        if (alive) {
+            const float iw = 1.0f / clip[3];
+            const float ndcx = clip[0] * iw, ndcy = clip[1] * iw, ndcz = clip[2] * iw;
+            const uint32_t packed = (uint32_t)c4.x;
+            float col[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) col[k] = (float)((packed >> (8 * k)) & 255u) * (1.0f / 255.0f);
+
+            if (SHFMT != GS_SH_NONE && sh_data_degree >= 1 && P.sh_degree >= 1) {
+                const int ncomp = sh_data_degree >= 2 ? 24 : 9;
+                float shv[24];
+                const int nuse = (sh_data_degree >= 2 && P.sh_degree >= 2) ? 24 : 9;
+                if (SHFMT == GS_SH_F16) {
+                    const __half *h = (const __half *)sh + (size_t)s * ncomp;
+                    if (ncomp == 24) {
+                        const uint4 *h4 = (const uint4 *)h;
+#pragma unroll
+                        for (int q = 0; q < 3; ++q) {
+                            const int4 v = ld_nc_v4(h4 + q);
+                            const uint32_t w[4] = {(uint32_t)v.x, (uint32_t)v.y, (uint32_t)v.z, (uint32_t)v.w};
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const __half2 hh = *reinterpret_cast<const __half2 *>(&w[k]);
+                                shv[q * 8 + 2 * k] = __low2float(hh);
+                                shv[q * 8 + 2 * k + 1] = __high2float(hh);
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 9; ++k) shv[k] = __half2float(h[k]);
+                    }
+                } else if (SHFMT == GS_SH_U8) {
+                    const unsigned char *b = (const unsigned char *)sh + (size_t)s * ncomp;
+                    const float lo = dyn->sh8_min[scene], range = dyn->sh8_max[scene] - dyn->sh8_min[scene];
+                    for (int k = 0; k < nuse; ++k) shv[k] = ((float)b[k] / 255.0f) * range + lo;
+                } else {
+                    const float *f = (const float *)sh + (size_t)s * ncomp;
+                    for (int k = 0; k < nuse; ++k) shv[k] = f[k];
+                }
+                float camx = P.cam[0], camy = P.cam[1], camz = P.cam[2];
+                if (P.dynamic) {
+                    float inv[16];
+                    mat4_inverse_dev(dyn->transforms + 16 * scene, inv);
+                    const float tx = inv[0] * camx + inv[4] * camy + inv[8] * camz + inv[12];
+                    const float ty = inv[1] * camx + inv[5] * camy + inv[9] * camz + inv[13];
+                    const float tz = inv[2] * camx + inv[6] * camy + inv[10] * camz + inv[14];
+                    camx = tx; camy = ty; camz = tz;
+                }
+                float dx = cx - camx, dy = cy - camy, dz = cz - camz;
+                const float il = rsqrtf(dx * dx + dy * dy + dz * dz);
+                const float x = dx * il, y = dy * il, z = dz * il;
+                const float C1 = 0.4886025119029199f;
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) col[ch] += C1 * (-shv[ch] * y + shv[3 + ch] * z - shv[6 + ch] * x);
+                if (nuse == 24) {
+                    const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+#pragma unroll
+                    for (int ch = 0; ch < 3; ++ch)
+                        col[ch] += (1.0925484f * xy) * shv[9 + ch] + (-1.0925484f * yz) * shv[12 + ch] +
+                                   (0.3153916f * (2.0f * zz - xx - yy)) * shv[15 + ch] + (-1.0925484f * xz) * shv[18 + ch] +
+                                   (0.5462742f * (xx - yy)) * shv[21 + ch];
+                }
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) col[ch] = __saturatef(col[ch]);
+            }
+
+            float V[6];
+            if (COVF16) {
+                const __half *h = (const __half *)cov + (size_t)s * 6;
+#pragma unroll
+                for (int k = 0; k < 6; ++k) V[k] = __half2float(h[k]);
+            } else {
+                const float2 *f2 = (const float2 *)cov + (size_t)s * 3;
+                const float2 a0 = f2[0], a1 = f2[1], a2 = f2[2];
+                V[0] = a0.x; V[1] = a0.y; V[2] = a1.x; V[3] = a1.y; V[4] = a2.x; V[5] = a2.y;
+            }
+            float j00, j02, j11, j12;
+            if (P.orthographic == 1) { j00 = P.ortho_zoom; j11 = P.ortho_zoom; j02 = 0.f; j12 = 0.f; }
+            else {
+                const float iz = 1.0f / view[2], sc = iz * iz;
+                j00 = P.focal[0] * iz; j11 = P.focal[1] * iz;
+                j02 = -(P.focal[0] * view[0]) * sc; j12 = -(P.focal[1] * view[1]) * sc;
+            }
+            float T0[3], T1[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const float w0 = mv[4 * k + 0], w1 = mv[4 * k + 1], w2 = mv[4 * k + 2];
+                T0[k] = w0 * j00 + w2 * j02;
+                T1[k] = w1 * j11 + w2 * j12;
+            }
+            const float VT0x = V[0] * T0[0] + V[1] * T0[1] + V[2] * T0[2];
+            const float VT0y = V[1] * T0[0] + V[3] * T0[1] + V[4] * T0[2];
+            const float VT0z = V[2] * T0[0] + V[4] * T0[1] + V[5] * T0[2];
+            const float VT1x = V[0] * T1[0] + V[1] * T1[1] + V[2] * T1[2];
+            const float VT1y = V[1] * T1[0] + V[3] * T1[1] + V[4] * T1[2];
+            const float VT1z = V[2] * T1[0] + V[4] * T1[1] + V[5] * T1[2];
+            float a = T0[0] * VT0x + T0[1] * VT0y + T0[2] * VT0z;
+            const float b = T0[0] * VT1x + T0[1] * VT1y + T0[2] * VT1z;
+            float d = T1[0] * VT1x + T1[1] * VT1y + T1[2] * VT1z;
+            if (P.antialiased) {
+                const float det0 = a * d - b * b;
+                a += P.kernel2d; d += P.kernel2d;
+                const float det1 = a * d - b * b;
+                col[3] *= sqrtf(fmaxf(det0 / det1, 0.0f));
+                if (col[3] < 1.0f / 255.0f) alive = false;
+            } else { a += P.kernel2d; d += P.kernel2d; }
+            const float D = a * d - b * b, half_tr = 0.5f * (a + d);
+            const float term2 = sqrtf(fmaxf(0.1f, half_tr * half_tr - D));
+            float l1 = half_tr + term2, l2 = half_tr - term2;
+            if (P.point_cloud == 1) l1 = l2 = 0.2f;
+            if (l2 <= 0.0f) alive = false;
+            if (alive) {
+                float ex = b, ey = l1 - a;
+                const float en = rsqrtf(ex * ex + ey * ey);
+                ex *= en; ey *= en;
+                const float sqrt8 = 2.8284271247461903f;
+                const float s1 = P.splat_scale * fminf(sqrt8 * sqrtf(l1), P.max_size) * P.inv_focal_adj;
+                const float s2 = P.splat_scale * fminf(sqrt8 * sqrtf(l2), P.max_size) * P.inv_focal_adj;
+                if (P.optional_effects) col[3] *= dyn->opacity[scene];
+                if (!P.fade_in_complete) {
+                    const float qx = cx - P.scene_center[0], qy = cy - P.scene_center[1], qz = cz - P.scene_center[2];
+                    const float dist = sqrtf(qx * qx + qy * qy + qz * qz);
+                    const float st = dist >= P.fade_start ? 1.0f : 0.0f;
+                    col[3] *= (1.0f - st) + (1.0f - __saturatef((dist - P.fade_start) / 0.75f)) * st;
+                }
+                // B1 = e1*s1, B2 = (e1.y,-e1.x)*s2 ; g = B/|B|^2 = e/s
+                const float is1 = 1.0f / s1, is2 = 1.0f / s2;
+                o.cx = (ndcx + 1.0f) * 0.5f * P.viewport[0];
+                o.cy = (ndcy + 1.0f) * 0.5f * P.viewport[1];
+                o.g1x = ex * is1; o.g1y = ey * is1;
+                o.g2x = ey * is2; o.g2y = -ex * is2;
+                o.ndc_z = ndcz; o.a = col[3];
+                o.r = col[0]; o.g = col[1]; o.b = col[2];
+                const bool in_depth = (ndcz >= -1.0f && ndcz <= 1.0f) && isfinite(s1) && isfinite(s2) && s1 > 0.f && s2 > 0.f;
+                o.valid = in_depth ? 1u : 0u;
+                if (in_depth) {
+                    // tight AABB of the ellipse u^2+w^2<=1 : half extents sqrt(B1x^2+B2x^2), sqrt(B1y^2+B2y^2)
+                    const float b1x = ex * s1, b1y = ey * s1, b2x = ey * s2, b2y = -ex * s2;
+                    const float hx = sqrtf(b1x * b1x + b2x * b2x) * 1.0005f + 0.01f;
+                    const float hy = sqrtf(b1y * b1y + b2y * b2y) * 1.0005f + 0.01f;
+                    // pixel centres (px+0.5) inside [c-h, c+h]
+                    const float fx0 = ceilf(o.cx - hx - 0.5f), fx1 = floorf(o.cx + hx - 0.5f);
+                    const float fy0 = ceilf(o.cy - hy - 0.5f), fy1 = floorf(o.cy + hy - 0.5f);
+                    const float W1 = (float)(P.width - 1), H1 = (float)(P.height - 1);
+                    if (fx1 >= 0.f && fy1 >= 0.f && fx0 <= W1 && fy0 <= H1 && fx0 <= fx1 && fy0 <= fy1) {
+                        const int px0 = (int)fmaxf(fx0, 0.f), px1 = (int)fminf(fx1, W1);
+                        const int py0 = (int)fmaxf(fy0, 0.f), py1 = (int)fminf(fy1, H1);
+                        rect = make_ushort4((unsigned short)(px0 >> kTileShift), (unsigned short)(py0 >> kTileShift),
+                                            (unsigned short)(px1 >> kTileShift), (unsigned short)(py1 >> kTileShift));
+                        visible = 1;
+                    }
+                }
+            }
+        }
+        float4 *dst = reinterpret_cast<float4 *>(rec + s);
+        dst[0] = make_float4(o.cx, o.cy, o.g1x, o.g1y);
+        dst[1] = make_float4(o.g2x, o.g2y, o.ndc_z, o.a);
+        dst[2] = make_float4(o.r, o.g, o.b, __uint_as_float(o.valid));
+        rects[s] = rect;
+    }
+    const uint32_t nvis = __popc(__ballot_sync(0xffffffffu, visible));
+    if ((threadIdx.x & 31) == 0 && nvis) atomicAdd(&rctl->visible, nvis);
+}
+
+__device__ __forceinline__ uint32_t rect_instances(ushort4 r, uint32_t rank, uint32_t world) {
+    if (r.z < r.x || r.w < r.y) return 0;
+    return (uint32_t)(r.z - r.x + 1) * (uint32_t)owned_rows(r.y, r.w, rank, world);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Draw-rank p (0 = nearest, i.e. LAST in the reference's draw order) -> exclusive offset of its tile instances.
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 4;
+constexpr int kScanTile = kScanThreads * kScanItems;
+constexpr unsigned long long kScanAggregate = 1ull << 62, kScanPrefix = 2ull << 62, kScanFlags = 3ull << 62;
+
+__global__ void __launch_bounds__(kScanThreads)
+k_tile_count(const uint32_t *__restrict__ order, uint32_t render_count, const ushort4 *__restrict__ rects, uint32_t rank,
+             uint32_t world, uint32_t *__restrict__ offsets, unsigned long long *lookback, RasterControl *rctl,
+             unsigned long long capacity) {
+    __shared__ uint32_t s_scan[40];
+    __shared__ uint32_t s_tile;
+    __shared__ unsigned long long s_prefix;
+    if (threadIdx.x == 0) s_tile = atomicAdd(&rctl->scan_ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint64_t base = (uint64_t)tile * kScanTile + (uint64_t)threadIdx.x * kScanItems;
+    uint32_t cnt[kScanItems], mine = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        const uint64_t p = base + k;
+        cnt[k] = 0;
+        if (p < render_count) {
+            const uint32_t s = ld_nc_u32(order + (render_count - 1u - p));
+            cnt[k] = rect_instances(rects[s], rank, world);
+        }
+        mine += cnt[k];
+    }
+    uint32_t total;
+    const uint32_t ex = block_exclusive_scan<kScanThreads>(mine, s_scan, total);
+    if (threadIdx.x == 0) {
+        unsigned long long excl = 0;
+        volatile unsigned long long *lb = lookback;
+        if (tile == 0) {
+            lb[0] = (unsigned long long)total | kScanPrefix;
+        } else {
+            lb[tile] = (unsigned long long)total | kScanAggregate;
+            __threadfence();
+            int64_t t = (int64_t)tile - 1;
+            while (true) {
+                const unsigned long long v = lb[t];
+                const unsigned long long f = v & kScanFlags;
+                if (f == 0) continue;
+                excl += v & ~kScanFlags;
+                if (f == kScanPrefix) break;
+                --t;
+            }
+            lb[tile] = (excl + total) | kScanPrefix;
+        }
+        s_prefix = excl;
+        if ((uint64_t)(tile + 1) * kScanTile >= render_count) { // last tile: publish the grand total
+            rctl->total_instances = excl + total;
+            if (excl + total > capacity) rctl->overflow = 1;
+        }
+    }
+    __syncthreads();
+    const unsigned long long pre = s_prefix + ex;
+    uint32_t run = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        const uint64_t p = base + k;
+        if (p < render_count) offsets[p] = (uint32_t)min(pre + run, (unsigned long long)0xffffffffu);
+        run += cnt[k];
+    }
+}
+
+// One warp per 32 draw ranks; lanes cooperate on large rects.  Writes key = local tile id, val = splat id, and the
+// per-pass digit histograms for the tile sort.
+constexpr int kEmitThreads = 256;
+
+template <typename KeyT>
+__global__ void __launch_bounds__(kEmitThreads)
+k_tile_emit(const uint32_t *__restrict__ order, uint32_t render_count, const ushort4 *__restrict__ rects,
+            const uint32_t *__restrict__ offsets, uint32_t rank, uint32_t world, int tiles_x, KeyT *__restrict__ keys,
+            uint32_t *__restrict__ vals, unsigned long long capacity, PassPlan plan, SortControl *ctl) {
+    __shared__ uint32_t s_hist[4][kRadix];
+    for (int i = threadIdx.x; i < 4 * kRadix; i += kEmitThreads) (&s_hist[0][0])[i] = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp_global = ((uint64_t)blockIdx.x * kEmitThreads + threadIdx.x) >> 5;
+    const uint64_t nwarps = ((uint64_t)gridDim.x * kEmitThreads) >> 5;
+    for (uint64_t p0 = warp_global * 32; p0 < render_count; p0 += nwarps * 32) {
+        const uint64_t p = p0 + lane;
+        uint32_t s = 0, off = 0, n = 0;
+        ushort4 r = make_ushort4(1, 1, 0, 0);
+        if (p < render_count) {
+            s = ld_nc_u32(order + (render_count - 1u - p));
+            r = rects[s];
+            n = rect_instances(r, rank, world);
+            off = offsets[p];
+        }
+        // small rects: each lane writes its own; large rects: the warp shares the work
+        const uint32_t big = __ballot_sync(0xffffffffu, n > 32u);
+        if (n > 0 && n <= 32u && (unsigned long long)off + n <= capacity) {
+            uint32_t w = off;
+            const int rw = r.z - r.x + 1;
+            for (int ty = r.y; ty <= r.w; ++ty) {
+                if (world > 1 && (uint32_t)ty % world != rank) continue;
+                const uint32_t row_base = (uint32_t)(ty / (int)world) * (uint32_t)tiles_x;
+                for (int i = 0; i < rw; ++i) {
+                    const uint32_t key = row_base + (uint32_t)(r.x + i);
+                    keys[w] = (KeyT)key;
+                    vals[w] = s;
+                    ++w;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        if (q < plan.npasses) atomicAdd(&s_hist[q][(key >> plan.shift[q]) & ((1u << plan.bits[q]) - 1u)], 1u);
+                }
+            }
+        }
+        uint32_t todo = big;
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const uint32_t bs = __shfl_sync(0xffffffffu, s, src), boff = __shfl_sync(0xffffffffu, off, src), bn = __shfl_sync(0xffffffffu, n, src);
+            const int bx0 = __shfl_sync(0xffffffffu, (int)r.x, src), by0 = __shfl_sync(0xffffffffu, (int)r.y, src);
+            const int bx1 = __shfl_sync(0xffffffffu, (int)r.z, src);
+            if ((unsigned long long)boff + bn > capacity) continue;
+            const int rw = bx1 - bx0 + 1;
+            // first owned row >= by0
+            const int first = by0 + (int)(((int)rank - (by0 % (int)world) + (int)world) % (int)world);
+            for (uint32_t i = lane; i < bn; i += 32) {
+                const int rowk = (int)(i / (uint32_t)rw), colk = (int)(i % (uint32_t)rw);
+                const int ty = first + rowk * (int)world;
+                const uint32_t key = (uint32_t)(ty / (int)world) * (uint32_t)tiles_x + (uint32_t)(bx0 + colk);
+                keys[boff + i] = (KeyT)key;
+                vals[boff + i] = bs;
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (q < plan.npasses) atomicAdd(&s_hist[q][(key >> plan.shift[q]) & ((1u << plan.bits[q]) - 1u)], 1u);
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < plan.npasses * kRadix; i += kEmitThreads) {
+        const uint32_t v = (&s_hist[0][0])[i];
+        if (v) atomicAdd(&ctl->hist[0][0] + i, v);
+    }
+}
+
+// tile ranges from the sorted keys
+template <typename KeyT>
+__global__ void k_tile_ranges(const KeyT *__restrict__ keys, const RasterControl *rctl, unsigned long long capacity, uint2 *__restrict__ ranges) {
+    const unsigned long long n = min(rctl->total_instances, capacity);
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint32_t k = keys[i];
+        if (i == 0 || (uint32_t)keys[i - 1] != k) ranges[k].x = (uint32_t)i;
+        if (i + 1 == n || (uint32_t)keys[i + 1] != k) ranges[k].y = (uint32_t)(i + 1);
+    }
+}
+
+__global__ void k_raster_init(RasterControl *rctl, SortControl *ctl, uint2 *ranges, uint32_t ntiles, uint32_t *lookback32,
+                              size_t lookback_words, unsigned long long *scan_lookback, size_t scan_words) {
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    if (tid == 0) {
+        rctl->total_instances = 0; rctl->overflow = 0; rctl->visible = 0; rctl->scan_ticket = 0;
+        ctl->error = 0;
+        for (int i = 0; i < 4; ++i) ctl->ticket[i] = 0;
+    }
+    uint32_t *h = &ctl->hist[0][0];
+    for (size_t i = tid; i < 4 * kRadix; i += stride) h[i] = 0;
+    for (size_t i = tid; i < ntiles; i += stride) ranges[i] = make_uint2(0u, 0u);
+    for (size_t i = tid; i < lookback_words; i += stride) lookback32[i] = 0;
+    for (size_t i = tid; i < scan_words; i += stride) scan_lookback[i] = 0ull;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Blend: one CTA per owned tile, one thread per pixel; the tile's list is staged through shared memory in batches.
+constexpr int kBlendThreads = kTile * kTile;
+
+template <int FORMAT>
+__global__ void __launch_bounds__(kBlendThreads)
+k_blend(const uint2 *__restrict__ ranges, const uint32_t *__restrict__ list, const SplatRecord *__restrict__ rec, int tiles_x,
+        uint32_t rank, uint32_t world, int width, int height, int flip_y, void *__restrict__ frame) {
+    __shared__ float4 s_rec[kBlendThreads][3];
+    const uint32_t local_tile = blockIdx.x;
+    const int tx = (int)(local_tile % (uint32_t)tiles_x), lrow = (int)(local_tile / (uint32_t)tiles_x);
+    const int ty = lrow * (int)world + (int)rank;
+    const int lx = threadIdx.x & (kTile - 1), ly = threadIdx.x >> kTileShift;
+    const int x = tx * kTile + lx, y = ty * kTile + ly;
+    const float pxc = (float)x + 0.5f, pyc = (float)y + 0.5f;
+    const uint2 rg = ranges[local_tile];
+    float T = 1.0f, Cr = 0.f, Cg = 0.f, Cb = 0.f;
+    bool done = !(x < width && y < height);
+    for (uint32_t base = rg.x; base < rg.y; base += kBlendThreads) {
+        if (__syncthreads_count(done) == kBlendThreads) break;
+        const uint32_t i = base + threadIdx.x;
+        if (i < rg.y) {
+            const uint32_t s = ld_nc_u32(list + i);
+            const float4 *src = reinterpret_cast<const float4 *>(rec + s);
+            s_rec[threadIdx.x][0] = src[0];
+            s_rec[threadIdx.x][1] = src[1];
+            s_rec[threadIdx.x][2] = src[2];
+        }
+        __syncthreads();
+        const int nb = (int)min((uint32_t)kBlendThreads, rg.y - base);
+        if (!done) {
+            for (int j = 0; j < nb; ++j) {
+                const float4 r0 = s_rec[j][0], r1 = s_rec[j][1];
+                const float dx = pxc - r0.x, dy = pyc - r0.y;
+                const float u = dx * r0.z + dy * r0.w;
+                const float w = dx * r1.x + dy * r1.y;
+                const float q = u * u + w * w;          // A = 8 q ; discard A > 8
+                if (q > 1.0f) continue;
+                const float4 r2 = s_rec[j][2];
+                const float alpha = __expf(-4.0f * q) * r1.w;  // exp(-0.5 A) * vColor.a
+                const float wgt = T * alpha;
+                Cr += wgt * r2.x; Cg += wgt * r2.y; Cb += wgt * r2.z;
+                T *= (1.0f - alpha);
+                if (T < kTransmittanceCutoff) { done = true; break; }
+            }
+        }
+    }
+    if (x < width && y < height) {
+        const float A = 1.0f - T; // alpha accumulates as 1 - prod(1 - alpha_i)
+        int out_row;
+        if (world == 1) out_row = flip_y ? (height - 1 - y) : y;
+        else out_row = lrow * kTile + ly;   // compact strip layout; assembled (and flipped) by the caller after the gather
+        const size_t at = (size_t)out_row * width + x;
+        if (FORMAT == GS_FRAME_RGBA32F) {
+            reinterpret_cast<float4 *>(frame)[at] = make_float4(Cr, Cg, Cb, A);
+        } else {
+            const uint32_t r8 = (uint32_t)(__saturatef(Cr) * 255.0f + 0.5f), g8 = (uint32_t)(__saturatef(Cg) * 255.0f + 0.5f);
+            const uint32_t b8 = (uint32_t)(__saturatef(Cb) * 255.0f + 0.5f), a8 = (uint32_t)(__saturatef(A) * 255.0f + 0.5f);
+            reinterpret_cast<uint32_t *>(frame)[at] = r8 | (g8 << 8) | (b8 << 16) | (a8 << 24);
+        }
+    }
+}
+
+// records -> the ABI's gs_projected_splat (basis vectors recovered from g = B/|B|^2)
+__global__ void k_export_projected(const SplatRecord *__restrict__ rec, const ushort4 *__restrict__ rects, uint32_t count, gs_projected_splat *out) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= count) return;
+    const SplatRecord r = rec[s];
+    gs_projected_splat o;
+    o.cx = r.cx; o.cy = r.cy;
+    const float n1 = r.g1x * r.g1x + r.g1y * r.g1y, n2 = r.g2x * r.g2x + r.g2y * r.g2y;
+    o.b1x = n1 > 0.f ? r.g1x / n1 : 0.f; o.b1y = n1 > 0.f ? r.g1y / n1 : 0.f;
+    o.b2x = n2 > 0.f ? r.g2x / n2 : 0.f; o.b2y = n2 > 0.f ? r.g2y / n2 : 0.f;
+    o.r = r.r; o.g = r.g; o.b = r.b; o.a = r.a;
+    o.ndc_z = r.ndc_z;
+    o.valid = r.valid;
+    out[s] = o;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Host side of the rasteriser
+template <typename T> struct RBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    cudaError_t ensure(size_t count) {
+        if (count <= n) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; n = 0;
+        cudaError_t e = cudaMalloc((void **)&p, (count ? count : 1) * sizeof(T));
+        if (e == cudaSuccess) n = count;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+struct RasterState {
+    RBuf<uint4> cc;
+    RBuf<unsigned char> cov, sh;
+    RBuf<uint32_t> scene_idx;
+    int cov_format = GS_COV_F32, sh_format = GS_SH_NONE;
+    uint32_t sh_degree = 0, uploaded = 0;
+    bool have_scene_idx = false;
+    RBuf<SplatRecord> records;
+    RBuf<ushort4> rects;
+    RBuf<uint32_t> offsets;
+    RBuf<uint32_t> ikeys[2];   // instance keys ping/pong (u16 or u32 elements)
+    RBuf<uint32_t> ivals[2];   // instance values ping/pong
+    RBuf<uint32_t> list;       // final per-tile lists
+    RBuf<uint2> ranges;
+    RBuf<RasterControl> rctl;
+    RBuf<SortControl> sctl;
+    RBuf<uint32_t> lookback;
+    RBuf<unsigned long long> scan_lookback;
+    RBuf<DynamicUniforms> dyn;
+    RBuf<unsigned char> frame;
+    RBuf<gs_projected_splat> exported;
+    unsigned long long instance_capacity = 0;
+    int sm_count = 148;
+    int last_format = GS_FRAME_RGBA32F;
+    size_t last_frame_bytes = 0;
+};
+
+#define RCU(call)                                                                                                 \
+    do {                                                                                                          \
+        cudaError_t _e = (call);                                                                                  \
+        if (_e != cudaSuccess) { snprintf(raster_err(), 512, "%s -> %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); return GS_ERR_CUDA; } \
+    } while (0)
+
+static inline char *raster_err() { return g_gs_err; }
+
+static int raster_init(RasterState &rs, const gs_config &c, int sm_count) {
+    rs.sm_count = sm_count;
+    const size_t n = c.max_splat_count ? c.max_splat_count : 1;
+    RCU(rs.rctl.ensure(1));
+    RCU(rs.sctl.ensure(1));
+    RCU(rs.dyn.ensure(1));
+    RCU(cudaMemset(rs.dyn.p, 0, sizeof(DynamicUniforms)));
+    if (c.max_width && c.max_height) {
+        RCU(rs.cc.ensure(n));
+        RCU(rs.records.ensure(n));
+        RCU(rs.rects.ensure(n));
+        RCU(rs.offsets.ensure(n));
+        const char *f = getenv("GS_INSTANCE_FACTOR");
+        const double factor = f ? atof(f) : 12.0;
+        const size_t tiles = (size_t)((c.max_width + kTile - 1) / kTile) * ((c.max_height + kTile - 1) / kTile);
+        rs.instance_capacity = (unsigned long long)(factor * (double)n) + 4ull * tiles + 65536ull;
+        if (rs.instance_capacity > 0xfffffff0ull) rs.instance_capacity = 0xfffffff0ull;
+        for (int i = 0; i < 2; ++i) { RCU(rs.ikeys[i].ensure(rs.instance_capacity)); RCU(rs.ivals[i].ensure(rs.instance_capacity)); }
+        RCU(rs.list.ensure(rs.instance_capacity));
+        RCU(rs.ranges.ensure(tiles));
+        RCU(rs.frame.ensure((size_t)c.max_width * (c.max_height + kTile) * 16));
+        const size_t itiles = (rs.instance_capacity + kRadixTile - 1) / kRadixTile;
+        RCU(rs.lookback.ensure(itiles * kRadix * 3));
+        RCU(rs.scan_lookback.ensure((n + kScanTile - 1) / kScanTile + 1));
+    }
+    return GS_OK;
+}
+
+static void raster_release(RasterState &rs) {
+    rs.cc.release(); rs.cov.release(); rs.sh.release(); rs.scene_idx.release(); rs.records.release(); rs.rects.release();
+    rs.offsets.release(); rs.ikeys[0].release(); rs.ikeys[1].release(); rs.ivals[0].release(); rs.ivals[1].release();
+    rs.list.release(); rs.ranges.release(); rs.rctl.release(); rs.sctl.release(); rs.lookback.release(); rs.scan_lookback.release();
+    rs.dyn.release(); rs.frame.release(); rs.exported.release();
+}
+
+static int raster_upload(RasterState &rs, const gs_config &c, const gs_splat_data &d, cudaStream_t st) {
+    if (!c.max_width || !c.max_height) { snprintf(raster_err(), 512, "engine created without a framebuffer (max_width/max_height = 0)"); return GS_ERR_NOT_READY; }
+    if ((uint64_t)d.from + d.count > c.max_splat_count) { snprintf(raster_err(), 512, "splat data [%u,%u) exceeds max_splat_count %u", d.from, d.from + d.count, c.max_splat_count); return GS_ERR_CAPACITY; }
+    if (!d.centers_colors || !d.covariances) { snprintf(raster_err(), 512, "gs_upload_splat_data: null centers_colors/covariances"); return GS_ERR_BAD_ARG; }
+    if (d.sh_degree > 2) { snprintf(raster_err(), 512, "sh_degree %u > 2", d.sh_degree); return GS_ERR_BAD_ARG; }
+    const size_t n = c.max_splat_count;
+    const size_t cov_elt = d.cov_format == GS_COV_F16 ? 12 : 24;
+    const size_t ncomp = d.sh_degree == 2 ? 24 : (d.sh_degree == 1 ? 9 : 0);
+    const size_t sh_elt = ncomp * (d.sh_format == GS_SH_F16 ? 2 : (d.sh_format == GS_SH_U8 ? 1 : 4));
+    if (rs.uploaded && (rs.cov_format != d.cov_format || (rs.sh_degree != d.sh_degree) || (ncomp && rs.sh_format != d.sh_format))) {
+        snprintf(raster_err(), 512, "splat data format changed between partial uploads"); return GS_ERR_BAD_ARG;
+    }
+    rs.cov_format = d.cov_format;
+    rs.sh_degree = d.sh_degree;
+    rs.sh_format = ncomp ? d.sh_format : GS_SH_NONE;
+    RCU(rs.cov.ensure(n * cov_elt + 16));
+    if (ncomp) {
+        if (!d.spherical_harmonics) { snprintf(raster_err(), 512, "sh_degree %u without spherical_harmonics", d.sh_degree); return GS_ERR_BAD_ARG; }
+        RCU(rs.sh.ensure(n * sh_elt + 16));
+    }
+    RCU(cudaMemcpyAsync(rs.cc.p + d.from, d.centers_colors, (size_t)d.count * 16, cudaMemcpyHostToDevice, st));
+    RCU(cudaMemcpyAsync(rs.cov.p + (size_t)d.from * cov_elt, d.covariances, (size_t)d.count * cov_elt, cudaMemcpyHostToDevice, st));
+    if (ncomp) RCU(cudaMemcpyAsync(rs.sh.p + (size_t)d.from * sh_elt, d.spherical_harmonics, (size_t)d.count * sh_elt, cudaMemcpyHostToDevice, st));
+    if (d.scene_indexes) {
+        RCU(rs.scene_idx.ensure(n));
+        RCU(cudaMemcpyAsync(rs.scene_idx.p + d.from, d.scene_indexes, (size_t)d.count * 4, cudaMemcpyHostToDevice, st));
+        rs.have_scene_idx = true;
+    }
+    rs.uploaded = std::max<uint32_t>(rs.uploaded, d.from + d.count);
+    return GS_OK;
+}
+
+static void *raster_frame_ptr(RasterState &rs, int) { return rs.frame.p; }
+
+template <bool COVF16>
+static void launch_project(RasterState &rs, const ProjParams &P, uint32_t count, cudaStream_t st) {
+    const int blocks = (int)((count + kProjThreads - 1) / kProjThreads);
+    const uint32_t *sc = rs.have_scene_idx ? rs.scene_idx.p : nullptr;
+#define GS_PROJ(FMT) k_project<COVF16, FMT><<<blocks, kProjThreads, 0, st>>>(rs.cc.p, rs.cov.p, rs.sh.p, (int)rs.sh_degree, sc, rs.dyn.p, P, count, rs.records.p, rs.rects.p, rs.rctl.p)
+    switch (rs.sh_format) {
+        case GS_SH_F16: GS_PROJ(GS_SH_F16); break;
+        case GS_SH_U8: GS_PROJ(GS_SH_U8); break;
+        case GS_SH_F32: GS_PROJ(GS_SH_F32); break;
+        default: GS_PROJ(GS_SH_NONE); break;
+    }
+#undef GS_PROJ
+}
+
+static int raster_render(RasterState &rs, const gs_config &c, const gs_uniforms &u, const gs_render_params &p, const uint32_t *d_order,
+                         cudaStream_t st, cudaEvent_t ev_project, cudaEvent_t ev_bin, gs_timings &tm) {
+    if (!rs.uploaded) { snprintf(raster_err(), 512, "gs_render before gs_upload_splat_data"); return GS_ERR_NOT_READY; }
+    if (p.width == 0 || p.height == 0 || p.width > c.max_width || p.height > c.max_height) {
+        snprintf(raster_err(), 512, "frame %ux%u outside the engine's %ux%u", p.width, p.height, c.max_width, c.max_height); return GS_ERR_BAD_ARG;
+    }
+    if (p.render_count > rs.uploaded) { snprintf(raster_err(), 512, "render_count %u > uploaded splats %u", p.render_count, rs.uploaded); return GS_ERR_CAPACITY; }
+    const int tiles_x = (p.width + kTile - 1) / kTile, tiles_y = (p.height + kTile - 1) / kTile;
+    const uint32_t world = c.world_size, rank = c.rank;
+    const int local_rows = owned_rows(0, tiles_y - 1, rank, world);
+    const uint32_t local_tiles = (uint32_t)local_rows * (uint32_t)tiles_x;
+    uint32_t launches = 0;
+
+    ProjParams P{};
+    memcpy(P.mv, u.model_view, 64); memcpy(P.proj, u.projection, 64);
+    memcpy(P.cam, u.camera_position, 12);
+    P.focal[0] = u.focal[0]; P.focal[1] = u.focal[1]; P.viewport[0] = u.viewport[0]; P.viewport[1] = u.viewport[1];
+    P.inv_focal_adj = u.inverse_focal_adjustment; P.ortho_zoom = u.ortho_zoom; P.orthographic = u.orthographic_mode;
+    P.splat_scale = u.splat_scale; P.point_cloud = u.point_cloud_mode; P.sh_degree = u.sh_degree; P.antialiased = u.antialiased;
+    P.kernel2d = u.kernel_2d_size; P.max_size = u.max_screen_space_splat_size; P.fade_in_complete = u.fade_in_complete;
+    memcpy(P.scene_center, u.scene_center, 12); P.fade_start = u.visible_region_fade_start_radius;
+    P.dynamic = u.dynamic_mode; P.optional_effects = u.enable_optional_effects; P.scene_count = (int)u.scene_count;
+    P.tiles_x = tiles_x; P.tiles_y = tiles_y; P.rank = rank; P.world = world; P.width = (int)p.width; P.height = (int)p.height;
+    if (u.dynamic_mode || u.enable_optional_effects || rs.sh_format == GS_SH_U8) {
+        DynamicUniforms du;
+        memcpy(du.view, u.view_matrix, 64);
+        memcpy(du.transforms, u.scene_transforms, sizeof(du.transforms));
+        memcpy(du.sh8_min, u.sh8_min, sizeof(du.sh8_min)); memcpy(du.sh8_max, u.sh8_max, sizeof(du.sh8_max));
+        memcpy(du.opacity, u.scene_opacity, sizeof(du.opacity)); memcpy(du.visibility, u.scene_visibility, sizeof(du.visibility));
+        RCU(cudaMemcpyAsync(rs.dyn.p, &du, sizeof(du), cudaMemcpyHostToDevice, st)); // pageable source: staged before return
+    }
+
+    int tile_bits = 1;
+    while ((1u << tile_bits) < std::max(local_tiles, 2u)) ++tile_bits;
+    const PassPlan pl = make_plan_bits(tile_bits);
+    const size_t itiles = (rs.instance_capacity + kRadixTile - 1) / kRadixTile;
+    const uint32_t scan_tiles = (p.render_count + kScanTile - 1) / kScanTile;
+    // look-back words actually needed are bounded by the capacity; zero only what the instance count can touch (worst case)
+    k_raster_init<<<rs.sm_count * 2, 256, 0, st>>>(rs.rctl.p, rs.sctl.p, rs.ranges.p, local_tiles, rs.lookback.p, itiles * kRadix * pl.npasses,
+                                                 rs.scan_lookback.p, (size_t)scan_tiles + 1);
+    ++launches;
+    const uint32_t count = rs.uploaded;
+    if (rs.cov_format == GS_COV_F16) launch_project<true>(rs, P, count, st); else launch_project<false>(rs, P, count, st);
+    ++launches;
+    RCU(cudaEventRecord(ev_project, st));
+    if (p.render_count && local_tiles) {
+        k_tile_count<<<scan_tiles, kScanThreads, 0, st>>>(d_order, p.render_count, rs.rects.p, rank, world, rs.offsets.p, rs.scan_lookback.p, rs.rctl.p, rs.instance_capacity);
+        ++launches;
+        const int eblocks = (int)std::min<uint64_t>(((uint64_t)p.render_count + kEmitThreads - 1) / kEmitThreads, (uint64_t)rs.sm_count * 8);
+        if (tile_bits <= 16) {
+            k_tile_emit<uint16_t><<<eblocks, kEmitThreads, 0, st>>>(d_order, p.render_count, rs.rects.p, rs.offsets.p, rank, world, tiles_x,
+                                                                  (uint16_t *)rs.ikeys[0].p, rs.ivals[0].p, rs.instance_capacity, pl, rs.sctl.p);
+        } else {
+            k_tile_emit<uint32_t><<<eblocks, kEmitThreads, 0, st>>>(d_order, p.render_count, rs.rects.p, rs.offsets.p, rank, world, tiles_x,
+                                                                  rs.ikeys[0].p, rs.ivals[0].p, rs.instance_capacity, pl, rs.sctl.p);
+        }
+        ++launches;
+        // The instance count lives on the device only: the radix grids are sized for the capacity and surplus CTAs exit.
+        const unsigned long long *n_dev = &rs.rctl.p->total_instances;
+        if (tile_bits <= 16) {
+            radix_sort_pairs<uint16_t>((uint16_t *)rs.ikeys[0].p, (uint16_t *)rs.ikeys[1].p, rs.ivals[0].p, 0u, kValArray, rs.ivals[1].p, rs.ivals[0].p,
+                                       rs.list.p, 0u, n_dev, rs.instance_capacity, pl, rs.sctl.p, rs.lookback.p, true, st, launches);
+            const uint16_t *sorted_keys = (pl.npasses & 1) ? (const uint16_t *)rs.ikeys[1].p : (const uint16_t *)rs.ikeys[0].p;
+            k_tile_ranges<uint16_t><<<rs.sm_count * 4, 256, 0, st>>>(sorted_keys, rs.rctl.p, rs.instance_capacity, rs.ranges.p);
+        } else {
+            radix_sort_pairs<uint32_t>(rs.ikeys[0].p, rs.ikeys[1].p, rs.ivals[0].p, 0u, kValArray, rs.ivals[1].p, rs.ivals[0].p, rs.list.p, 0u, n_dev,
+                                       rs.instance_capacity, pl, rs.sctl.p, rs.lookback.p, true, st, launches);
+            const uint32_t *sorted_keys = (pl.npasses & 1) ? rs.ikeys[1].p : rs.ikeys[0].p;
+            k_tile_ranges<uint32_t><<<rs.sm_count * 4, 256, 0, st>>>(sorted_keys, rs.rctl.p, rs.instance_capacity, rs.ranges.p);
+        }
+        ++launches;
+    }
+    RCU(cudaEventRecord(ev_bin, st));
+    if (local_tiles) {
+        if (p.frame_format == GS_FRAME_RGBA8)
+            k_blend<GS_FRAME_RGBA8><<<local_tiles, kBlendThreads, 0, st>>>(rs.ranges.p, rs.list.p, rs.records.p, tiles_x, rank, world, (int)p.width, (int)p.height, p.flip_y, rs.frame.p);
+        else
+            k_blend<GS_FRAME_RGBA32F><<<local_tiles, kBlendThreads, 0, st>>>(rs.ranges.p, rs.list.p, rs.records.p, tiles_x, rank, world, (int)p.width, (int)p.height, p.flip_y, rs.frame.p);
+        ++launches;
+    }
+    rs.last_format = p.frame_format;
+    const size_t rows = world == 1 ? p.height : (size_t)local_rows * kTile;
+    rs.last_frame_bytes = rows * p.width * (p.frame_format == GS_FRAME_RGBA8 ? 4 : 16);
+    tm.kernel_launches = launches;
+    return GS_OK;
+}
+
+static int raster_read_projected(RasterState &rs, gs_projected_splat *out, uint32_t count, cudaStream_t st) {
+    if (count > rs.uploaded) { snprintf(raster_err(), 512, "count %u > uploaded %u", count, rs.uploaded); return GS_ERR_CAPACITY; }
+    RCU(rs.exported.ensure(count));
+    if (count) k_export_projected<<<(count + 255) / 256, 256, 0, st>>>(rs.records.p, rs.rects.p, count, rs.exported.p);
+    RCU(cudaMemcpyAsync(out, rs.exported.p, (size_t)count * sizeof(gs_projected_splat), cudaMemcpyDeviceToHost, st));
+    return GS_OK;
+}
+
+} // namespace gs

@@ -1,0 +1,245 @@
+/* gsplat_b200.h -- C ABI of libgsplat_b200.so: the B200 (sm_100a) depth -> sort -> rasterise engine that
+ * sits behind the GaussianSplats3D sort-worker / SplatMesh boundary.
+ *
+ * Every entry point cites the reference interface (file:line under mkkellogg/GaussianSplats3D @ v0.4.7)
+ * it replaces.  Plain pointers and sizes only; no torch / C++ types.  All functions return 0 (GS_OK) or a
+ * gs_status error code unless stated otherwise; nothing in this library falls back to the CPU: without a
+ * CUDA device every compute entry returns GS_ERR_NO_DEVICE.
+ *
+ * Memory kinds: pointers are HOST pointers unless the parameter name ends in `_dev`.
+ */
+#ifndef GSPLAT_B200_H
+#define GSPLAT_B200_H
+
+#include <stdint.h>
+#include <stdbool.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GS_API __attribute__((visibility("default")))
+#define GS_ABI_VERSION 1
+#define GS_MAX_SCENES 32 /* Constants.MaxScenes, src/Constants.js:7 */
+
+typedef enum gs_status {
+    GS_OK = 0,
+    GS_ERR_BAD_ARG = 1,       /* null pointer, sortCount > renderCount, range < 2, ...                        */
+    GS_ERR_NO_DEVICE = 2,     /* no CUDA device / CUDA runtime error at init                                   */
+    GS_ERR_CUDA = 3,          /* a CUDA call failed; gs_last_error_message() has the text                      */
+    GS_ERR_DEGENERATE = 4,    /* all distances equal (reference: rangeMap = inf -> NaN -> wasm trap)           */
+    GS_ERR_BUCKET_RANGE = 5,  /* a bucket index fell outside [0, distanceMapRange) (reference: OOB write)      */
+    GS_ERR_NOT_READY = 6,     /* render before upload / sort                                                   */
+    GS_ERR_CAPACITY = 7       /* splat range outside the capacity given at create time                         */
+} gs_status;
+
+GS_API int gs_abi_version(void);
+GS_API const char *gs_status_string(int status);
+GS_API const char *gs_last_error_message(void); /* thread-local text of the last failing call */
+GS_API int gs_device_count(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * 1. Stateless drop-in for the reference's only native symbol
+ *      extern "C" void sortIndexes(...16 args...)                     src/worker/sorter.cpp:17-22
+ *    Same argument order and meaning.  HOST pointers, as the wasm module sees its linear memory
+ *    (SortWorker.js:56-60).  The two scratch outputs are reproduced too when their pointers are non-NULL:
+ *    `mappedDistances[sortStart..renderCount)` = bucket of each position, `frequencies[b]` = number of
+ *    sorted splats in buckets < b (what the reference's in-place counters hold on return).
+ *    Every call uploads its inputs, runs the CUDA pipeline and downloads indexesOut: this is the
+ *    parity-test boundary; the persistent-state path (section 2) is the fast one.
+ * ---------------------------------------------------------------------------------------------------------- */
+GS_API int gs_sort_indexes(const uint32_t *indexes, const void *centers, const void *precomputedDistances,
+                           int32_t *mappedDistances, uint32_t *frequencies, const float *modelViewProj,
+                           uint32_t *indexesOut, const uint32_t *sceneIndexes, const float *transforms,
+                           uint32_t distanceMapRange, uint32_t sortCount, uint32_t renderCount, uint32_t splatCount,
+                           bool usePrecomputedDistances, bool useIntegerSort, bool dynamicMode);
+
+/* void twin with the reference's exact symbol name and signature; errors are swallowed like a wasm trap
+ * would abort the call (indexesOut untouched on failure). */
+GS_API void sortIndexes(unsigned int *indexes, void *centers, void *precomputedDistances, int *mappedDistances,
+                        unsigned int *frequencies, float *modelViewProj, unsigned int *indexesOut,
+                        unsigned int *sceneIndexes, float *transforms, unsigned int distanceMapRange,
+                        unsigned int sortCount, unsigned int renderCount, unsigned int splatCount,
+                        bool usePrecomputedDistances, bool useIntegerSort, bool dynamicMode);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * 2. Engine handle: the state a sort Worker + SplatMesh pair keeps on the device.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct gs_engine gs_engine;
+
+typedef struct gs_config {
+    uint32_t struct_size;           /* sizeof(gs_config), for ABI growth                                        */
+    int32_t device;                 /* CUDA device ordinal                                                       */
+    uint32_t max_splat_count;       /* 'splatCount' of createSortWorker          SortWorker.js:202               */
+    uint32_t distance_map_range;    /* 1 << splatSortDistanceMapPrecision        SortWorker.js:243, Constants.js:3 */
+    uint8_t integer_based_sort;     /* Viewer option integerBasedSort            Viewer.js:95-98                 */
+    uint8_t dynamic_mode;           /* Viewer option dynamicScene                SortWorker.js:120               */
+    uint8_t reserved0[2];
+    uint32_t max_width, max_height; /* largest framebuffer gs_render will be asked for (0,0: sort only)          */
+    /* multi-GPU sharding (one engine per process per GPU).  tile rows [tile_row_begin, tile_row_end) of the
+     * 16x16-pixel tile grid are rendered by this engine; 0,0 = all rows.                                        */
+    uint32_t rank, world_size;
+} gs_config;
+
+GS_API int gs_create(const gs_config *cfg, gs_engine **out);
+GS_API void gs_destroy(gs_engine *e); /* worker.terminate()  Viewer.js:1311 */
+
+/* 'centers' message: persistent sorter centres for splats [from, from+count)      SortWorker.js:84-98
+ * centers: int32x4 (integer_based_sort) or f32x4 per splat, exactly what SplatMesh.getIntegerCenters /
+ * getFloatCenters(padFour=true) produce (SplatMesh.js:1912-1948).  sceneIndexes may be NULL unless dynamic. */
+GS_API int gs_upload_centers(gs_engine *e, const void *centers, const uint32_t *sceneIndexes, uint32_t from,
+                             uint32_t count);
+
+typedef struct gs_sort_params {
+    uint32_t struct_size;
+    float model_view_proj[16];           /* column-major, Viewer.js:1888-1891                                    */
+    uint32_t sort_count, render_count;   /* 'splatSortCount' / 'splatRenderCount'    SortWorker.js:99-101         */
+    const uint32_t *indexes_to_sort;     /* HOST u32[render_count]; NULL = identity (gatherSceneNodesForSort's
+                                            no-tree case, Viewer.js:2061-2074)                                    */
+    const uint32_t *indexes_to_sort_dev; /* or DEVICE pointer (takes precedence)                                  */
+    const float *transforms;             /* HOST f32[16*GS_MAX_SCENES] when dynamic  SortWorker.js:38-39          */
+    const void *precomputed_distances;   /* HOST i32/f32[splat_count] when use_precomputed (SortWorker.js:40-50)  */
+    uint8_t use_precomputed_distances;
+    uint8_t reserved[3];
+} gs_sort_params;
+
+/* 'sort' message -> 'sortDone'.  Runs asynchronously on the engine's stream; the sorted order stays on the
+ * device for gs_render.  sorted_out (HOST u32[render_count], may be NULL) receives 'sortedIndexes'
+ * (SortWorker.js:68-75); sort_time_ms (may be NULL) the device time of the sort kernels.                       */
+GS_API int gs_sort(gs_engine *e, const gs_sort_params *p, uint32_t *sorted_out, float *sort_time_ms);
+
+/* D1: the transform-feedback distance pre-pass, SplatMesh.computeDistancesOnGPU (SplatMesh.js:1701-1814): distances
+ * in SPLAT order from the uploaded centres.  model_view_proj is f64 because three.js matrices are JS numbers and the
+ * integer rows are Math.round(element * 1000) of those doubles (getIntegerMatrixArray, SplatMesh.js:2057-2064);
+ * scene_transforms (f64[16*GS_MAX_SCENES], dynamic mode only, else NULL) are the per-scene matrices multiplied in at
+ * SplatMesh.js:1722-1724.  out: HOST i32[count] (integer mode) or f32[count] (float mode, SplatMesh.js:1473-1502).   */
+GS_API int gs_compute_distances(gs_engine *e, const double *model_view_proj, const double *scene_transforms,
+                                uint32_t count, void *out);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * 3. Rasteriser: the data textures SplatMesh uploads (setupDataTextures, SplatMesh.js:637-898) and the uniforms
+ *    it sets per frame (updateUniforms :1248-1280, Viewer.updateSplatMesh Viewer.js:651-677, three.js camera
+ *    matrices).
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef enum gs_cov_format { GS_COV_F32 = 0, GS_COV_F16 = 1 } gs_cov_format;
+typedef enum gs_sh_format { GS_SH_NONE = 0, GS_SH_F16 = 1, GS_SH_U8 = 2, GS_SH_F32 = 3 } gs_sh_format;
+
+typedef struct gs_splat_data {
+    uint32_t struct_size;
+    uint32_t from, count;             /* splat range being (re)uploaded                                          */
+    const uint32_t *centers_colors;   /* u32x4: {r|g<<8|b<<16|a<<24, bits(x), bits(y), bits(z)}  SplatMesh.js:1143-1153 */
+    const void *covariances;          /* 6 x f32 (GS_COV_F32) or 6 x f16 (GS_COV_F16, tightly packed) per splat:
+                                         [m00 m01 m02 m11 m12 m22]                     SplatBuffer.js:440-486       */
+    int32_t cov_format;
+    const void *spherical_harmonics;  /* sh_components values per splat, coefficient-major RGB triples
+                                         (sh1.rgb, sh2.rgb, ...)                        SplatBuffer.js:551-734      */
+    int32_t sh_format;                /* gs_sh_format                                                             */
+    uint32_t sh_degree;               /* 0, 1 (9 values) or 2 (24 values)                                         */
+    const uint32_t *scene_indexes;    /* u32 per splat or NULL (single scene)                                     */
+} gs_splat_data;
+
+GS_API int gs_upload_splat_data(gs_engine *e, const gs_splat_data *d);
+
+typedef struct gs_uniforms {
+    uint32_t struct_size;
+    float model_view[16];             /* three: modelViewMatrix = camera.matrixWorldInverse * mesh.matrixWorld    */
+    float projection[16];             /* camera.projectionMatrix                                                  */
+    float camera_position[3];         /* cameraPosition uniform (world)                                           */
+    float focal[2];                   /* SplatMesh.js:1262                                                        */
+    float viewport[2];                /* render dimensions * devicePixelRatio, SplatMesh.js:1257-1259             */
+    float inverse_focal_adjustment;   /* SplatMesh.js:1265                                                        */
+    float ortho_zoom;                 /* SplatMesh.js:1264                                                        */
+    int32_t orthographic_mode;        /* SplatMesh.js:1263                                                        */
+    float splat_scale;                /* SplatMaterial.js:469                                                     */
+    int32_t point_cloud_mode;         /* SplatMaterial.js:473                                                     */
+    int32_t sh_degree;                /* sphericalHarmonicsDegree uniform (<= uploaded degree)                    */
+    int32_t antialiased;              /* SplatMaterial3D.js:137-145                                               */
+    float kernel_2d_size;             /* default 0.3, SplatMaterial3D.js:21                                       */
+    float max_screen_space_splat_size;/* default 1024 (Viewer.js:201), SplatMaterial3D.js:193-194                 */
+    float sh8_min[GS_MAX_SCENES];     /* sphericalHarmonics8BitCompressionRangeMin/Max, SplatMaterial.js:402-409  */
+    float sh8_max[GS_MAX_SCENES];
+    uint32_t scene_count;
+    float scene_transforms[16 * GS_MAX_SCENES]; /* dynamic mode `transforms` uniform                              */
+    float view_matrix[16];            /* three: viewMatrix (dynamic mode only)                                    */
+    float scene_opacity[GS_MAX_SCENES];   /* enableOptionalEffects                                                */
+    int32_t scene_visibility[GS_MAX_SCENES];
+    int32_t enable_optional_effects;  /* SplatMaterial.js:23-28,124-133; SplatMaterial3D.js:198-202           */
+    int32_t dynamic_mode;             /* per-scene transforms in the vertex stage, SplatMaterial.js:136-146       */
+    /* fade-in (SplatMaterial.js:347-363) */
+    int32_t fade_in_complete;
+    float scene_center[3];
+    float visible_region_fade_start_radius;
+} gs_uniforms;
+
+typedef enum gs_frame_format {
+    GS_FRAME_RGBA32F = 0, /* float accumulators, premultiplied colour + coverage alpha                            */
+    GS_FRAME_RGBA8 = 1    /* the canvas format: round(clamp(v,0,1)*255) once at the end                           */
+} gs_frame_format;
+
+typedef struct gs_render_params {
+    uint32_t struct_size;
+    uint32_t width, height;
+    uint32_t render_count;              /* geometry.instanceCount, SplatMesh.js:1233-1234                         */
+    const uint32_t *sorted_indexes;     /* HOST u32[render_count] = the splatIndex attribute
+                                           (SplatMesh.updateRenderIndexes :1228-1235); NULL = use the order of
+                                           the engine's last gs_sort                                              */
+    const uint32_t *sorted_indexes_dev; /* or DEVICE pointer                                                      */
+    int32_t frame_format;               /* gs_frame_format                                                        */
+    int32_t flip_y;                     /* 0: row 0 = bottom (GL window coords); 1: row 0 = top (image order)     */
+} gs_render_params;
+
+/* renderer.render(splatMesh, camera)  Viewer.js:1616.  frame_out: HOST buffer of width*height*4 floats or bytes
+ * (may be NULL: the frame stays on the device, see gs_frame_dev).                                               */
+GS_API int gs_render(gs_engine *e, const gs_uniforms *u, const gs_render_params *p, void *frame_out);
+
+/* One viewer frame: Viewer.update() -> runSplatSort (full sort) + render  (Viewer.js:1625-1644, 1599-1623).    */
+GS_API int gs_frame(gs_engine *e, const gs_sort_params *s, const gs_uniforms *u, const gs_render_params *p,
+                    uint32_t *sorted_out, void *frame_out);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * 4. Device-side access for zero-copy callers and for the multi-GPU plumbing (tile gather over NCCL).
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef enum gs_buffer_id {
+    GS_BUF_SORTED_INDEXES = 0, /* u32[render_count]                                                               */
+    GS_BUF_FRAME = 1,          /* last rendered frame in the requested format                                     */
+    GS_BUF_CENTERS = 2,
+    GS_BUF_DISTANCES = 3,      /* i32[render_count] scratch (= mappedDistances)                                   */
+    GS_BUF_SPLAT_RECORDS = 4,  /* per-splat projected records (engine-internal 48-byte layout)                    */
+    GS_BUF_INDEXES_TO_SORT = 5 /* u32[max_splat_count] staging for indexesToSort                                  */
+} gs_buffer_id;
+GS_API int gs_buffer_dev(gs_engine *e, int buffer_id, void **ptr_dev, size_t *bytes);
+GS_API int gs_stream(gs_engine *e, void **cuda_stream); /* cudaStream_t of the engine */
+GS_API int gs_synchronize(gs_engine *e);
+
+/* Page-locked host memory for callers: the counterpart of the SharedArrayBuffer views a shared-memory sort worker
+ * hands to the main thread (SortWorker.js:180-191).  Buffers passed to gs_sort / gs_render from such memory are
+ * copied asynchronously without an extra staging copy. */
+GS_API int gs_host_alloc(void **ptr, size_t bytes);
+GS_API int gs_host_free(void *ptr);
+
+/* Per-splat output of the projection stage (what the vertex shader hands to rasterisation), for parity tests. */
+typedef struct gs_projected_splat {
+    float cx, cy;        /* quad centre, pixels, GL window coordinates (y up, pixel centres at +0.5)              */
+    float b1x, b1y;      /* basisVector1 * inverseFocalAdjustment, pixels    SplatMaterial3D.js:193,206-207        */
+    float b2x, b2y;      /* basisVector2 ...                                                                      */
+    float r, g, b, a;    /* vColor                                                                                */
+    float ndc_z;
+    uint32_t valid;      /* 0 = culled / dropped                                                                  */
+} gs_projected_splat;
+GS_API int gs_read_projected(gs_engine *e, gs_projected_splat *out, uint32_t count); /* splat order */
+
+typedef struct gs_timings {
+    float depth_ms, bucket_ms, scatter_ms, sort_total_ms;
+    float project_ms, bin_ms, blend_ms, render_total_ms;
+    float h2d_ms, d2h_ms;
+    uint64_t tile_instances;   /* (splat, tile) pairs binned in the last render                                   */
+    uint32_t kernel_launches;  /* kernels launched by the last gs_sort/gs_render/gs_frame                          */
+    uint32_t visible_splats;
+} gs_timings;
+GS_API int gs_last_timings(gs_engine *e, gs_timings *t);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSPLAT_B200_H */

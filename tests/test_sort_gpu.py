@@ -1,0 +1,132 @@
+"""GPU parity: the CUDA sort (through the C ABI) must reproduce the reference's sortIndexes() bit for bit."""
+import numpy as np
+import pytest
+
+import cases
+
+pytestmark = pytest.mark.gpu
+
+
+def _expect(oracle_mod, c, R):
+    if oracle_mod.have_ref():
+        return oracle_mod.ref_sort_indexes(*cases.call_args(c, R))
+    return oracle_mod.port_sort_indexes(*cases.call_args(c, R))
+
+
+@pytest.mark.parametrize("name,kw", cases.sort_matrix(n=20000, seeds=(0,)))
+def test_dropin_sortIndexes_bit_exact(gs, oracle_mod, name, kw):
+    c = cases.sort_case(**kw)
+    for R in cases.RANGES + ((1 << 22,) if not c["integer_sort"] else ()):
+        want = _expect(oracle_mod, c, R)
+        got = gs.sort_indexes(*cases.call_args(c, R))
+        assert np.array_equal(got, want), f"{name} R={R}: first mismatch at {np.flatnonzero(got != want)[:5]}"
+
+
+def test_dropin_scratch_outputs(gs, oracle_mod):
+    """mappedDistances / frequencies hold what the reference leaves there."""
+    c = cases.sort_case(seed=3, n=50000, index_kind="shuffled", sort_frac=0.6)
+    R = 1 << 16
+    out, mapped, freq = gs.sort_indexes(*cases.call_args(c, R), want_scratch=True)
+    want, buckets = oracle_mod.port_sort_indexes(*cases.call_args(c, R), want_buckets=True)
+    s0 = c["render_count"] - c["sort_count"]
+    assert np.array_equal(out, want)
+    assert np.array_equal(mapped[s0:], buckets[s0:])
+    counts = np.bincount(buckets[s0:], minlength=R)
+    assert np.array_equal(freq, (np.cumsum(counts) - counts).astype(np.uint32))
+    if oracle_mod.have_ref():
+        _, rmapped, rfreq = oracle_mod.ref_sort_indexes(*cases.call_args(c, R), want_scratch=True)
+        assert np.array_equal(mapped[s0:], rmapped[s0:]) and np.array_equal(freq, rfreq)
+
+
+def test_golden_vectors(gs):
+    """Committed outputs of the reference's compiled sorter (tests/golden/make_golden.py)."""
+    gold = np.load(cases.__file__.replace("cases.py", "golden/sort_golden.npz"))
+    table = dict(cases.sort_matrix(n=3000, seeds=(11,)))
+    for key in [str(k) for k in gold["names"]]:
+        name, rtag = key.split("|")
+        c = cases.sort_case(**table[name])
+        got = gs.sort_indexes(*cases.call_args(c, int(rtag[1:])))
+        assert np.array_equal(got, gold[key + "|out"]), key
+
+
+@pytest.mark.parametrize("integer,dynamic", [(True, False), (False, False), (True, True), (False, True)])
+def test_engine_worker_protocol(gs, oracle_mod, integer, dynamic):
+    """init -> centers (in two ranges) -> sort (partial, then full), like the Viewer drives the worker."""
+    n = 150_000
+    c = cases.sort_case(seed=9, n=n, integer=integer, dynamic=dynamic, index_kind="octree")
+    R = 1 << 16
+    with gs.Engine(n, distance_map_range=R, integer_based_sort=integer, dynamic_mode=dynamic) as e:
+        half = n // 2
+        si = c["scene_indexes"]
+        e.upload_centers(c["centers"][:half], None if si is None else si[:half], 0)
+        e.upload_centers(c["centers"][half:], None if si is None else si[half:], half)
+        for sort_count in (c["render_count"] // 8, c["render_count"]):
+            c2 = dict(c, sort_count=sort_count)
+            out, ms = e.sort(c["mvp"], sort_count, c["render_count"], c["indexes"], transforms=c["transforms"])
+            assert np.array_equal(out, _expect(oracle_mod, c2, R))
+            assert ms > 0
+        t = e.timings()
+        assert t["kernel_launches"] >= 4
+
+
+def test_identity_fast_path_and_precomputed(gs, oracle_mod):
+    n = 300_000
+    c = cases.sort_case(seed=21, n=n, index_kind="identity")
+    with gs.Engine(n) as e:
+        e.upload_centers(c["centers"])
+        out, _ = e.sort(c["mvp"], n, n, None)          # NULL indexes = identity (Viewer.js:2061-2074)
+        assert np.array_equal(out, _expect(oracle_mod, c, 1 << 16))
+        # D1 + usePrecomputedDistances branch: integer rows are Math.round of the f64 matrix
+        mvp64 = c["mvp"].astype(np.float64)
+        d = e.compute_distances(mvp64, n)
+        rows = np.floor(mvp64[[2, 6, 10]] * 1000.0 + 0.5).astype(np.int64)
+        want_d = (c["centers"][:, :3].astype(np.int64) * rows).sum(1)
+        want_d = ((want_d + 2**31) % 2**32 - 2**31).astype(np.int32)
+        assert np.array_equal(d, want_d)
+        out2, _ = e.sort(c["mvp"], n, n, None, precomputed=d)
+        c3 = dict(c, precomputed=d, use_precomputed=True)
+        assert np.array_equal(out2, _expect(oracle_mod, c3, 1 << 16))
+
+
+@pytest.mark.parametrize("n", [1_000_000, 16_000_000])
+def test_full_size_properties(gs, oracle_mod, n):
+    """BASELINE sizes: permutation, monotone buckets, reverse-stable ties; 1M is also diffed against the oracle."""
+    c = cases.sort_case(seed=10, n=n, index_kind="shuffled" if n <= 1_000_000 else "identity")
+    R = 1 << 16
+    with gs.Engine(n) as e:
+        e.upload_centers(c["centers"])
+        out, ms = e.sort(c["mvp"], n, n, c["indexes"])
+    assert np.array_equal(np.sort(out), np.arange(n, dtype=np.uint32)), "not a permutation"
+    # recompute buckets independently (numpy, int64 wrap) and check the ordering contract
+    m = c["mvp"]
+    rows = np.array([int(np.float64(m[2]) * 1000.0), int(np.float64(m[6]) * 1000.0), int(np.float64(m[10]) * 1000.0)], np.int64)
+    d = (c["centers"][:, :3].astype(np.int64) * rows).sum(1)
+    d = ((d + 2**31) % 2**32 - 2**31).astype(np.int32)
+    dmin, dmax = int(d.min()), int(d.max())
+    rm = np.float32(R - 1) / (np.float32(dmax) - np.float32(dmin))
+    b = ((d.astype(np.int64) - dmin).astype(np.float32) * rm).astype(np.int32)
+    bs = b[out]
+    assert np.all(np.diff(bs) <= 0), "buckets must be non-increasing (back to front)"
+    pos = np.empty(n, np.int64)
+    pos[c["indexes"]] = np.arange(n)
+    same = np.diff(bs) == 0
+    assert np.all(np.diff(pos[out])[same] < 0), "equal buckets must come in descending input position"
+    if n <= 1_000_000:
+        assert np.array_equal(out, _expect(oracle_mod, c, R))
+
+
+def test_edge_cases(gs, oracle_mod):
+    # single splat and all-equal distances: the reference traps (NaN bucket); we define bucket 0 -> reversed input order
+    c = cases.sort_case(seed=1, n=1)
+    assert np.array_equal(gs.sort_indexes(*cases.call_args(c, 1 << 16)), c["indexes"])
+    n = 5000
+    c = cases.sort_case(seed=2, n=n)
+    c["centers"][:] = c["centers"][0]
+    got = gs.sort_indexes(*cases.call_args(c, 1 << 16))
+    assert np.array_equal(got, c["indexes"][::-1])
+    # sortCount = 0: pure copy-through
+    c = cases.sort_case(seed=3, n=1000, sort_frac=0.0)
+    assert np.array_equal(gs.sort_indexes(*cases.call_args(c, 1 << 16)), c["indexes"])
+    # bad arguments are reported, not executed
+    with pytest.raises(gs.GsError):
+        gs.sort_indexes(c["indexes"], c["centers"], None, c["mvp"], None, None, 1 << 16, 2000, 1000, 1000, False, True, False)

@@ -1,0 +1,252 @@
+"""Host-side mirror of the slice of the reference's Viewer / SplatMesh that drives the hot path.
+
+    SplatMesh.build(...)                  src/splatmesh/SplatMesh.js:306-405    -> SplatMesh.build
+    SplatMesh.getIntegerCenters/Float...  :1912-1948                            -> SplatMesh.getIntegerCenters / getFloatCenters
+    SplatMesh.updateRenderIndexes         :1228-1235                            -> SplatMesh.updateRenderIndexes
+    SplatMesh.updateUniforms              :1248-1280                            -> SplatMesh.updateUniforms
+    Viewer.runSplatSort                   src/Viewer.js:1833-1964               -> Viewer.runSplatSort
+    Viewer.updateSplatMesh                :651-677                              -> Viewer.updateSplatMesh
+    Viewer.render                         :1599-1623                            -> Viewer.render
+    Viewer.update                         :1625-1644                            -> Viewer.update
+
+Only the arithmetic-free orchestration lives here (matrix set-up in float64 like three.js, message passing, option
+bag).  Sorting and rasterisation run in libgsplat_b200.so through Engine / SortWorker.  Everything the reference does
+around the path (loading UI, controls, octree culling, WebXR ...) is out of scope.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _native as N
+from . import three_math as TM
+from .engine import Engine, Uniforms
+from .scenes import PackedScene, RawScene, float_centers, integer_centers, pack_scene
+from .sort_worker import DefaultSplatSortDistanceMapPrecision, createSortWorker, start
+
+THREE_CAMERA_FOV = 50  # Viewer.js:30
+
+
+class SplatMesh:
+    """Owns the GPU-side splat data of one (static) scene and the uniforms of the splat material."""
+
+    def __init__(self, *, dynamicMode=False, halfPrecisionCovariancesOnGPU=False, devicePixelRatio=1.0, antialiased=False,
+                 maxScreenSpaceSplatSize=1024, splatScale=1.0, pointCloudModeEnabled=False, sphericalHarmonicsDegree=0,
+                 kernel2DSize=0.3, enableOptionalEffects=False):
+        self.dynamicMode = dynamicMode
+        self.halfPrecisionCovariancesOnGPU = halfPrecisionCovariancesOnGPU
+        self.devicePixelRatio = devicePixelRatio
+        self.antialiased = antialiased
+        self.maxScreenSpaceSplatSize = maxScreenSpaceSplatSize
+        self.splatScale = splatScale
+        self.pointCloudModeEnabled = pointCloudModeEnabled
+        self.sphericalHarmonicsDegree = sphericalHarmonicsDegree
+        self.kernel2DSize = kernel2DSize
+        self.enableOptionalEffects = enableOptionalEffects
+        self.matrixWorld = TM.identity()
+        self.packed: PackedScene | None = None
+        self.raw: RawScene | None = None
+        self.uniforms: dict = {}
+        self.renderIndexes: np.ndarray | None = None
+        self.instanceCount = 0
+        self.engine: Engine | None = None
+        self.visibleRegionFadeStartRadius = 0.0
+        self.fadeInComplete = True
+        self.sceneCenter = (0.0, 0.0, 0.0)
+
+    def build(self, raw_scene: RawScene, *, sh_format: str = "f16") -> None:
+        """Decode + pack the scene like refreshGPUDataFromSplatBuffers (SplatMesh.js:588-603) and keep it for upload."""
+        self.raw = raw_scene
+        degree = min(self.sphericalHarmonicsDegree, raw_scene.sh_degree)
+        if degree < raw_scene.sh_degree:  # minSphericalHarmonicsDegree clamp (SplatMesh.js:680-683)
+            ncoef = 0 if degree == 0 else (3 if degree == 1 else 8)
+            raw_scene = RawScene(raw_scene.centers, raw_scene.scales, raw_scene.rotations, raw_scene.colors,
+                                 None if degree == 0 else raw_scene.sh[:, :ncoef], degree)
+        self.packed = pack_scene(raw_scene, half_covariances=self.halfPrecisionCovariancesOnGPU, sh_format=sh_format)
+
+    def getSplatCount(self) -> int:  # noqa: N802
+        return 0 if self.packed is None else self.packed.count
+
+    def getIntegerCenters(self, start: int, end: int, padFour: bool = False) -> np.ndarray:  # noqa: N802,N803
+        c = integer_centers(self.raw.centers[start:end + 1])
+        return c if padFour else c[:, :3].copy()
+
+    def getFloatCenters(self, start: int, end: int, padFour: bool = False) -> np.ndarray:  # noqa: N802,N803
+        c = float_centers(self.raw.centers[start:end + 1])
+        return c if padFour else c[:, :3].copy()
+
+    def setRenderer(self, engine: Engine) -> None:  # noqa: N802
+        """The WebGL renderer of the reference (SplatMesh.js:1300-1340) becomes the CUDA engine; uploads the 'textures'."""
+        self.engine = engine
+        p = self.packed
+        engine.upload_splat_data(p.centers_colors, p.covariances, p.sh, p.sh_degree)
+
+    def updateRenderIndexes(self, globalIndexes: np.ndarray | None, renderSplatCount: int) -> None:  # noqa: N802,N803
+        """SplatMesh.js:1228-1235.  globalIndexes None = keep the order the engine's last sort left on the device."""
+        self.renderIndexes = globalIndexes
+        self.instanceCount = int(renderSplatCount)
+
+    def updateUniforms(self, renderDimensions, cameraFocalLengthX, cameraFocalLengthY, orthographicMode, orthographicZoom,  # noqa: N802,N803
+                       inverseFocalAdjustment) -> None:
+        vw, vh = renderDimensions[0] * self.devicePixelRatio, renderDimensions[1] * self.devicePixelRatio
+        self.uniforms.update(viewport=(vw, vh), basisViewport=(1.0 / vw, 1.0 / vh), focal=(cameraFocalLengthX, cameraFocalLengthY),
+                             orthographicMode=1 if orthographicMode else 0, orthoZoom=orthographicZoom,
+                             inverseFocalAdjustment=inverseFocalAdjustment)
+
+
+class Viewer:
+    """Frame loop of the reference's Viewer reduced to the hot path: update() -> runSplatSort + updateSplatMesh, render()."""
+
+    def __init__(self, options: dict | None = None):
+        o = dict(options or {})
+        self.cameraUp = np.asarray(o.get("cameraUp", (0, 1, 0)), np.float64)            # Viewer.js:51
+        self.initialCameraPosition = np.asarray(o.get("initialCameraPosition", (0, 10, 15)), np.float64)
+        self.initialCameraLookAt = np.asarray(o.get("initialCameraLookAt", (0, 0, 0)), np.float64)
+        self.renderWidth = int(o.get("width", 1920))
+        self.renderHeight = int(o.get("height", 1080))
+        self.devicePixelRatio = float(o.get("devicePixelRatio", 1.0))
+        self.gpuAcceleratedSort = bool(o.get("gpuAcceleratedSort", False))                  # Viewer.js:90
+        self.integerBasedSort = bool(o.get("integerBasedSort", True))                       # Viewer.js:95-98
+        self.sharedMemoryForWorkers = bool(o.get("sharedMemoryForWorkers", True))
+        self.enableSIMDInSort = bool(o.get("enableSIMDInSort", True))
+        self.dynamicScene = bool(o.get("dynamicScene", False))
+        self.antialiased = bool(o.get("antialiased", False))
+        self.kernel2DSize = float(o.get("kernel2DSize", 0.3))
+        self.sphericalHarmonicsDegree = int(o.get("sphericalHarmonicsDegree", 0))
+        self.focalAdjustment = float(o.get("focalAdjustment", 1.0))
+        self.maxScreenSpaceSplatSize = float(o.get("maxScreenSpaceSplatSize", 1024))
+        self.halfPrecisionCovariancesOnGPU = bool(o.get("halfPrecisionCovariancesOnGPU", False))
+        prec = int(o.get("splatSortDistanceMapPrecision", DefaultSplatSortDistanceMapPrecision))
+        self.splatSortDistanceMapPrecision = int(np.clip(prec, 10, 20 if self.integerBasedSort else 24))  # Viewer.js:207-210
+        self.device = int(o.get("device", 0))
+        self.rank, self.world_size = int(o.get("rank", 0)), int(o.get("world_size", 1))
+        self.camera = TM.PerspectiveCamera(THREE_CAMERA_FOV, self.renderWidth / self.renderHeight, 0.1, 1000)  # Viewer.js:338
+        self.camera.position = self.initialCameraPosition.copy()
+        self.camera.up = self.cameraUp / np.linalg.norm(self.cameraUp)
+        self.camera.look_at(self.initialCameraLookAt)
+        self.splatMesh: SplatMesh | None = None
+        self.engine: Engine | None = None
+        self.sortWorker = None
+        self.sortRunning = False
+        self.splatRenderCount = 0
+        self.splatSortCount = 0
+        self.lastSortTime = 0.0
+        self.sortWorkerIndexesToSort: np.ndarray | None = None
+        self.sortWorkerSortedIndexes: np.ndarray | None = None
+        self._sorted_on_device = False
+
+    # -- scene set-up (addSplatBuffers / setupSortWorker, Viewer.js:1094-1300) ------------------------------------------------
+    def addSplatScene(self, raw_scene: RawScene, *, separate_sort_worker: bool = False) -> None:  # noqa: N802
+        self.splatMesh = SplatMesh(dynamicMode=self.dynamicScene, halfPrecisionCovariancesOnGPU=self.halfPrecisionCovariancesOnGPU,
+                                   devicePixelRatio=self.devicePixelRatio, antialiased=self.antialiased,
+                                   maxScreenSpaceSplatSize=self.maxScreenSpaceSplatSize, sphericalHarmonicsDegree=self.sphericalHarmonicsDegree,
+                                   kernel2DSize=self.kernel2DSize)
+        self.splatMesh.build(raw_scene)
+        n = self.splatMesh.getSplatCount()
+        self.engine = Engine(n, device=self.device, distance_map_range=1 << self.splatSortDistanceMapPrecision,
+                             integer_based_sort=self.integerBasedSort, dynamic_mode=self.dynamicScene,
+                             max_width=self.renderWidth, max_height=self.renderHeight, rank=self.rank, world_size=self.world_size)
+        self.splatMesh.setRenderer(self.engine)
+        centers = (self.splatMesh.getIntegerCenters(0, n - 1, True) if self.integerBasedSort else self.splatMesh.getFloatCenters(0, n - 1, True))
+        if separate_sort_worker:
+            # the reference's topology: a worker with its own memory, sorted indexes travel back through the host
+            self.sortWorker = createSortWorker(n, self.sharedMemoryForWorkers, self.enableSIMDInSort, self.integerBasedSort,
+                                               self.dynamicScene, self.splatSortDistanceMapPrecision, device=self.device)
+            self.sortWorker.onmessage = self._on_worker_message
+            start(self.sortWorker)
+            self.sortWorker.postMessage({"centers": centers, "sceneIndexes": None, "range": {"from": 0, "to": n - 1, "count": n}})
+        else:
+            self.engine.upload_centers(centers)
+        self.splatRenderCount = n
+
+    def _on_worker_message(self, e) -> None:  # Viewer.js:1243-1298
+        d = e.data
+        if d.get("sortDone"):
+            self.sortRunning = False
+            self.lastSortTime = d["sortTime"]
+            sorted_idx = self.sortWorkerSortedIndexes if self.sharedMemoryForWorkers else d["sortedIndexes"]
+            self.splatMesh.updateRenderIndexes(sorted_idx[: d["splatRenderCount"]], d["splatRenderCount"])
+        elif d.get("sortSetupPhase1Complete"):
+            if self.sharedMemoryForWorkers:
+                self.sortWorkerIndexesToSort = d["indexesToSortBuffer"]
+                self.sortWorkerSortedIndexes = d["sortedIndexesBuffer"]
+                self.sortWorkerIndexesToSort[:] = np.arange(self.sortWorkerIndexesToSort.shape[0], dtype=np.uint32)  # Viewer.js:1282-1284
+
+    # -- matrices ----------------------------------------------------------------------------------------------------------------
+    def mvp_matrix(self) -> np.ndarray:
+        """Viewer.js:1888-1891 in float64: projection * inverse(camera.matrixWorld) * splatMesh.matrixWorld."""
+        m = TM.invert(self.camera.matrixWorld)
+        m = TM.multiply(self.camera.projectionMatrix, m)
+        if not self.splatMesh.dynamicMode:
+            m = TM.multiply(m, self.splatMesh.matrixWorld)
+        return m
+
+    def updateSplatMesh(self) -> None:  # noqa: N802  Viewer.js:651-677
+        w, h = self.renderWidth, self.renderHeight
+        fx = self.camera.projectionMatrix[0] * 0.5 * self.devicePixelRatio * w
+        fy = self.camera.projectionMatrix[5] * 0.5 * self.devicePixelRatio * h
+        fa = self.focalAdjustment * (1.0 / self.devicePixelRatio if self.camera.isOrthographicCamera else 1.0)
+        self.splatMesh.updateUniforms((w, h), fx * fa, fy * fa, self.camera.isOrthographicCamera, self.camera.zoom or 1.0, 1.0 / fa)
+
+    def uniforms(self) -> Uniforms:
+        """What three.js + SplatMesh hand the splat shaders for the current camera."""
+        sm = self.splatMesh
+        mv = TM.multiply(self.camera.matrixWorldInverse, sm.matrixWorld)
+        u = sm.uniforms
+        return Uniforms(model_view=mv.astype(np.float32), projection=self.camera.projectionMatrix.astype(np.float32),
+                        camera_position=np.asarray(self.camera.position, np.float32), focal=u["focal"], viewport=u["viewport"],
+                        inverse_focal_adjustment=u["inverseFocalAdjustment"], ortho_zoom=u["orthoZoom"], orthographic_mode=u["orthographicMode"],
+                        splat_scale=sm.splatScale, point_cloud_mode=1 if sm.pointCloudModeEnabled else 0,
+                        sh_degree=sm.packed.sh_degree, antialiased=1 if sm.antialiased else 0, kernel_2d_size=sm.kernel2DSize,
+                        max_screen_space_splat_size=sm.maxScreenSpaceSplatSize, fade_in_complete=1 if sm.fadeInComplete else 0,
+                        scene_center=sm.sceneCenter, visible_region_fade_start_radius=sm.visibleRegionFadeStartRadius)
+
+    # -- the per-frame path --------------------------------------------------------------------------------------------------------
+    def runSplatSort(self, force: bool = False, forceSortAll: bool = True) -> bool:  # noqa: N802,N803  Viewer.js:1833-1964
+        """Full sort of all splats (gatherSceneNodesForSort's shouldSortAll case, Viewer.js:2061-2074); the partial-sort
+        queue and the octree gather are out of scope."""
+        del force, forceSortAll
+        if self.sortRunning:
+            return True
+        n = self.splatMesh.getSplatCount()
+        if n <= 0:
+            self.splatRenderCount = 0
+            return False
+        self.splatRenderCount = self.splatSortCount = n
+        mvp = self.mvp_matrix()
+        if self.sortWorker is not None:
+            self.sortRunning = True
+            msg = {"modelViewProj": mvp.astype(np.float32), "cameraPosition": list(self.camera.position), "splatRenderCount": n,
+                   "splatSortCount": n, "usePrecomputedDistances": False}
+            if not self.sharedMemoryForWorkers:
+                msg["indexesToSort"] = np.arange(n, dtype=np.uint32)
+                msg["transforms"] = None
+            self.sortWorker.postMessage({"sort": msg})
+        else:
+            _, ms = self.engine.sort(mvp.astype(np.float32), n, n, None, download=False)
+            self.lastSortTime = ms
+            self.splatMesh.updateRenderIndexes(None, n)
+        return True
+
+    def update(self) -> None:  # Viewer.js:1625-1644
+        self.camera.update()
+        self.runSplatSort()
+        self.updateSplatMesh()
+
+    def render(self, *, frame_format: int = N.GS_FRAME_RGBA8, flip_y: bool = True, download: bool = True):  # Viewer.js:1599-1623
+        sm = self.splatMesh
+        return self.engine.render(self.uniforms(), self.renderWidth, self.renderHeight, sm.instanceCount, sm.renderIndexes,
+                                  frame_format=frame_format, flip_y=flip_y, download=download)
+
+    def frame(self, *, frame_format: int = N.GS_FRAME_RGBA8, flip_y: bool = True, download: bool = True, frame_out=None):
+        """update() + render() fused into one engine call (sort order never leaves the device)."""
+        self.camera.update()
+        self.updateSplatMesh()
+        n = self.splatMesh.getSplatCount()
+        return self.engine.frame(self.mvp_matrix().astype(np.float32), self.uniforms(), self.renderWidth, self.renderHeight, n, None,
+                                 frame_format=frame_format, flip_y=flip_y, download=download, frame_out=frame_out)
+
+    def dispose(self) -> None:
+        if self.sortWorker is not None:
+            self.sortWorker.terminate()
+        if self.engine is not None:
+            self.engine.close()

@@ -1,0 +1,366 @@
+#!/usr/bin/env python
+"""bench.py -- the depth -> sort -> rasterise hot path on N B200s (BASELINE.json metric: frames/s and sorted
+Msplats/s at 1920x1080; HBM GB/s against the measured roofline).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload bonsai|garden|synth16m]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one viewer frame: full depth sort of every splat + projection + tile binning + front-to-back blend into an
+RGBA8 1920x1080 frame (Viewer.update + Viewer.render of the reference).  Prints ONE JSON line on rank 0.
+
+value   device-timed (CUDA events on the engine's stream), scene resident in HBM, L2 flushed between steps.
+e2e     the same frame through the C ABI with HOST buffers: indexesToSort + camera uniforms go host->device from pinned
+        memory, the RGBA8 frame comes back device->host, all inside the timed region.
+N > 1   strong scaling of ONE frame: rank r rasterises tile rows r, r+N, ...; every rank sorts (replicated scene, no
+        splat exchange); the finished strips are all-gathered with NCCL (the only collective).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+WORKLOADS = {
+    # name: (splats, sh_degree, kind, seed, camera, width, height)   -- BASELINE.json configs[1], [2], [3]
+    "bonsai": (1_200_000, 0, "bonsai", 1, "bonsai", 1920, 1080),
+    "garden": (5_800_000, 2, "garden", 2, "garden", 1920, 1080),
+    "synth16m": (16_000_000, 0, "bonsai", 3, "bonsai", 3840, 2160),
+    "tiny": (100_000, 0, "uniform", 0, "default", 640, 360),
+}
+SH_BYTES = {0: 0, 1: 18, 2: 48}
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled every 200 ms while the timed regions run."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                pass
+        sm, mx, reasons = [], 0.0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = max(mx, float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_viewer(workload: str, rank: int, world: int, device: int):
+    from gaussiansplats3d_b200.scenes import CAMERAS, synthetic_scene
+    from gaussiansplats3d_b200.viewer import Viewer
+    n, sh, kind, seed, cam, w, h = WORKLOADS[workload]
+    raw = synthetic_scene(n, seed=seed, kind=kind, sh_degree=sh)
+    c = CAMERAS[cam]
+    v = Viewer(dict(cameraUp=c["up"], initialCameraPosition=c["position"], initialCameraLookAt=c["look_at"], width=w, height=h,
+                    sphericalHarmonicsDegree=sh, device=device, rank=rank, world_size=world))
+    v.addSplatScene(raw)
+    v.camera.update()
+    v.updateSplatMesh()
+    return v, raw
+
+
+# ------------------------------------------------------------------------------------------------------------------------------
+def cpu_frame_seconds(workload: str, repeats: int, threads: int | None = None):
+    """The reference's CPU path for one frame: its own sorter (oracle/_ref, single-threaded like its one Web Worker; the C
+    restatement when the compiled reference is absent) + the CPU restatement of its shaders/blend (all cores, OpenMP)."""
+    import oracle
+    from gaussiansplats3d_b200 import three_math as TM
+    from gaussiansplats3d_b200.engine import Uniforms
+    from gaussiansplats3d_b200.scenes import CAMERAS, pack_scene, synthetic_scene
+    oracle.build()
+    n, sh, kind, seed, cam, w, h = WORKLOADS[workload]
+    raw = synthetic_scene(n, seed=seed, kind=kind, sh_degree=sh)
+    p = pack_scene(raw)
+    c = CAMERAS[cam]
+    camera = TM.PerspectiveCamera(50, w / h, 0.1, 1000)
+    camera.position = np.asarray(c["position"], np.float64)
+    camera.up = np.asarray(c["up"], np.float64) / np.linalg.norm(c["up"])
+    camera.look_at(c["look_at"])
+    mvp = TM.multiply(camera.projectionMatrix, camera.matrixWorldInverse).astype(np.float32)
+    u = Uniforms(model_view=camera.matrixWorldInverse.astype(np.float32), projection=camera.projectionMatrix.astype(np.float32),
+                 camera_position=camera.position.astype(np.float32), focal=(camera.projectionMatrix[0] * 0.5 * w, camera.projectionMatrix[5] * 0.5 * h),
+                 viewport=(w, h), sh_degree=p.sh_degree)
+    idx = np.arange(n, dtype=np.uint32)
+    kind_used = "reference" if oracle.have_ref() else "port"
+    sorter = oracle.ref_sort_indexes if oracle.have_ref() else oracle.port_sort_indexes
+    sort_s, frame_s = [], []
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        order = sorter(idx, p.int_centers, None, mvp, None, None, 1 << 16, n, n, n, False, True, False)
+        t1 = time.perf_counter()
+        oracle.render(u, p.centers_colors, p.covariances, order, w, h, sh=p.sh, sh_degree=p.sh_degree)
+        t2 = time.perf_counter()
+        sort_s.append(t1 - t0)
+        frame_s.append(t2 - t0)
+    return dict(n=n, sort_s=sort_s, frame_s=frame_s, sort_kind=kind_used, cores=os.cpu_count() or 1)
+
+
+def run_reference(args):
+    """--impl reference: the CPU path timed on the box's host cores; rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n, sh, kind, seed, cam, w, h = WORKLOADS[args.workload]
+    res = cpu_frame_seconds(args.workload, args.warmup + args.steps)
+    fs = res["frame_s"][args.warmup:]
+    ss = res["sort_s"][args.warmup:]
+    total = float(np.sum(fs))
+    value = len(fs) / total
+    line = {
+        "impl": "reference", "metric": "frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": args.gpus, "steps": len(fs),
+        "warmup": args.warmup, "ms_per_step": 1000.0 * total / len(fs), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "int32 sort keys / f32 raster", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {n} splats SH{sh} {w}x{h} fixed camera (synthetic stand-in, seed {seed})"},
+        "sorted_msplats_per_sec": n / float(np.mean(ss)) / 1e6,
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": res["cores"], "kind": "port" if res["sort_kind"] == "port" else "reference",
+                         "sample": f"{len(fs)} full frames: depth sort by the reference's own sorter_no_simd.cpp compiled natively ({res['sort_kind']}, 1 thread) + "
+                                   f"CPU restatement of its shaders/blend (port, OpenMP {res['cores']} threads); the WASM + WebGL path itself cannot run here"},
+        "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------------------------
+def algorithmic_bytes(kernel: str, n: int, sh: int, w: int, h: int, instances: int, visible: int) -> float | None:
+    """Compulsory HBM bytes per launch (DESIGN.md 'Kernels').  None = not an HBM-stream kernel."""
+    table = {
+        "k_depth": n * (16 + 4),                     # int32x4 centre in, distance out (identity indexes)
+        "k_bucket": n * (4 + 2),                     # distance in, 16-bit key out
+        "k_radix_pass[depth,0]": n * (2 + 2 + 4),    # key in, key + index out
+        "k_radix_pass[depth,1]": n * (2 + 4 + 4),    # key + index in, index out
+        "k_project": n * (16 + 24 + SH_BYTES[sh]) + n * (48 + 8),
+        "k_tile_count": n * (4 + 8 + 4),
+        "k_tile_emit": n * (4 + 8 + 4) + instances * 6,
+        "k_radix_pass[tile,0]": instances * 12,
+        "k_radix_pass[tile,1]": instances * 12,
+        "k_tile_ranges": instances * 2,
+        "k_blend": instances * 4 + visible * 48 + w * h * 4,
+    }
+    return float(table[kernel]) if kernel in table else None
+
+
+def run_ours(args):
+    import gaussiansplats3d_b200 as gs
+    from gaussiansplats3d_b200 import _native as N
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    torch = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if args.gpus != world and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+
+    K, W = args.steps, max(args.warmup, 3)
+    n, sh, kind, seed, cam, width, height = WORKLOADS[args.workload]
+    v, raw = build_viewer(args.workload, rank, world, local)
+    e = v.engine
+    mvp = v.mvp_matrix().astype(np.float32)
+    prepared = e.prepare_frame(mvp, v.uniforms(), width, height, n, frame_format=N.GS_FRAME_RGBA8, flip_y=True)
+
+    gather = None
+    if world > 1:
+        from gaussiansplats3d_b200.parallel import TileGather
+        gather = TileGather(e, width, height, rank, world, fmt=N.GS_FRAME_RGBA8)
+
+    def step_async():
+        e.frame_async(None, None, width, height, n, prepared=prepared)
+        if gather is not None:
+            gather.all_gather()
+
+    def barrier():
+        e.synchronize()
+        if dist is not None:
+            torch.cuda.synchronize()
+            dist.barrier()
+
+    sampler = ClockSampler(local)
+    for _ in range(W):
+        step_async()
+    barrier()
+    sampler.start()
+
+    # ---- value: device time, scene resident, L2 flushed before every step ----------------------------------------------
+    ev0 = [e.event() for _ in range(K)]
+    ev1 = [e.event() for _ in range(K)]
+    launches = 0
+    barrier()
+    for i in range(K):
+        e.flush_l2()
+        ev0[i].record()
+        step_async()
+        ev1[i].record()
+    barrier()
+    launches = e.timings()["kernel_launches"] * K
+    step_ms = np.array([ev0[i].elapsed_ms(ev1[i]) for i in range(K)])
+    total_ms = float(step_ms.sum())
+    if dist is not None:
+        t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    fps = K / (total_ms / 1000.0)
+
+    # ---- per-kernel timeline (same region, profiling events on) --------------------------------------------------------------
+    e.set_profiling(True)
+    acc: dict[str, list[float]] = {}
+    for i in range(K):
+        e.flush_l2()
+        step_async()
+        e.synchronize()
+        for name, ms in e.kernel_timings():
+            acc.setdefault(name, []).append(ms)
+    e.set_profiling(False)
+    tm = e.timings()
+    kernels = {k: float(np.mean(vv)) for k, vv in acc.items()}
+    frame_kernel_ms = float(sum(kernels.values()))
+    sort_ms = sum(ms for k, ms in kernels.items() if k in ("k_sort_init", "k_depth", "k_bucket") or k.startswith("k_radix_pass[depth"))
+    dominant = max(kernels, key=kernels.get)
+    peak, peak_src = peaks()
+    inst, vis = int(tm["tile_instances"]), int(tm["visible_splats"])
+    ab = algorithmic_bytes(dominant, n, sh, width, height, inst, vis)
+    achieved = (ab / (kernels[dominant] * 1e-3) / 1e9) if ab else None
+    path_bytes = n * (44 + SH_BYTES[sh]) + width * height * 4       # per rendered splat + framebuffer
+    sort_bytes = n * 24                                             # 16 B centre + 4 B index in + 4 B index out
+
+    # ---- e2e: C ABI with host buffers (pinned), copies inside the timed region -----------------------------------------------------
+    e2e = None
+    if world == 1:
+        idx_host = N.pinned_empty(n, np.uint32)
+        idx_host[:] = np.arange(n, dtype=np.uint32)
+        frame_host = N.pinned_empty((height, width, 4), np.uint8)
+        sp = e._sort_params(mvp, n, n, idx_host, None, None)
+        prepared_host = (sp, prepared[1], prepared[2])
+        for _ in range(W):
+            e.frame_prepared(prepared_host, frame_host)
+        t_e2e = []
+        for i in range(K):
+            e.flush_l2()
+            e.synchronize()
+            t0 = time.perf_counter()
+            e.frame_prepared(prepared_host, frame_host)     # H2D indexes + params, sort, render, D2H frame, sync
+            t_e2e.append(time.perf_counter() - t0)
+        e2e = {"value": K / float(np.sum(t_e2e)), "unit": "frames/s", "h2d_bytes_per_step": int(n * 4 + 64 + 3000),
+               "d2h_bytes_per_step": int(width * height * 4), "ms_per_step": 1000.0 * float(np.mean(t_e2e))}
+    else:
+        # N GPUs: the frame is assembled on every rank by the NCCL gather; rank 0 copies it to pinned host memory
+        frame_host = None
+        if rank == 0:
+            frame_host = torch.empty((gather.padded_rows * world, width, 4), dtype=torch.uint8).pin_memory()
+        t_e2e = []
+        for i in range(W + K):
+            e.flush_l2()
+            barrier()
+            t0 = time.perf_counter()
+            step_async()
+            gather.sync_to_torch()
+            if rank == 0:
+                frame_host.copy_(gather.gathered.view(-1, width, 4), non_blocking=True)
+            torch.cuda.synchronize()
+            dt = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            if i >= W:
+                t_e2e.append(float(dt.item()))
+        e2e = {"value": K / float(np.sum(t_e2e)), "unit": "frames/s", "h2d_bytes_per_step": int(64 + 3000),
+               "d2h_bytes_per_step": int(width * height * 4), "ms_per_step": 1000.0 * float(np.mean(t_e2e))}
+
+    clocks = sampler.stop()
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only; bounded sample) ---------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        res = cpu_frame_seconds(args.workload, 3)
+        cpu = {"value": 1.0 / float(np.min(res["frame_s"])), "unit": "frames/s", "cores": res["cores"],
+               "kind": "port" if res["sort_kind"] == "port" else "reference",
+               "sample": f"best of 3 full frames of the same workload: sort = reference sorter_no_simd.cpp compiled natively ({res['sort_kind']}, 1 thread, "
+                         f"{n / float(np.min(res['sort_s'])) / 1e6:.1f} Msplats/s), raster = CPU restatement of the reference shaders (port, OpenMP {res['cores']} threads)",
+               "sort_msplats_per_sec": n / float(np.min(res["sort_s"])) / 1e6}
+
+    if rank == 0:
+        line = {
+            "metric": "frames_per_sec", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "int32 sort keys / f32 raster", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {n} splats SH{sh} {width}x{height} fixed camera (synthetic stand-in for the .ksplat, seed {seed})",
+                       "l2": "flushed between steps (192 MiB write)", "parallelism": f"tile-row interleave x{world}" if world > 1 else "single GPU",
+                       "distance_map_range": 65536},
+            "sorted_msplats_per_sec": n / (sort_ms * 1e-3) / 1e6 if sort_ms > 0 else None,
+            "sort_ms": sort_ms, "kernel_ms": kernels, "tile_instances": inst, "visible_splats": vis,
+            "roofline": {"kernel": dominant, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
+                         "traffic": None, "peak_source": peak_src, "launch_ms": kernels[dominant]},
+            "path_roofline": {"bound": "hbm", "frame_bytes": path_bytes, "frame_gbs": path_bytes / (frame_kernel_ms * 1e-3) / 1e9,
+                              "frame_frac": path_bytes / (frame_kernel_ms * 1e-3) / 1e9 / peak,
+                              "sort_bytes": sort_bytes, "sort_gbs": sort_bytes / (sort_ms * 1e-3) / 1e9 if sort_ms else None,
+                              "sort_frac": sort_bytes / (sort_ms * 1e-3) / 1e9 / peak if sort_ms else None},
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    v.dispose()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="bonsai", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -102,11 +102,16 @@ class gs_timings(C.Structure):
         return {n: getattr(self, n) for n, _ in self._fields_}
 
 
+class gs_kernel_time(C.Structure):
+    _fields_ = [("name", C.c_char * 40), ("ms", C.c_float)]
+
+
 EXPORTED_SYMBOLS = [
     "gs_abi_version", "gs_status_string", "gs_last_error_message", "gs_device_count", "gs_sort_indexes", "sortIndexes",
     "gs_create", "gs_destroy", "gs_upload_centers", "gs_sort", "gs_compute_distances", "gs_upload_splat_data",
     "gs_render", "gs_frame", "gs_buffer_dev", "gs_stream", "gs_synchronize", "gs_host_alloc", "gs_host_free",
-    "gs_read_projected", "gs_last_timings",
+    "gs_read_projected", "gs_last_timings", "gs_frame_async", "gs_flush_l2", "gs_event_create", "gs_event_record",
+    "gs_event_elapsed_ms", "gs_event_destroy", "gs_set_profiling", "gs_kernel_timings",
 ]
 
 _lib = None
@@ -165,6 +170,22 @@ def load() -> C.CDLL:
     lib.gs_read_projected.argtypes = [vp, vp, u32]
     lib.gs_last_timings.restype = C.c_int
     lib.gs_last_timings.argtypes = [vp, C.POINTER(gs_timings)]
+    lib.gs_frame_async.restype = C.c_int
+    lib.gs_frame_async.argtypes = [vp, C.POINTER(gs_sort_params), C.POINTER(gs_uniforms), C.POINTER(gs_render_params)]
+    lib.gs_flush_l2.restype = C.c_int
+    lib.gs_flush_l2.argtypes = [vp]
+    lib.gs_event_create.restype = C.c_int
+    lib.gs_event_create.argtypes = [C.POINTER(vp)]
+    lib.gs_event_record.restype = C.c_int
+    lib.gs_event_record.argtypes = [vp, vp]
+    lib.gs_event_elapsed_ms.restype = C.c_int
+    lib.gs_event_elapsed_ms.argtypes = [vp, vp, C.POINTER(C.c_float)]
+    lib.gs_event_destroy.restype = C.c_int
+    lib.gs_event_destroy.argtypes = [vp]
+    lib.gs_set_profiling.restype = C.c_int
+    lib.gs_set_profiling.argtypes = [vp, C.c_int]
+    lib.gs_kernel_timings.restype = C.c_int
+    lib.gs_kernel_timings.argtypes = [vp, C.POINTER(gs_kernel_time), u32, C.POINTER(u32)]
     _ = i32
     _lib = lib
     return lib

@@ -7,7 +7,27 @@
 // last error text of the calling host thread (defined in engine.cu)
 extern thread_local char g_gs_err[512];
 
+#include <vector>
+#include <string.h>
+
 namespace gs {
+
+// Optional per-kernel timeline: one CUDA event after every kernel launch (gs_set_profiling).  Durations are the gaps
+// between consecutive events on the engine's stream, i.e. device time of each kernel including its launch gap.
+struct Profiler {
+    bool on = false;
+    std::vector<cudaEvent_t> ev;
+    std::vector<const char *> names;
+    size_t used = 0;
+    void begin(cudaStream_t st) { used = 0; names.clear(); mark("<begin>", st); }
+    void mark(const char *name, cudaStream_t st) {
+        if (!on) return;
+        if (used == ev.size()) { cudaEvent_t e; cudaEventCreate(&e); ev.push_back(e); }
+        cudaEventRecord(ev[used++], st);
+        names.push_back(name);
+    }
+    void release() { for (auto e : ev) cudaEventDestroy(e); ev.clear(); used = 0; }
+};
 
 #define GS_MAX_SCENES_DEV 32 /* == GS_MAX_SCENES (power of two: used as a mask) */
 

@@ -120,6 +120,11 @@ struct gs_engine {
     RasterState rs;
 
     gs_timings tm{};
+    Profiler prof;
+    bool have_prof_begin = false;    // true while a frame's sort already opened the timeline
+    bool pending_async = false;
+    gs_render_params pending_rp{};
+    DevBuf<uint32_t> flush;          // L2 flush scratch (bench hygiene)
 };
 
 static int check_engine(gs_engine *e) {
@@ -182,7 +187,7 @@ extern "C" void gs_destroy(gs_engine *e) {
     e->centers.release(); e->scene_idx.release(); e->indexes.release(); e->precomputed.release(); e->dist.release();
     e->keys[0].release(); e->keys[1].release(); e->vals[0].release(); e->vals[1].release(); e->sorted.release();
     e->transforms.release(); e->ctl.release(); e->lookback.release(); e->freq.release();
-    e->h_indexes.release(); e->h_sorted.release(); e->h_ctl.release(); e->h_frame.release();
+    e->h_indexes.release(); e->h_sorted.release(); e->h_ctl.release(); e->h_frame.release(); e->flush.release(); e->prof.release();
     raster_release(e->rs);
     for (int i = 0; i < EV_COUNT; ++i) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
     if (e->stream) cudaStreamDestroy(e->stream);
@@ -211,6 +216,8 @@ static void launch_depth(bool identity, int blocks, cudaStream_t st, const uint3
 }
 
 // The sort proper, everything already on the device.  d_indexes == nullptr: identity.
+static const char *const depth_pass_names[4] = {"k_radix_pass[depth,0]", "k_radix_pass[depth,1]", "k_radix_pass[depth,2]", "k_radix_pass[depth,3]"};
+
 static int sort_on_device(gs_engine *e, const uint32_t *d_indexes, const float *mvp, uint32_t sort_count, uint32_t render_count,
                           bool use_pre, bool write_buckets) {
     if (sort_count > render_count) return fail(GS_ERR_BAD_ARG, "sortCount %u > renderCount %u", sort_count, render_count);
@@ -222,8 +229,10 @@ static int sort_on_device(gs_engine *e, const uint32_t *d_indexes, const float *
     int rc = e->lookback.ensure(radix_lookback_words(std::max(n, 1u), pl.npasses));
     if (rc) return rc;
     CU(cudaEventRecord(e->ev[EV_SORT0], st));
+    e->prof.begin(st);
     k_sort_init<<<std::max(1, e->sm_count), 256, 0, st>>>(e->ctl.p, e->lookback.p, radix_lookback_words(std::max(n, 1u), pl.npasses));
     ++launches;
+    e->prof.mark("k_sort_init", st);
     if (s0 > 0) { k_copy_head<<<std::min<uint32_t>((s0 + 255) / 256, e->sm_count * 8), 256, 0, st>>>(d_indexes, e->sorted.p, s0); ++launches; }
     if (n > 0) {
         DepthParams P{};
@@ -248,6 +257,7 @@ static int sort_on_device(gs_engine *e, const uint32_t *d_indexes, const float *
             default: launch_depth<kFloatPrecomputed>(identity, dblocks, st, d_indexes, e->centers.p, pre, e->scene_idx.p, e->transforms.p, P, s0, render_count, e->dist.p, e->ctl.p); break;
         }
         ++launches;
+        e->prof.mark("k_depth", st);
         CU(cudaEventRecord(e->ev[EV_DEPTH], st));
         const int bblocks = (int)std::min<uint64_t>(((uint64_t)n + kBucketThreads * kBucketItems - 1) / (kBucketThreads * kBucketItems), (uint64_t)e->sm_count * 8);
         const uint32_t R = e->cfg.distance_map_range;
@@ -256,15 +266,17 @@ static int sort_on_device(gs_engine *e, const uint32_t *d_indexes, const float *
         if (e->key_bits <= 16) {
             k_bucket<uint16_t><<<bblocks, kBucketThreads, 0, st>>>(e->dist.p, (uint16_t *)e->keys[0].p, s0, render_count, R, pl, write_buckets ? 1 : 0, e->ctl.p);
             ++launches;
+            e->prof.mark("k_bucket", st);
             CU(cudaEventRecord(e->ev[EV_BUCKET], st));
             radix_sort_pairs<uint16_t>((uint16_t *)e->keys[0].p, (uint16_t *)e->keys[1].p, vsrc, render_count - 1u, vmode, e->vals[0].p, e->vals[1].p,
-                                       e->sorted.p + s0, n, nullptr, 0ull, pl, e->ctl.p, e->lookback.p, false, st, launches);
+                                       e->sorted.p + s0, n, nullptr, 0ull, pl, e->ctl.p, e->lookback.p, false, st, launches, &e->prof, depth_pass_names);
         } else {
             k_bucket<uint32_t><<<bblocks, kBucketThreads, 0, st>>>(e->dist.p, e->keys[0].p, s0, render_count, R, pl, write_buckets ? 1 : 0, e->ctl.p);
             ++launches;
+            e->prof.mark("k_bucket", st);
             CU(cudaEventRecord(e->ev[EV_BUCKET], st));
             radix_sort_pairs<uint32_t>(e->keys[0].p, e->keys[1].p, vsrc, render_count - 1u, vmode, e->vals[0].p, e->vals[1].p, e->sorted.p + s0, n,
-                                       nullptr, 0ull, pl, e->ctl.p, e->lookback.p, false, st, launches);
+                                       nullptr, 0ull, pl, e->ctl.p, e->lookback.p, false, st, launches, &e->prof, depth_pass_names);
         }
     } else {
         CU(cudaEventRecord(e->ev[EV_DEPTH], st));
@@ -464,7 +476,8 @@ extern "C" int gs_upload_splat_data(gs_engine *e, const gs_splat_data *d) {
 static int render_on_device(gs_engine *e, const gs_uniforms *u, const gs_render_params *p, const uint32_t *d_order) {
     cudaStream_t st = e->stream;
     CU(cudaEventRecord(e->ev[EV_R0], st));
-    int rc = raster_render(e->rs, e->cfg, *u, *p, d_order, st, e->ev[EV_PROJECT], e->ev[EV_BIN], e->tm);
+    if (!e->have_prof_begin) e->prof.begin(st);
+    int rc = raster_render(e->rs, e->cfg, *u, *p, d_order, st, e->ev[EV_PROJECT], e->ev[EV_BIN], e->tm, e->prof);
     if (rc) return rc;
     CU(cudaEventRecord(e->ev[EV_R1], st));
     CU(cudaGetLastError());
@@ -520,27 +533,50 @@ extern "C" int gs_render(gs_engine *e, const gs_uniforms *u, const gs_render_par
     return finish_render(e, p, frame_out);
 }
 
+static int enqueue_frame(gs_engine *e, const gs_sort_params *s, const gs_uniforms *u, const gs_render_params *p, gs_sort_params &q, gs_render_params &rp) {
+    q = *s;
+    q.render_count = std::min(q.render_count, e->uploaded_splats);
+    q.sort_count = std::min(q.sort_count, e->uploaded_splats);
+    const uint32_t *d_idx = nullptr;
+    int rc;
+    if ((rc = stage_sort_inputs(e, &q, &d_idx))) return rc;
+    if ((rc = sort_on_device(e, d_idx, q.model_view_proj, q.sort_count, q.render_count, q.use_precomputed_distances != 0, false))) return rc;
+    const uint32_t sort_launches = e->tm.kernel_launches;
+    e->have_prof_begin = true;
+    rp = *p;
+    rp.sorted_indexes = nullptr; rp.sorted_indexes_dev = nullptr;
+    rp.render_count = std::min(rp.render_count, q.render_count);
+    rc = render_on_device(e, u, &rp, e->sorted.p);
+    e->have_prof_begin = false;
+    if (rc) return rc;
+    e->tm.kernel_launches += sort_launches;
+    return GS_OK;
+}
+
 extern "C" int gs_frame(gs_engine *e, const gs_sort_params *s, const gs_uniforms *u, const gs_render_params *p, uint32_t *sorted_out, void *frame_out) {
     int rc = check_engine(e);
     if (rc) return rc;
     if (!s || !u || !p) return fail(GS_ERR_BAD_ARG, "gs_frame: null argument");
-    gs_sort_params q = *s;
-    q.render_count = std::min(q.render_count, e->uploaded_splats);
-    q.sort_count = std::min(q.sort_count, e->uploaded_splats);
-    const uint32_t *d_idx = nullptr;
-    if ((rc = stage_sort_inputs(e, &q, &d_idx))) return rc;
-    if ((rc = sort_on_device(e, d_idx, q.model_view_proj, q.sort_count, q.render_count, q.use_precomputed_distances != 0, false))) return rc;
-    const uint32_t sort_launches = e->tm.kernel_launches;
-    gs_render_params rp = *p;
-    rp.sorted_indexes = nullptr; rp.sorted_indexes_dev = nullptr;
-    rp.render_count = std::min(rp.render_count, q.render_count);
-    if ((rc = render_on_device(e, u, &rp, e->sorted.p))) return rc;
-    e->tm.kernel_launches += sort_launches;
+    gs_sort_params q; gs_render_params rp;
+    if ((rc = enqueue_frame(e, s, u, p, q, rp))) return rc;
     if (sorted_out && q.render_count) CU(cudaMemcpyAsync(sorted_out, e->sorted.p, (size_t)q.render_count * 4, cudaMemcpyDeviceToHost, e->stream));
     int rc2 = finish_render(e, &rp, frame_out);
     rc = finish_sort(e, nullptr);
     cudaEventElapsedTime(&e->tm.h2d_ms, e->ev[EV_H2D0], e->ev[EV_H2D1]);
     return rc ? rc : rc2;
+}
+
+// Enqueue one frame and return without waiting: the frame stays on the device (gs_buffer_dev(GS_BUF_FRAME)), errors and
+// timings are collected by the next gs_synchronize().  Lets a caller keep several frames in flight on the stream.
+extern "C" int gs_frame_async(gs_engine *e, const gs_sort_params *s, const gs_uniforms *u, const gs_render_params *p) {
+    int rc = check_engine(e);
+    if (rc) return rc;
+    if (!s || !u || !p) return fail(GS_ERR_BAD_ARG, "gs_frame_async: null argument");
+    gs_sort_params q; gs_render_params rp;
+    if ((rc = enqueue_frame(e, s, u, p, q, rp))) return rc;
+    e->pending_async = true;
+    e->pending_rp = rp;
+    return GS_OK;
 }
 
 extern "C" int gs_read_projected(gs_engine *e, gs_projected_splat *out, uint32_t count) {
@@ -576,7 +612,76 @@ extern "C" int gs_stream(gs_engine *e, void **s) {
 extern "C" int gs_synchronize(gs_engine *e) {
     int rc = check_engine(e);
     if (rc) return rc;
+    if (e->pending_async) { // collect errors + timings of the last asynchronous frame
+        e->pending_async = false;
+        int rc2 = finish_render(e, &e->pending_rp, nullptr);
+        rc = finish_sort(e, nullptr);
+        return rc ? rc : rc2;
+    }
     CU(cudaStreamSynchronize(e->stream));
+    return GS_OK;
+}
+
+// ---- measurement helpers (bench hygiene; no effect on results) -------------------------------------------------------
+__global__ void k_flush_l2(uint32_t *buf, size_t words, uint32_t v) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < words; i += (size_t)gridDim.x * blockDim.x) buf[i] = v;
+}
+extern "C" int gs_flush_l2(gs_engine *e) { // overwrite a buffer larger than L2 on the engine's stream
+    int rc = check_engine(e);
+    if (rc) return rc;
+    const size_t words = (size_t)192 * 1024 * 1024 / 4;
+    if ((rc = e->flush.ensure(words))) return rc;
+    static uint32_t tick = 0;
+    k_flush_l2<<<e->sm_count * 8, 512, 0, e->stream>>>(e->flush.p, words, ++tick);
+    CU(cudaGetLastError());
+    return GS_OK;
+}
+extern "C" int gs_set_profiling(gs_engine *e, int on) {
+    if (!e) return fail(GS_ERR_BAD_ARG, "gs_set_profiling: null");
+    e->prof.on = on != 0;
+    return GS_OK;
+}
+// Per-kernel device times of the last sort / render / frame (call after gs_synchronize or a blocking entry).
+extern "C" int gs_kernel_timings(gs_engine *e, gs_kernel_time *out, uint32_t capacity, uint32_t *count) {
+    int rc = check_engine(e);
+    if (rc) return rc;
+    if (!count) return fail(GS_ERR_BAD_ARG, "gs_kernel_timings: null");
+    CU(cudaStreamSynchronize(e->stream));
+    uint32_t n = 0;
+    for (size_t i = 1; i < e->prof.used; ++i) {
+        if (n < capacity && out) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, e->prof.ev[i - 1], e->prof.ev[i]);
+            strncpy(out[n].name, e->prof.names[i], sizeof(out[n].name) - 1);
+            out[n].name[sizeof(out[n].name) - 1] = 0;
+            out[n].ms = ms;
+        }
+        ++n;
+    }
+    *count = n;
+    return GS_OK;
+}
+extern "C" int gs_event_create(void **ev) {
+    if (!ev) return fail(GS_ERR_BAD_ARG, "gs_event_create: null");
+    cudaEvent_t x;
+    CU(cudaEventCreate(&x));
+    *ev = (void *)x;
+    return GS_OK;
+}
+extern "C" int gs_event_record(gs_engine *e, void *ev) {
+    int rc = check_engine(e);
+    if (rc) return rc;
+    CU(cudaEventRecord((cudaEvent_t)ev, e->stream));
+    return GS_OK;
+}
+extern "C" int gs_event_elapsed_ms(void *ev0, void *ev1, float *ms) {
+    if (!ms) return fail(GS_ERR_BAD_ARG, "gs_event_elapsed_ms: null");
+    CU(cudaEventSynchronize((cudaEvent_t)ev1));
+    CU(cudaEventElapsedTime(ms, (cudaEvent_t)ev0, (cudaEvent_t)ev1));
+    return GS_OK;
+}
+extern "C" int gs_event_destroy(void *ev) {
+    if (ev) CU(cudaEventDestroy((cudaEvent_t)ev));
     return GS_OK;
 }
 extern "C" int gs_last_timings(gs_engine *e, gs_timings *t) {

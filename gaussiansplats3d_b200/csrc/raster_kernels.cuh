@@ -646,6 +646,7 @@ static int raster_upload(RasterState &rs, const gs_config &c, const gs_splat_dat
     const size_t cov_elt = d.cov_format == GS_COV_F16 ? 12 : 24;
     const size_t ncomp = d.sh_degree == 2 ? 24 : (d.sh_degree == 1 ? 9 : 0);
     const size_t sh_elt = ncomp * (d.sh_format == GS_SH_F16 ? 2 : (d.sh_format == GS_SH_U8 ? 1 : 4));
+    if (d.from == 0) rs.uploaded = 0; // a (re)upload from splat 0 may change the storage formats
     if (rs.uploaded && (rs.cov_format != d.cov_format || (rs.sh_degree != d.sh_degree) || (ncomp && rs.sh_format != d.sh_format))) {
         snprintf(raster_err(), 512, "splat data format changed between partial uploads"); return GS_ERR_BAD_ARG;
     }
@@ -686,7 +687,7 @@ static void launch_project(RasterState &rs, const ProjParams &P, uint32_t count,
 }
 
 static int raster_render(RasterState &rs, const gs_config &c, const gs_uniforms &u, const gs_render_params &p, const uint32_t *d_order,
-                         cudaStream_t st, cudaEvent_t ev_project, cudaEvent_t ev_bin, gs_timings &tm) {
+                         cudaStream_t st, cudaEvent_t ev_project, cudaEvent_t ev_bin, gs_timings &tm, Profiler &prof) {
     if (!rs.uploaded) { snprintf(raster_err(), 512, "gs_render before gs_upload_splat_data"); return GS_ERR_NOT_READY; }
     if (p.width == 0 || p.height == 0 || p.width > c.max_width || p.height > c.max_height) {
         snprintf(raster_err(), 512, "frame %ux%u outside the engine's %ux%u", p.width, p.height, c.max_width, c.max_height); return GS_ERR_BAD_ARG;
@@ -726,13 +727,16 @@ static int raster_render(RasterState &rs, const gs_config &c, const gs_uniforms 
     k_raster_init<<<rs.sm_count * 2, 256, 0, st>>>(rs.rctl.p, rs.sctl.p, rs.ranges.p, local_tiles, rs.lookback.p, itiles * kRadix * pl.npasses,
                                                  rs.scan_lookback.p, (size_t)scan_tiles + 1);
     ++launches;
+    prof.mark("k_raster_init", st);
     const uint32_t count = rs.uploaded;
     if (rs.cov_format == GS_COV_F16) launch_project<true>(rs, P, count, st); else launch_project<false>(rs, P, count, st);
     ++launches;
+    prof.mark("k_project", st);
     RCU(cudaEventRecord(ev_project, st));
     if (p.render_count && local_tiles) {
         k_tile_count<<<scan_tiles, kScanThreads, 0, st>>>(d_order, p.render_count, rs.rects.p, rank, world, rs.offsets.p, rs.scan_lookback.p, rs.rctl.p, rs.instance_capacity);
         ++launches;
+        prof.mark("k_tile_count", st);
         const int eblocks = (int)std::min<uint64_t>(((uint64_t)p.render_count + kEmitThreads - 1) / kEmitThreads, (uint64_t)rs.sm_count * 8);
         if (tile_bits <= 16) {
             k_tile_emit<uint16_t><<<eblocks, kEmitThreads, 0, st>>>(d_order, p.render_count, rs.rects.p, rs.offsets.p, rank, world, tiles_x,
@@ -742,20 +746,23 @@ static int raster_render(RasterState &rs, const gs_config &c, const gs_uniforms 
                                                                   rs.ikeys[0].p, rs.ivals[0].p, rs.instance_capacity, pl, rs.sctl.p);
         }
         ++launches;
+        prof.mark("k_tile_emit", st);
+        static const char *const tile_pass_names[4] = {"k_radix_pass[tile,0]", "k_radix_pass[tile,1]", "k_radix_pass[tile,2]", "k_radix_pass[tile,3]"};
         // The instance count lives on the device only: the radix grids are sized for the capacity and surplus CTAs exit.
         const unsigned long long *n_dev = &rs.rctl.p->total_instances;
         if (tile_bits <= 16) {
             radix_sort_pairs<uint16_t>((uint16_t *)rs.ikeys[0].p, (uint16_t *)rs.ikeys[1].p, rs.ivals[0].p, 0u, kValArray, rs.ivals[1].p, rs.ivals[0].p,
-                                       rs.list.p, 0u, n_dev, rs.instance_capacity, pl, rs.sctl.p, rs.lookback.p, true, st, launches);
+                                       rs.list.p, 0u, n_dev, rs.instance_capacity, pl, rs.sctl.p, rs.lookback.p, true, st, launches, &prof, tile_pass_names);
             const uint16_t *sorted_keys = (pl.npasses & 1) ? (const uint16_t *)rs.ikeys[1].p : (const uint16_t *)rs.ikeys[0].p;
             k_tile_ranges<uint16_t><<<rs.sm_count * 4, 256, 0, st>>>(sorted_keys, rs.rctl.p, rs.instance_capacity, rs.ranges.p);
         } else {
             radix_sort_pairs<uint32_t>(rs.ikeys[0].p, rs.ikeys[1].p, rs.ivals[0].p, 0u, kValArray, rs.ivals[1].p, rs.ivals[0].p, rs.list.p, 0u, n_dev,
-                                       rs.instance_capacity, pl, rs.sctl.p, rs.lookback.p, true, st, launches);
+                                       rs.instance_capacity, pl, rs.sctl.p, rs.lookback.p, true, st, launches, &prof, tile_pass_names);
             const uint32_t *sorted_keys = (pl.npasses & 1) ? rs.ikeys[1].p : rs.ikeys[0].p;
             k_tile_ranges<uint32_t><<<rs.sm_count * 4, 256, 0, st>>>(sorted_keys, rs.rctl.p, rs.instance_capacity, rs.ranges.p);
         }
         ++launches;
+        prof.mark("k_tile_ranges", st);
     }
     RCU(cudaEventRecord(ev_bin, st));
     if (local_tiles) {
@@ -764,6 +771,7 @@ static int raster_render(RasterState &rs, const gs_config &c, const gs_uniforms 
         else
             k_blend<GS_FRAME_RGBA32F><<<local_tiles, kBlendThreads, 0, st>>>(rs.ranges.p, rs.list.p, rs.records.p, tiles_x, rank, world, (int)p.width, (int)p.height, p.flip_y, rs.frame.p);
         ++launches;
+        prof.mark("k_blend", st);
     }
     rs.last_format = p.frame_format;
     const size_t rows = world == 1 ? p.height : (size_t)local_rows * kTile;

@@ -439,7 +439,8 @@ static void launch_radix_pass(uint32_t grid, bool first, bool write_keys, int va
 template <typename KeyT>
 static void radix_sort_pairs(KeyT *keys0, KeyT *keys1, const uint32_t *vals_src, uint32_t iota_top, int first_valmode, uint32_t *vtmp0,
                              uint32_t *vtmp1, uint32_t *vals_final, uint32_t n, const unsigned long long *n_dev, unsigned long long n_cap,
-                             const PassPlan &pl, SortControl *ctl, uint32_t *lookback, bool write_keys_last, cudaStream_t st, uint32_t &launches) {
+                             const PassPlan &pl, SortControl *ctl, uint32_t *lookback, bool write_keys_last, cudaStream_t st, uint32_t &launches,
+                             Profiler *prof = nullptr, const char *const *pass_names = nullptr) {
     const unsigned long long n_grid = n_dev ? n_cap : n;
     const uint32_t tiles = (uint32_t)((n_grid + kRadixTile - 1) / kRadixTile);
     if (!tiles) return;
@@ -452,6 +453,7 @@ static void radix_sort_pairs(KeyT *keys0, KeyT *keys1, const uint32_t *vals_src,
         launch_radix_pass<KeyT>(tiles, p == 0, !last || write_keys_last, first_valmode, kin, vin, iota_top, kout, vout, n, n_dev, n_cap, pl.shift[p],
                                 pl.bits[p], &ctl->hist[p][0], lookback + (size_t)p * tiles * kRadix, &ctl->ticket[p], st);
         ++launches;
+        if (prof) prof->mark(pass_names ? pass_names[p] : "k_radix_pass", st);
         vin = vout;
         KeyT *t = kin; kin = kout; kout = t;
     }

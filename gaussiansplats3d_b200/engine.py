@@ -254,6 +254,41 @@ class Engine:
         N.check(self._lib.gs_frame(self._h, C.byref(sp), C.byref(u), C.byref(rp), N.ptr(sorted_out), N.ptr(frame_out) if download else None), "gs_frame")
         return frame_out if download else None
 
+    def frame_async(self, mvp, uniforms: Uniforms, width: int, height: int, render_count: int, *, frame_format: int = N.GS_FRAME_RGBA8,
+                    flip_y: bool = True, prepared=None):
+        """Enqueue one frame without waiting (gs_frame_async).  `prepared` = a tuple from prepare_frame() to skip re-marshalling."""
+        if prepared is None:
+            prepared = self.prepare_frame(mvp, uniforms, width, height, render_count, frame_format=frame_format, flip_y=flip_y)
+        sp, u, rp = prepared
+        N.check(self._lib.gs_frame_async(self._h, C.byref(sp), C.byref(u), C.byref(rp)), "gs_frame_async")
+
+    def prepare_frame(self, mvp, uniforms: Uniforms, width: int, height: int, render_count: int, *, frame_format: int = N.GS_FRAME_RGBA8,
+                      flip_y: bool = True):
+        sp = self._sort_params(mvp, render_count, render_count, None, None, None)
+        rp, _ = self._render_params(width, height, render_count, None, frame_format, flip_y)
+        return sp, uniforms.to_c(), rp
+
+    def frame_prepared(self, prepared, frame_out: np.ndarray | None, sorted_out: np.ndarray | None = None) -> None:
+        """gs_frame with pre-marshalled arguments (host buffers: frame_out / sorted_out may be pinned arrays)."""
+        sp, u, rp = prepared
+        N.check(self._lib.gs_frame(self._h, C.byref(sp), C.byref(u), C.byref(rp), N.ptr(sorted_out), N.ptr(frame_out)), "gs_frame")
+
+    def set_profiling(self, on: bool) -> None:
+        N.check(self._lib.gs_set_profiling(self._h, 1 if on else 0), "gs_set_profiling")
+
+    def kernel_timings(self) -> list[tuple[str, float]]:
+        """[(kernel name, device ms)] of the last sort / render / frame, in launch order (needs set_profiling(True))."""
+        buf = (N.gs_kernel_time * 64)()
+        n = C.c_uint32(0)
+        N.check(self._lib.gs_kernel_timings(self._h, buf, 64, C.byref(n)), "gs_kernel_timings")
+        return [(buf[i].name.decode(), buf[i].ms) for i in range(min(n.value, 64))]
+
+    def flush_l2(self) -> None:
+        N.check(self._lib.gs_flush_l2(self._h), "gs_flush_l2")
+
+    def event(self) -> "DeviceEvent":
+        return DeviceEvent(self)
+
     def read_projected(self, count: int) -> np.ndarray:
         out = np.empty(count, N.PROJECTED_DTYPE)
         N.check(self._lib.gs_read_projected(self._h, N.ptr(out), count), "gs_read_projected")
@@ -277,6 +312,29 @@ class Engine:
         t = N.gs_timings()
         N.check(self._lib.gs_last_timings(self._h, C.byref(t)), "gs_last_timings")
         return t.as_dict()
+
+
+class DeviceEvent:
+    """CUDA event recorded on the engine's stream (gs_event_*)."""
+
+    def __init__(self, engine: Engine):
+        self._e = engine
+        self._ev = C.c_void_p()
+        N.check(engine._lib.gs_event_create(C.byref(self._ev)), "gs_event_create")
+
+    def record(self) -> None:
+        N.check(self._e._lib.gs_event_record(self._e._h, self._ev), "gs_event_record")
+
+    def elapsed_ms(self, later: "DeviceEvent") -> float:
+        ms = C.c_float(0)
+        N.check(self._e._lib.gs_event_elapsed_ms(self._ev, later._ev, C.byref(ms)), "gs_event_elapsed_ms")
+        return ms.value
+
+    def __del__(self):
+        try:
+            self._e._lib.gs_event_destroy(self._ev)
+        except Exception:
+            pass
 
 
 def sort_indexes(indexes, centers, precomputed, mvp, scene_indexes, transforms, distance_map_range, sort_count, render_count,

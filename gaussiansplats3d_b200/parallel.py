@@ -37,3 +37,45 @@ def assemble_frame(strips: list, width: int, height: int, flip_y: bool = True):
     if flip_y:
         out = out.flip(0) if hasattr(out, "flip") and not isinstance(out, np.ndarray) else out[::-1]
     return out
+
+
+class _DevicePointer:
+    """Expose a raw device pointer to torch through __cuda_array_interface__ (no copy)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+class TileGather:
+    """The final tile gather: every rank's finished strips -> the whole frame on every rank, one NCCL all-gather enqueued on
+    the ENGINE's stream (torch.cuda.ExternalStream), so it is ordered after the blend kernel without a host sync."""
+
+    def __init__(self, engine, width: int, height: int, rank: int, world: int, fmt: int):
+        import torch
+        import torch.distributed as dist
+        from . import _native as N
+        self.torch, self.dist = torch, dist
+        self.engine, self.width, self.height, self.rank, self.world = engine, width, height, rank, world
+        self.bpp = 4 if fmt == N.GS_FRAME_RGBA8 else 16
+        self.tiles_y = (height + TILE - 1) // TILE
+        self.padded_rows = ((self.tiles_y + world - 1) // world) * TILE
+        ptr, nbytes = engine.buffer_dev(N.GS_BUF_FRAME)
+        need = self.padded_rows * width * self.bpp
+        dev = torch.device("cuda", torch.cuda.current_device())
+        raw = torch.as_tensor(_DevicePointer(ptr, max(need, 1)), device=dev)
+        self.strip = raw[:need]
+        self.gathered = torch.empty((world, need), dtype=torch.uint8, device=dev)
+        self.stream = torch.cuda.ExternalStream(engine.stream(), device=dev)
+
+    def all_gather(self) -> None:
+        with self.torch.cuda.stream(self.stream):
+            self.dist.all_gather_into_tensor(self.gathered.view(-1), self.strip)
+
+    def sync_to_torch(self) -> None:
+        self.torch.cuda.current_stream().wait_stream(self.stream)
+
+    def assemble(self, flip_y: bool = True):
+        """[world, strips] -> [height, width, bpp] image tensor on the device (tile row r + k*world lives at [r, k])."""
+        t = self.gathered.view(self.world, self.padded_rows // TILE, TILE, self.width, self.bpp)
+        img = t.permute(1, 0, 2, 3, 4).reshape(-1, self.width, self.bpp)[: self.height]
+        return img.flip(0) if flip_y else img

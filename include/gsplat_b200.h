@@ -197,6 +197,10 @@ GS_API int gs_render(gs_engine *e, const gs_uniforms *u, const gs_render_params 
 GS_API int gs_frame(gs_engine *e, const gs_sort_params *s, const gs_uniforms *u, const gs_render_params *p,
                     uint32_t *sorted_out, void *frame_out);
 
+/* Same, but only enqueued on the engine's stream: returns without waiting, the frame stays on the device
+ * (gs_buffer_dev(GS_BUF_FRAME)); device-side errors and timings are collected by the next gs_synchronize().         */
+GS_API int gs_frame_async(gs_engine *e, const gs_sort_params *s, const gs_uniforms *u, const gs_render_params *p);
+
 /* ------------------------------------------------------------------------------------------------------------
  * 4. Device-side access for zero-copy callers and for the multi-GPU plumbing (tile gather over NCCL).
  * ---------------------------------------------------------------------------------------------------------- */
@@ -238,6 +242,19 @@ typedef struct gs_timings {
     uint32_t visible_splats;
 } gs_timings;
 GS_API int gs_last_timings(gs_engine *e, gs_timings *t);
+
+/* Measurement helpers for bench.py (no effect on results): L2 flush on the engine's stream (writes a 192 MiB scratch
+ * buffer) and CUDA events recorded on that stream, so per-step device times can be taken without touching torch.     */
+GS_API int gs_flush_l2(gs_engine *e);
+/* Per-kernel timeline: when on, a CUDA event is recorded after every kernel the engine launches; gs_kernel_timings
+ * returns {kernel name, device ms} for the last gs_sort / gs_render / gs_frame in launch order.                      */
+typedef struct gs_kernel_time { char name[40]; float ms; } gs_kernel_time;
+GS_API int gs_set_profiling(gs_engine *e, int on);
+GS_API int gs_kernel_timings(gs_engine *e, gs_kernel_time *out, uint32_t capacity, uint32_t *count);
+GS_API int gs_event_create(void **event);
+GS_API int gs_event_record(gs_engine *e, void *event);
+GS_API int gs_event_elapsed_ms(void *event0, void *event1, float *ms); /* waits for event1 */
+GS_API int gs_event_destroy(void *event);
 
 #ifdef __cplusplus
 }

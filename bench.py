@@ -165,18 +165,23 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------------------------------------
 def algorithmic_bytes(kernel: str, n: int, sh: int, w: int, h: int, instances: int, visible: int) -> float | None:
     """Compulsory HBM bytes per launch (DESIGN.md 'Kernels').  None = not an HBM-stream kernel."""
+    ntd = (n + 4095) // 4096            # radix tiles of the depth sort
+    nti = (instances + 4095) // 4096    # radix tiles of the tile-instance sort
     table = {
-        "k_depth": n * (16 + 4),                     # int32x4 centre in, distance out (identity indexes)
-        "k_bucket": n * (4 + 2),                     # distance in, 16-bit key out
-        "k_radix_pass[depth,0]": n * (2 + 2 + 4),    # key in, key + index out
-        "k_radix_pass[depth,1]": n * (2 + 4 + 4),    # key + index in, index out
+        "k_depth": n * (16 + 4),                           # int32x4 centre in, distance out (identity indexes)
+        "k_bucket": n * (4 + 2),                           # distance in, 16-bit key out
+        "k_radix_scan[depth,0]": ntd * 256 * 8, "k_radix_scan[depth,1]": ntd * 256 * 8,
+        "k_radix_hist[depth,1]": n * 2,
+        "k_radix_scatter[depth,0]": n * (2 + 2 + 4),       # key in, key + index out (iota values)
+        "k_radix_scatter[depth,1]": n * (2 + 4 + 4),       # key + index in, index out
         "k_project": n * (16 + 24 + SH_BYTES[sh]) + n * (48 + 8),
-        "k_tile_count": n * (4 + 8 + 4),
-        "k_tile_emit": n * (4 + 8 + 4) + instances * 6,
-        "k_radix_pass[tile,0]": instances * 12,
-        "k_radix_pass[tile,1]": instances * 12,
-        "k_tile_ranges": instances * 2,
-        "k_blend": instances * 4 + visible * 48 + w * h * 4,
+        "k_tile_count": n * (4 + 8),
+        "k_tile_emit": n * (4 + 8) + instances * 10,       # order + rect in, (u16 coarse id, u64 {mask, splat}) out
+        "k_radix_hist[tile,0]": instances * 2, "k_radix_hist[tile,1]": instances * 2,
+        "k_radix_scan[tile,0]": nti * 256 * 8, "k_radix_scan[tile,1]": nti * 256 * 8,
+        "k_radix_scatter[tile,0]": instances * (10 + 8),   # key + value in, value out (single pass at 1080p)
+        "k_radix_scatter[tile,1]": instances * (10 + 8),
+        "k_blend": instances * 8 + visible * 48 + w * h * 4,   # each list entry once + each visible record once + the frame
     }
     return float(table[kernel]) if kernel in table else None
 
@@ -260,7 +265,7 @@ def run_ours(args):
     tm = e.timings()
     kernels = {k: float(np.mean(vv)) for k, vv in acc.items()}
     frame_kernel_ms = float(sum(kernels.values()))
-    sort_ms = sum(ms for k, ms in kernels.items() if k in ("k_sort_init", "k_depth", "k_bucket") or k.startswith("k_radix_pass[depth"))
+    sort_ms = sum(ms for k, ms in kernels.items() if k in ("k_sort_init", "k_depth", "k_bucket") or "[depth" in k)
     dominant = max(kernels, key=kernels.get)
     peak, peak_src = peaks()
     inst, vis = int(tm["tile_instances"]), int(tm["visible_splats"])

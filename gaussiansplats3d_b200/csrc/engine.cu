@@ -105,7 +105,7 @@ struct gs_engine {
     DevBuf<uint32_t> sorted;         // sortedIndexes
     DevBuf<float> transforms;        // 32 x mat4
     DevBuf<SortControl> ctl;
-    DevBuf<uint32_t> lookback;
+    DevBuf<uint32_t> lookback;       // radix tile histograms / offsets [pass][digit][tile]
     DevBuf<uint32_t> freq;           // scratch reproduction for gs_sort_indexes
     uint32_t uploaded_splats = 0;    // 'uploadedSplatCount' SortWorker.js:97
     uint32_t last_render_count = 0;
@@ -216,8 +216,6 @@ static void launch_depth(bool identity, int blocks, cudaStream_t st, const uint3
 }
 
 // The sort proper, everything already on the device.  d_indexes == nullptr: identity.
-static const char *const depth_pass_names[4] = {"k_radix_pass[depth,0]", "k_radix_pass[depth,1]", "k_radix_pass[depth,2]", "k_radix_pass[depth,3]"};
-
 static int sort_on_device(gs_engine *e, const uint32_t *d_indexes, const float *mvp, uint32_t sort_count, uint32_t render_count,
                           bool use_pre, bool write_buckets) {
     if (sort_count > render_count) return fail(GS_ERR_BAD_ARG, "sortCount %u > renderCount %u", sort_count, render_count);
@@ -226,14 +224,15 @@ static int sort_on_device(gs_engine *e, const uint32_t *d_indexes, const float *
     const uint32_t s0 = render_count - sort_count, n = sort_count;
     const PassPlan pl = make_plan_bits(e->key_bits);
     uint32_t launches = 0;
-    int rc = e->lookback.ensure(radix_lookback_words(std::max(n, 1u), pl.npasses));
+    uint32_t stride = 0;
+    int rc = e->lookback.ensure(radix_tile_hist_words(std::max(n, 1u), pl.npasses, &stride));
     if (rc) return rc;
     CU(cudaEventRecord(e->ev[EV_SORT0], st));
     e->prof.begin(st);
-    k_sort_init<<<std::max(1, e->sm_count), 256, 0, st>>>(e->ctl.p, e->lookback.p, radix_lookback_words(std::max(n, 1u), pl.npasses));
+    k_sort_init<<<1, 256, 0, st>>>(e->ctl.p);
     ++launches;
     e->prof.mark("k_sort_init", st);
-    if (s0 > 0) { k_copy_head<<<std::min<uint32_t>((s0 + 255) / 256, e->sm_count * 8), 256, 0, st>>>(d_indexes, e->sorted.p, s0); ++launches; }
+    if (s0 > 0) { k_copy_head<<<std::min<uint32_t>((s0 + 255) / 256, e->sm_count * 8), 256, 0, st>>>(d_indexes, e->sorted.p, s0); ++launches; e->prof.mark("k_copy_head", st); }
     if (n > 0) {
         DepthParams P{};
         memcpy(P.mvp, mvp, 64);
@@ -259,24 +258,27 @@ static int sort_on_device(gs_engine *e, const uint32_t *d_indexes, const float *
         ++launches;
         e->prof.mark("k_depth", st);
         CU(cudaEventRecord(e->ev[EV_DEPTH], st));
-        const int bblocks = (int)std::min<uint64_t>(((uint64_t)n + kBucketThreads * kBucketItems - 1) / (kBucketThreads * kBucketItems), (uint64_t)e->sm_count * 8);
+        const uint32_t tiles = (n + kRadixTile - 1) / kRadixTile;
         const uint32_t R = e->cfg.distance_map_range;
         const uint32_t *vsrc = identity ? nullptr : d_indexes + s0;
         const int vmode = identity ? kValIotaReversed : kValArrayReversed;
+        static const RadixNames names = {{"k_radix_hist[depth,0]", "k_radix_hist[depth,1]", "k_radix_hist[depth,2]", "k_radix_hist[depth,3]"},
+                                         {"k_radix_scan[depth,0]", "k_radix_scan[depth,1]", "k_radix_scan[depth,2]", "k_radix_scan[depth,3]"},
+                                         {"k_radix_scatter[depth,0]", "k_radix_scatter[depth,1]", "k_radix_scatter[depth,2]", "k_radix_scatter[depth,3]"}};
         if (e->key_bits <= 16) {
-            k_bucket<uint16_t><<<bblocks, kBucketThreads, 0, st>>>(e->dist.p, (uint16_t *)e->keys[0].p, s0, render_count, R, pl, write_buckets ? 1 : 0, e->ctl.p);
+            k_bucket<uint16_t><<<tiles, kRadixThreads, 0, st>>>(e->dist.p, (uint16_t *)e->keys[0].p, s0, render_count, R, pl, write_buckets ? 1 : 0, e->ctl.p, e->lookback.p, stride);
             ++launches;
             e->prof.mark("k_bucket", st);
             CU(cudaEventRecord(e->ev[EV_BUCKET], st));
-            radix_sort_pairs<uint16_t>((uint16_t *)e->keys[0].p, (uint16_t *)e->keys[1].p, vsrc, render_count - 1u, vmode, e->vals[0].p, e->vals[1].p,
-                                       e->sorted.p + s0, n, nullptr, 0ull, pl, e->ctl.p, e->lookback.p, false, st, launches, &e->prof, depth_pass_names);
+            radix_sort_pairs<uint16_t, uint32_t>((uint16_t *)e->keys[0].p, (uint16_t *)e->keys[1].p, vsrc, render_count - 1u, vmode, e->vals[0].p, e->vals[1].p,
+                                       e->sorted.p + s0, n, nullptr, 0ull, pl, e->ctl.p, e->lookback.p, stride, true, nullptr, st, launches, &e->prof, names);
         } else {
-            k_bucket<uint32_t><<<bblocks, kBucketThreads, 0, st>>>(e->dist.p, e->keys[0].p, s0, render_count, R, pl, write_buckets ? 1 : 0, e->ctl.p);
+            k_bucket<uint32_t><<<tiles, kRadixThreads, 0, st>>>(e->dist.p, e->keys[0].p, s0, render_count, R, pl, write_buckets ? 1 : 0, e->ctl.p, e->lookback.p, stride);
             ++launches;
             e->prof.mark("k_bucket", st);
             CU(cudaEventRecord(e->ev[EV_BUCKET], st));
-            radix_sort_pairs<uint32_t>(e->keys[0].p, e->keys[1].p, vsrc, render_count - 1u, vmode, e->vals[0].p, e->vals[1].p, e->sorted.p + s0, n,
-                                       nullptr, 0ull, pl, e->ctl.p, e->lookback.p, false, st, launches, &e->prof, depth_pass_names);
+            radix_sort_pairs<uint32_t, uint32_t>(e->keys[0].p, e->keys[1].p, vsrc, render_count - 1u, vmode, e->vals[0].p, e->vals[1].p, e->sorted.p + s0, n,
+                                       nullptr, 0ull, pl, e->ctl.p, e->lookback.p, stride, true, nullptr, st, launches, &e->prof, names);
         }
     } else {
         CU(cudaEventRecord(e->ev[EV_DEPTH], st));

@@ -1,8 +1,8 @@
 // raster_kernels.cuh -- tile-binned forward rasteriser (sm_100a) replacing the reference's WebGL path:
 //   k_project     : vertex shader, once per splat (not x4)    SplatMaterial.js:112-341, SplatMaterial3D.js:83-216
-//   k_tile_count  : per draw-rank tile counts + exclusive scan (decoupled look-back)
-//   k_tile_emit   : (tile, splat) instances in DRAW order + radix digit histograms
-//   k_radix_pass  : stable sort of the instances by tile id (sort_kernels.cuh) -> per-tile lists in draw order
+//   k_tile_count  : coarse-tile instances per chunk of draw ranks
+//   k_tile_emit   : (coarse tile, {fine mask, splat}) instances in DRAW order
+//   k_radix_*     : stable sort of the instances by coarse tile id (sort_kernels.cuh) -> per-coarse-tile lists in draw order
 //   k_blend       : fragment shader + blend, front-to-back      SplatMaterial3D.js:234-252, :65-75
 // Draw order is the reference's (sorted_indexes[0] first = farthest).  We composite front-to-back over the REVERSED
 // list with a transmittance accumulator, which is algebraically the same "over" chain.
@@ -22,9 +22,10 @@ struct __align__(16) SplatRecord {     // 48 bytes, read as 3 x 16 B
     float cx, cy;                      // quad centre in pixels, GL window coordinates (y up)
     float g1x, g1y;                    // g1 = B1 / |B1|^2 : u = dot(d, g1) is the quad-local coordinate in [-1,1]
     float g2x, g2y;                    // g2 = B2 / |B2|^2
-    float ndc_z, a;
+    uint32_t hxhy;                     // half2: half extents of the ellipse's pixel AABB, rounded UP (culling only)
+    float a;
     float r, g, b;
-    uint32_t valid;
+    float ndc_z;                       // outside [-1,1] (2.0 for culled splats) <=> not drawn
 };
 
 struct RasterControl {
@@ -115,8 +116,9 @@ k_project(const uint4 *__restrict__ cc, const void *__restrict__ cov, const void
     uint32_t visible = 0;
     if (s < count) {
         SplatRecord o;
-        o.cx = o.cy = o.g1x = o.g1y = o.g2x = o.g2y = o.ndc_z = o.a = o.r = o.g = o.b = 0.f;
-        o.valid = 0;
+        o.cx = o.cy = o.g1x = o.g1y = o.g2x = o.g2y = o.a = o.r = o.g = o.b = 0.f;
+        o.ndc_z = 2.0f;
+        o.hxhy = 0;
         ushort4 rect = make_ushort4(1, 1, 0, 0); // empty
         const int4 c4 = ld_nc_v4(cc + s);
         const float cx = __int_as_float(c4.y), cy = __int_as_float(c4.z), cz = __int_as_float(c4.w);
@@ -269,12 +271,14 @@ k_project(const uint4 *__restrict__ cc, const void *__restrict__ cov, const void
                 o.ndc_z = ndcz; o.a = col[3];
                 o.r = col[0]; o.g = col[1]; o.b = col[2];
                 const bool in_depth = (ndcz >= -1.0f && ndcz <= 1.0f) && isfinite(s1) && isfinite(s2) && s1 > 0.f && s2 > 0.f;
-                o.valid = in_depth ? 1u : 0u;
+                if (!in_depth && ndcz >= -1.0f && ndcz <= 1.0f) o.ndc_z = 2.0f;
                 if (in_depth) {
                     // tight AABB of the ellipse u^2+w^2<=1 : half extents sqrt(B1x^2+B2x^2), sqrt(B1y^2+B2y^2)
                     const float b1x = ex * s1, b1y = ey * s1, b2x = ey * s2, b2y = -ex * s2;
                     const float hx = sqrtf(b1x * b1x + b2x * b2x) * 1.0005f + 0.01f;
                     const float hy = sqrtf(b1y * b1y + b2y * b2y) * 1.0005f + 0.01f;
+                    const __half2 hh = __halves2half2(__float2half_ru(fminf(hx, 60000.f)), __float2half_ru(fminf(hy, 60000.f)));
+                    o.hxhy = *reinterpret_cast<const uint32_t *>(&hh);
                     // pixel centres (px+0.5) inside [c-h, c+h]
                     const float fx0 = ceilf(o.cx - hx - 0.5f), fx1 = floorf(o.cx + hx - 0.5f);
                     const float fy0 = ceilf(o.cy - hy - 0.5f), fy1 = floorf(o.cy + hy - 0.5f);
@@ -291,173 +295,121 @@ k_project(const uint4 *__restrict__ cc, const void *__restrict__ cov, const void
         }
         float4 *dst = reinterpret_cast<float4 *>(rec + s);
         dst[0] = make_float4(o.cx, o.cy, o.g1x, o.g1y);
-        dst[1] = make_float4(o.g2x, o.g2y, o.ndc_z, o.a);
-        dst[2] = make_float4(o.r, o.g, o.b, __uint_as_float(o.valid));
+        dst[1] = make_float4(o.g2x, o.g2y, __uint_as_float(o.hxhy), o.a);
+        dst[2] = make_float4(o.r, o.g, o.b, o.ndc_z);
         rects[s] = rect;
     }
     const uint32_t nvis = __popc(__ballot_sync(0xffffffffu, visible));
     if ((threadIdx.x & 31) == 0 && nvis) atomicAdd(&rctl->visible, nvis);
 }
 
-__device__ __forceinline__ uint32_t rect_instances(ushort4 r, uint32_t rank, uint32_t world) {
+// ---------------------------------------------------------------------------------------------------------------
+// Hierarchical binning.  Splats are binned (in draw order) into COARSE tiles of kCoarseW x kCoarseH fine tiles
+// (128 x 64 px: <= 256 coarse tiles at 1920x1080 -> ONE stable radix pass over ~1.1 instances per splat).  Each instance
+// carries a 32-bit mask of the fine tiles it touches inside that coarse tile; the blend CTA of a fine tile streams its
+// coarse tile's list and keeps the entries whose mask bit is set.  Order inside a list = draw order (stable sort of a
+// sequence generated in draw order), so filtering preserves it.
+constexpr int kCoarseW = 8, kCoarseH = 4, kCoarseShiftX = 3, kCoarseShiftY = 2;
+constexpr int kFinePerCoarse = kCoarseW * kCoarseH;   // 32 = bits of the mask
+
+__device__ __forceinline__ uint32_t coarse_instances(ushort4 r) {
     if (r.z < r.x || r.w < r.y) return 0;
-    return (uint32_t)(r.z - r.x + 1) * (uint32_t)owned_rows(r.y, r.w, rank, world);
+    return (uint32_t)((r.z >> kCoarseShiftX) - (r.x >> kCoarseShiftX) + 1) * (uint32_t)((r.w >> kCoarseShiftY) - (r.y >> kCoarseShiftY) + 1);
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// Draw-rank p (0 = nearest, i.e. LAST in the reference's draw order) -> exclusive offset of its tile instances.
-constexpr int kScanThreads = 256;
-constexpr int kScanItems = 4;
-constexpr int kScanTile = kScanThreads * kScanItems;
-constexpr unsigned long long kScanAggregate = 1ull << 62, kScanPrefix = 2ull << 62, kScanFlags = 3ull << 62;
+constexpr int kBinThreads = 256;
+constexpr int kBinItems = 8;
+constexpr int kBinTile = kBinThreads * kBinItems;   // draw ranks per CTA
 
-__global__ void __launch_bounds__(kScanThreads)
-k_tile_count(const uint32_t *__restrict__ order, uint32_t render_count, const ushort4 *__restrict__ rects, uint32_t rank,
-             uint32_t world, uint32_t *__restrict__ offsets, unsigned long long *lookback, RasterControl *rctl,
-             unsigned long long capacity) {
+// pass 1: instances per CTA-chunk of draw ranks (rank p = 0 is the NEAREST splat = last in the reference's draw order)
+__global__ void __launch_bounds__(kBinThreads)
+k_tile_count(const uint32_t *__restrict__ order, uint32_t render_count, const ushort4 *__restrict__ rects,
+             uint32_t *__restrict__ block_sums, RasterControl *rctl) {
     __shared__ uint32_t s_scan[40];
-    __shared__ uint32_t s_tile;
-    __shared__ unsigned long long s_prefix;
-    if (threadIdx.x == 0) s_tile = atomicAdd(&rctl->scan_ticket, 1u);
-    __syncthreads();
-    const uint32_t tile = s_tile;
-    const uint64_t base = (uint64_t)tile * kScanTile + (uint64_t)threadIdx.x * kScanItems;
-    uint32_t cnt[kScanItems], mine = 0;
+    const uint32_t base = blockIdx.x * kBinTile;
+    uint32_t mine = 0;
 #pragma unroll
-    for (int k = 0; k < kScanItems; ++k) {
-        const uint64_t p = base + k;
-        cnt[k] = 0;
-        if (p < render_count) {
-            const uint32_t s = ld_nc_u32(order + (render_count - 1u - p));
-            cnt[k] = rect_instances(rects[s], rank, world);
-        }
-        mine += cnt[k];
+    for (int k = 0; k < kBinItems; ++k) {
+        const uint32_t p = base + (uint32_t)k * kBinThreads + threadIdx.x;
+        if (p < render_count) mine += coarse_instances(rects[ld_nc_u32(order + (render_count - 1u - p))]);
     }
     uint32_t total;
-    const uint32_t ex = block_exclusive_scan<kScanThreads>(mine, s_scan, total);
+    (void)block_exclusive_scan<kBinThreads>(mine, s_scan, total);
     if (threadIdx.x == 0) {
-        unsigned long long excl = 0;
-        volatile unsigned long long *lb = lookback;
-        if (tile == 0) {
-            lb[0] = (unsigned long long)total | kScanPrefix;
-        } else {
-            lb[tile] = (unsigned long long)total | kScanAggregate;
-            __threadfence();
-            int64_t t = (int64_t)tile - 1;
-            while (true) {
-                const unsigned long long v = lb[t];
-                const unsigned long long f = v & kScanFlags;
-                if (f == 0) continue;
-                excl += v & ~kScanFlags;
-                if (f == kScanPrefix) break;
-                --t;
-            }
-            lb[tile] = (excl + total) | kScanPrefix;
-        }
-        s_prefix = excl;
-        if ((uint64_t)(tile + 1) * kScanTile >= render_count) { // last tile: publish the grand total
-            rctl->total_instances = excl + total;
-            if (excl + total > capacity) rctl->overflow = 1;
-        }
-    }
-    __syncthreads();
-    const unsigned long long pre = s_prefix + ex;
-    uint32_t run = 0;
-#pragma unroll
-    for (int k = 0; k < kScanItems; ++k) {
-        const uint64_t p = base + k;
-        if (p < render_count) offsets[p] = (uint32_t)min(pre + run, (unsigned long long)0xffffffffu);
-        run += cnt[k];
+        block_sums[blockIdx.x] = total;
+        atomicAdd(&rctl->total_instances, (unsigned long long)total);
     }
 }
 
-// One warp per 32 draw ranks; lanes cooperate on large rects.  Writes key = local tile id, val = splat id, and the
-// per-pass digit histograms for the tile sort.
-constexpr int kEmitThreads = 256;
-
-template <typename KeyT>
-__global__ void __launch_bounds__(kEmitThreads)
+// pass 2: write (coarse tile id, {fine mask, splat id}) for every instance, in draw order.  Warp-striped: warp w owns 256
+// consecutive draw ranks, item k of lane l is rank run + 32k + l, so loads are coalesced and (warp, k, lane) order = draw order.
+__global__ void __launch_bounds__(kBinThreads)
 k_tile_emit(const uint32_t *__restrict__ order, uint32_t render_count, const ushort4 *__restrict__ rects,
-            const uint32_t *__restrict__ offsets, uint32_t rank, uint32_t world, int tiles_x, KeyT *__restrict__ keys,
-            uint32_t *__restrict__ vals, unsigned long long capacity, PassPlan plan, SortControl *ctl) {
-    __shared__ uint32_t s_hist[4][kRadix];
-    for (int i = threadIdx.x; i < 4 * kRadix; i += kEmitThreads) (&s_hist[0][0])[i] = 0;
-    __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const uint64_t warp_global = ((uint64_t)blockIdx.x * kEmitThreads + threadIdx.x) >> 5;
-    const uint64_t nwarps = ((uint64_t)gridDim.x * kEmitThreads) >> 5;
-    for (uint64_t p0 = warp_global * 32; p0 < render_count; p0 += nwarps * 32) {
-        const uint64_t p = p0 + lane;
-        uint32_t s = 0, off = 0, n = 0;
-        ushort4 r = make_ushort4(1, 1, 0, 0);
-        if (p < render_count) {
-            s = ld_nc_u32(order + (render_count - 1u - p));
-            r = rects[s];
-            n = rect_instances(r, rank, world);
-            off = offsets[p];
-        }
-        // small rects: each lane writes its own; large rects: the warp shares the work
-        const uint32_t big = __ballot_sync(0xffffffffu, n > 32u);
-        if (n > 0 && n <= 32u && (unsigned long long)off + n <= capacity) {
-            uint32_t w = off;
-            const int rw = r.z - r.x + 1;
-            for (int ty = r.y; ty <= r.w; ++ty) {
-                if (world > 1 && (uint32_t)ty % world != rank) continue;
-                const uint32_t row_base = (uint32_t)(ty / (int)world) * (uint32_t)tiles_x;
-                for (int i = 0; i < rw; ++i) {
-                    const uint32_t key = row_base + (uint32_t)(r.x + i);
-                    keys[w] = (KeyT)key;
-                    vals[w] = s;
-                    ++w;
+            const uint32_t *__restrict__ block_sums, int coarse_x, uint16_t *__restrict__ keys,
+            unsigned long long *__restrict__ vals, unsigned long long capacity, RasterControl *rctl) {
+    __shared__ unsigned long long s_prefix;
+    __shared__ uint32_t s_wsum[kBinThreads / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // instances of all earlier chunks
+    unsigned long long before = 0;
+    for (uint32_t b = threadIdx.x; b < blockIdx.x; b += kBinThreads) before += block_sums[b];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        if (q < plan.npasses) atomicAdd(&s_hist[q][(key >> plan.shift[q]) & ((1u << plan.bits[q]) - 1u)], 1u);
-                }
+    for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(0xffffffffu, before, o);
+    if (threadIdx.x == 0) s_prefix = 0;
+    __syncthreads();
+    if (lane == 0 && before) atomicAdd(&s_prefix, before);
+    const uint32_t run = blockIdx.x * kBinTile + (uint32_t)warp * (32 * kBinItems);
+    uint32_t sid[kBinItems], cnt[kBinItems], mine = 0;
+    ushort4 rr[kBinItems];
+#pragma unroll
+    for (int k = 0; k < kBinItems; ++k) {
+        const uint32_t p = run + (uint32_t)k * 32 + lane;
+        sid[k] = (p < render_count) ? ld_nc_u32(order + (render_count - 1u - p)) : 0xffffffffu;
+    }
+#pragma unroll
+    for (int k = 0; k < kBinItems; ++k) {
+        cnt[k] = 0; rr[k] = make_ushort4(1, 1, 0, 0);
+        if (sid[k] != 0xffffffffu) { rr[k] = rects[sid[k]]; cnt[k] = coarse_instances(rr[k]); }
+        mine += cnt[k];
+    }
+    uint32_t wtot = mine;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wtot += __shfl_xor_sync(0xffffffffu, wtot, o);
+    if (lane == 0) s_wsum[warp] = wtot;
+    __syncthreads();
+    unsigned long long w0 = s_prefix;
+    for (int w = 0; w < warp; ++w) w0 += s_wsum[w];
+    bool overflow = false;
+#pragma unroll
+    for (int k = 0; k < kBinItems; ++k) {
+        const uint32_t inc = warp_inclusive_scan(cnt[k]);
+        unsigned long long w = w0 + (inc - cnt[k]);
+        w0 += __shfl_sync(0xffffffffu, inc, 31);
+        if (cnt[k] == 0) continue;
+        const ushort4 r = rr[k];
+        const int cx0 = r.x >> kCoarseShiftX, cx1 = r.z >> kCoarseShiftX, cy0 = r.y >> kCoarseShiftY, cy1 = r.w >> kCoarseShiftY;
+#pragma unroll 1
+        for (int cy = cy0; cy <= cy1; ++cy) {
+            const int fy0 = max((int)r.y, cy * kCoarseH) - cy * kCoarseH, fy1 = min((int)r.w, cy * kCoarseH + kCoarseH - 1) - cy * kCoarseH;
+            // rows fy0..fy1 selected: one bit per byte, then multiplied by the 8-bit column pattern (no carries)
+            const uint32_t rowsel = (0x01010101u >> (8 * (kCoarseH - 1 - (fy1 - fy0)))) << (8 * fy0);
+#pragma unroll 1
+            for (int cx = cx0; cx <= cx1; ++cx) {
+                const int fx0 = max((int)r.x, cx * kCoarseW) - cx * kCoarseW, fx1 = min((int)r.z, cx * kCoarseW + kCoarseW - 1) - cx * kCoarseW;
+                const uint32_t row = ((1u << (fx1 - fx0 + 1)) - 1u) << fx0;
+                const uint32_t mask = row * rowsel;
+                if (w < capacity) {
+                    keys[w] = (uint16_t)(cy * coarse_x + cx);
+                    vals[w] = ((unsigned long long)mask << 32) | sid[k];
+                } else overflow = true;
+                ++w;
             }
         }
-        uint32_t todo = big;
-        while (todo) {
-            const int src = __ffs(todo) - 1;
-            todo &= todo - 1;
-            const uint32_t bs = __shfl_sync(0xffffffffu, s, src), boff = __shfl_sync(0xffffffffu, off, src), bn = __shfl_sync(0xffffffffu, n, src);
-            const int bx0 = __shfl_sync(0xffffffffu, (int)r.x, src), by0 = __shfl_sync(0xffffffffu, (int)r.y, src);
-            const int bx1 = __shfl_sync(0xffffffffu, (int)r.z, src);
-            if ((unsigned long long)boff + bn > capacity) continue;
-            const int rw = bx1 - bx0 + 1;
-            // first owned row >= by0
-            const int first = by0 + (int)(((int)rank - (by0 % (int)world) + (int)world) % (int)world);
-            for (uint32_t i = lane; i < bn; i += 32) {
-                const int rowk = (int)(i / (uint32_t)rw), colk = (int)(i % (uint32_t)rw);
-                const int ty = first + rowk * (int)world;
-                const uint32_t key = (uint32_t)(ty / (int)world) * (uint32_t)tiles_x + (uint32_t)(bx0 + colk);
-                keys[boff + i] = (KeyT)key;
-                vals[boff + i] = bs;
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    if (q < plan.npasses) atomicAdd(&s_hist[q][(key >> plan.shift[q]) & ((1u << plan.bits[q]) - 1u)], 1u);
-            }
-        }
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < plan.npasses * kRadix; i += kEmitThreads) {
-        const uint32_t v = (&s_hist[0][0])[i];
-        if (v) atomicAdd(&ctl->hist[0][0] + i, v);
-    }
+    if (overflow) rctl->overflow = 1;
 }
 
-// tile ranges from the sorted keys
-template <typename KeyT>
-__global__ void k_tile_ranges(const KeyT *__restrict__ keys, const RasterControl *rctl, unsigned long long capacity, uint2 *__restrict__ ranges) {
-    const unsigned long long n = min(rctl->total_instances, capacity);
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
-        const uint32_t k = keys[i];
-        if (i == 0 || (uint32_t)keys[i - 1] != k) ranges[k].x = (uint32_t)i;
-        if (i + 1 == n || (uint32_t)keys[i + 1] != k) ranges[k].y = (uint32_t)(i + 1);
-    }
-}
-
-__global__ void k_raster_init(RasterControl *rctl, SortControl *ctl, uint2 *ranges, uint32_t ntiles, uint32_t *lookback32,
-                              size_t lookback_words, unsigned long long *scan_lookback, size_t scan_words) {
+__global__ void k_raster_init(RasterControl *rctl, SortControl *ctl, uint2 *ranges, uint32_t ntiles) {
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     if (tid == 0) {
@@ -467,70 +419,132 @@ __global__ void k_raster_init(RasterControl *rctl, SortControl *ctl, uint2 *rang
     }
     uint32_t *h = &ctl->hist[0][0];
     for (size_t i = tid; i < 4 * kRadix; i += stride) h[i] = 0;
-    for (size_t i = tid; i < ntiles; i += stride) ranges[i] = make_uint2(0u, 0u);
-    for (size_t i = tid; i < lookback_words; i += stride) lookback32[i] = 0;
-    for (size_t i = tid; i < scan_words; i += stride) scan_lookback[i] = 0ull;
+    for (size_t i = tid; i < ntiles; i += stride) ranges[i] = make_uint2(0xffffffffu, 0u); // empty: first > last
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Blend: one CTA per owned tile, one thread per pixel; the tile's list is staged through shared memory in batches.
-constexpr int kBlendThreads = kTile * kTile;
+// Blend: one 64-thread CTA per fine tile (16x16 px); each thread owns a COLUMN of 4 pixels so that, per splat, the quad-local
+// coordinates are evaluated once and stepped down the column with two adds per extra pixel (u += g1.y, w += g2.y).  CTAs of one
+// coarse tile are adjacent in the grid so their common list stays in L1/L2.  Per 256 list entries: filter by mask bit (ballot
+// compaction keeps draw order), then stage the survivors' records through shared memory 64 at a time and composite front to back.
+constexpr int kBlendThreads = 64;
+constexpr int kBlendPix = 4;                       // pixels per thread (a column)
+constexpr int kBlendScan = 4 * kBlendThreads;      // list entries filtered per batch
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 
 template <int FORMAT>
 __global__ void __launch_bounds__(kBlendThreads)
-k_blend(const uint2 *__restrict__ ranges, const uint32_t *__restrict__ list, const SplatRecord *__restrict__ rec, int tiles_x,
-        uint32_t rank, uint32_t world, int width, int height, int flip_y, void *__restrict__ frame) {
+k_blend(const uint2 *__restrict__ ranges, const unsigned long long *__restrict__ list, const SplatRecord *__restrict__ rec, int tiles_x,
+        int tiles_y, int coarse_x, uint32_t rank, uint32_t world, int width, int height, int flip_y, void *__restrict__ frame) {
     __shared__ float4 s_rec[kBlendThreads][3];
-    const uint32_t local_tile = blockIdx.x;
-    const int tx = (int)(local_tile % (uint32_t)tiles_x), lrow = (int)(local_tile / (uint32_t)tiles_x);
-    const int ty = lrow * (int)world + (int)rank;
-    const int lx = threadIdx.x & (kTile - 1), ly = threadIdx.x >> kTileShift;
-    const int x = tx * kTile + lx, y = ty * kTile + ly;
-    const float pxc = (float)x + 0.5f, pyc = (float)y + 0.5f;
-    const uint2 rg = ranges[local_tile];
-    float T = 1.0f, Cr = 0.f, Cg = 0.f, Cb = 0.f;
-    bool done = !(x < width && y < height);
-    for (uint32_t base = rg.x; base < rg.y; base += kBlendThreads) {
+    __shared__ uint32_t s_ids[kBlendScan];
+    __shared__ uint32_t s_cnt[2][4][2];
+    const uint32_t coarse = blockIdx.x / kFinePerCoarse, sub = blockIdx.x % kFinePerCoarse;
+    const int tx = (int)(coarse % (uint32_t)coarse_x) * kCoarseW + (int)(sub & (kCoarseW - 1));
+    const int ty = (int)(coarse / (uint32_t)coarse_x) * kCoarseH + (int)(sub >> kCoarseShiftX);
+    if (tx >= tiles_x || ty >= tiles_y) return;
+    if (world > 1 && (uint32_t)ty % world != rank) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lx = lane & 15, ly0 = ((lane >> 4) + 2 * warp) * kBlendPix;     // column lx, rows ly0 .. ly0+3 of the tile
+    const int x = tx * kTile + lx, y0 = ty * kTile + ly0;
+    const float pxc = (float)x + 0.5f, pyc = (float)y0 + 0.5f;
+    const uint2 rg = ranges[coarse];
+    float T[kBlendPix], Cr[kBlendPix], Cg[kBlendPix], Cb[kBlendPix];
+#pragma unroll
+    for (int k = 0; k < kBlendPix; ++k) { T[k] = 1.0f; Cr[k] = Cg[k] = Cb[k] = 0.f; }
+    bool done = !(x < width && y0 < height);
+    int parity = 0;
+    for (uint32_t base = rg.x; base < rg.y; base += kBlendScan) {
         if (__syncthreads_count(done) == kBlendThreads) break;
-        const uint32_t i = base + threadIdx.x;
-        if (i < rg.y) {
-            const uint32_t s = ld_nc_u32(list + i);
-            const float4 *src = reinterpret_cast<const float4 *>(rec + s);
-            s_rec[threadIdx.x][0] = src[0];
-            s_rec[threadIdx.x][1] = src[1];
-            s_rec[threadIdx.x][2] = src[2];
+        // ---- filter 4 x 64 entries, order-preserving compaction (order: round k, warp, lane) ----------------------------------
+        uint32_t ids[4], bal[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t i = base + (uint32_t)k * kBlendThreads + threadIdx.x;
+            bool hit = false;
+            ids[k] = 0;
+            if (i < rg.y) {
+                const unsigned long long e = __ldg(list + i);
+                hit = ((uint32_t)(e >> 32) >> sub) & 1u;
+                ids[k] = (uint32_t)e;
+            }
+            bal[k] = __ballot_sync(0xffffffffu, hit);
+            if (lane == 0) s_cnt[parity][k][warp] = __popc(bal[k]);
         }
         __syncthreads();
-        const int nb = (int)min((uint32_t)kBlendThreads, rg.y - base);
-        if (!done) {
-            for (int j = 0; j < nb; ++j) {
-                const float4 r0 = s_rec[j][0], r1 = s_rec[j][1];
-                const float dx = pxc - r0.x, dy = pyc - r0.y;
-                const float u = dx * r0.z + dy * r0.w;
-                const float w = dx * r1.x + dy * r1.y;
-                const float q = u * u + w * w;          // A = 8 q ; discard A > 8
-                if (q > 1.0f) continue;
-                const float4 r2 = s_rec[j][2];
-                const float alpha = __expf(-4.0f * q) * r1.w;  // exp(-0.5 A) * vColor.a
-                const float wgt = T * alpha;
-                Cr += wgt * r2.x; Cg += wgt * r2.y; Cb += wgt * r2.z;
-                T *= (1.0f - alpha);
-                if (T < kTransmittanceCutoff) { done = true; break; }
+        uint32_t nsurv = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t c0 = s_cnt[parity][k][0], c1 = s_cnt[parity][k][1];
+            const uint32_t off = nsurv + (warp ? c0 : 0u);
+            if ((bal[k] >> lane) & 1u) s_ids[off + __popc(bal[k] & lanemask_lt())] = ids[k];
+            nsurv += c0 + c1;
+        }
+        parity ^= 1;
+        __syncthreads();
+        // ---- composite the survivors, 64 records at a time ------------------------------------------------------------------
+        for (uint32_t c0 = 0; c0 < nsurv; c0 += kBlendThreads) {
+            const uint32_t j = c0 + threadIdx.x;
+            if (j < nsurv) {
+                const float4 *src = reinterpret_cast<const float4 *>(rec + s_ids[j]);
+                s_rec[threadIdx.x][0] = __ldg(src);
+                s_rec[threadIdx.x][1] = __ldg(src + 1);
+                s_rec[threadIdx.x][2] = __ldg(src + 2);
             }
+            __syncthreads();
+            const int nb = (int)min((uint32_t)kBlendThreads, nsurv - c0);
+            if (!done) {
+#pragma unroll 2
+                for (int jj = 0; jj < nb; ++jj) {
+                    const float4 r0 = s_rec[jj][0], r1 = s_rec[jj][1];
+                    const float dx = pxc - r0.x, dy = pyc - r0.y;
+                    float u = dx * r0.z + dy * r0.w;          // quad-local coordinates of the top pixel of my column
+                    float w = dx * r1.x + dy * r1.y;
+                    float q[kBlendPix];
+#pragma unroll
+                    for (int k = 0; k < kBlendPix; ++k) {
+                        q[k] = u * u + w * w;                 // A = 8 q ; the fragment shader discards A > 8
+                        u += r0.w; w += r1.y;                 // one pixel up the column: d/dy of (u, w) = (g1.y, g2.y)
+                    }
+                    if (fminf(fminf(q[0], q[1]), fminf(q[2], q[3])) > 1.0f) continue;
+                    const float4 r2 = s_rec[jj][2];
+#pragma unroll
+                    for (int k = 0; k < kBlendPix; ++k) {
+                        if (q[k] <= 1.0f) {
+                            const float alpha = ex2_approx(q[k] * -5.770780163555854f) * r1.w;   // exp(-0.5 A) * vColor.a, A = 8 q
+                            const float wgt = T[k] * alpha;
+                            Cr[k] += wgt * r2.x; Cg[k] += wgt * r2.y; Cb[k] += wgt * r2.z;
+                            T[k] *= (1.0f - alpha);
+                        }
+                    }
+                    if (fmaxf(fmaxf(T[0], T[1]), fmaxf(T[2], T[3])) < kTransmittanceCutoff) { done = true; break; }
+                }
+            }
+            __syncthreads();
         }
     }
-    if (x < width && y < height) {
-        const float A = 1.0f - T; // alpha accumulates as 1 - prod(1 - alpha_i)
-        int out_row;
-        if (world == 1) out_row = flip_y ? (height - 1 - y) : y;
-        else out_row = lrow * kTile + ly;   // compact strip layout; assembled (and flipped) by the caller after the gather
-        const size_t at = (size_t)out_row * width + x;
-        if (FORMAT == GS_FRAME_RGBA32F) {
-            reinterpret_cast<float4 *>(frame)[at] = make_float4(Cr, Cg, Cb, A);
-        } else {
-            const uint32_t r8 = (uint32_t)(__saturatef(Cr) * 255.0f + 0.5f), g8 = (uint32_t)(__saturatef(Cg) * 255.0f + 0.5f);
-            const uint32_t b8 = (uint32_t)(__saturatef(Cb) * 255.0f + 0.5f), a8 = (uint32_t)(__saturatef(A) * 255.0f + 0.5f);
-            reinterpret_cast<uint32_t *>(frame)[at] = r8 | (g8 << 8) | (b8 << 16) | (a8 << 24);
+    if (x < width) {
+#pragma unroll
+        for (int k = 0; k < kBlendPix; ++k) {
+            const int y = y0 + k;
+            if (y >= height) break;
+            const float A = 1.0f - T[k]; // alpha accumulates as 1 - prod(1 - alpha_i)
+            int out_row;
+            if (world == 1) out_row = flip_y ? (height - 1 - y) : y;
+            else out_row = (ty / (int)world) * kTile + ly0 + k;   // compact strip layout; assembled (and flipped) by the caller after the gather
+            const size_t at = (size_t)out_row * width + x;
+            if (FORMAT == GS_FRAME_RGBA32F) {
+                reinterpret_cast<float4 *>(frame)[at] = make_float4(Cr[k], Cg[k], Cb[k], A);
+            } else {
+                const uint32_t r8 = (uint32_t)(__saturatef(Cr[k]) * 255.0f + 0.5f), g8 = (uint32_t)(__saturatef(Cg[k]) * 255.0f + 0.5f);
+                const uint32_t b8 = (uint32_t)(__saturatef(Cb[k]) * 255.0f + 0.5f), a8 = (uint32_t)(__saturatef(A) * 255.0f + 0.5f);
+                reinterpret_cast<uint32_t *>(frame)[at] = r8 | (g8 << 8) | (b8 << 16) | (a8 << 24);
+            }
         }
     }
 }
@@ -547,7 +561,8 @@ __global__ void k_export_projected(const SplatRecord *__restrict__ rec, const us
     o.b2x = n2 > 0.f ? r.g2x / n2 : 0.f; o.b2y = n2 > 0.f ? r.g2y / n2 : 0.f;
     o.r = r.r; o.g = r.g; o.b = r.b; o.a = r.a;
     o.ndc_z = r.ndc_z;
-    o.valid = r.valid;
+    o.valid = (r.ndc_z >= -1.0f && r.ndc_z <= 1.0f) ? 1u : 0u;
+    if (!o.valid) o.ndc_z = 0.f;
     out[s] = o;
 }
 
@@ -576,19 +591,19 @@ struct RasterState {
     bool have_scene_idx = false;
     RBuf<SplatRecord> records;
     RBuf<ushort4> rects;
-    RBuf<uint32_t> offsets;
-    RBuf<uint32_t> ikeys[2];   // instance keys ping/pong (u16 or u32 elements)
-    RBuf<uint32_t> ivals[2];   // instance values ping/pong
-    RBuf<uint32_t> list;       // final per-tile lists
+    RBuf<uint32_t> block_sums; // coarse instances per chunk of draw ranks
+    RBuf<uint16_t> ikeys[2];   // instance keys ping/pong (coarse tile ids)
+    RBuf<unsigned long long> ivals[2];   // instance values ping/pong: {fine-tile mask, splat id}
+    RBuf<unsigned long long> list;       // final per-coarse-tile lists
     RBuf<uint2> ranges;
     RBuf<RasterControl> rctl;
     RBuf<SortControl> sctl;
-    RBuf<uint32_t> lookback;
-    RBuf<unsigned long long> scan_lookback;
+    RBuf<uint32_t> lookback;   // radix tile histograms
     RBuf<DynamicUniforms> dyn;
     RBuf<unsigned char> frame;
     RBuf<gs_projected_splat> exported;
     unsigned long long instance_capacity = 0;
+    uint32_t hist_stride = 0;
     int sm_count = 148;
     int last_format = GS_FRAME_RGBA32F;
     size_t last_frame_bytes = 0;
@@ -613,27 +628,25 @@ static int raster_init(RasterState &rs, const gs_config &c, int sm_count) {
         RCU(rs.cc.ensure(n));
         RCU(rs.records.ensure(n));
         RCU(rs.rects.ensure(n));
-        RCU(rs.offsets.ensure(n));
+        RCU(rs.block_sums.ensure((n + kBinTile - 1) / kBinTile + 1));
         const char *f = getenv("GS_INSTANCE_FACTOR");
-        const double factor = f ? atof(f) : 12.0;
+        const double factor = f ? atof(f) : 4.0;
         const size_t tiles = (size_t)((c.max_width + kTile - 1) / kTile) * ((c.max_height + kTile - 1) / kTile);
         rs.instance_capacity = (unsigned long long)(factor * (double)n) + 4ull * tiles + 65536ull;
         if (rs.instance_capacity > 0xfffffff0ull) rs.instance_capacity = 0xfffffff0ull;
         for (int i = 0; i < 2; ++i) { RCU(rs.ikeys[i].ensure(rs.instance_capacity)); RCU(rs.ivals[i].ensure(rs.instance_capacity)); }
         RCU(rs.list.ensure(rs.instance_capacity));
-        RCU(rs.ranges.ensure(tiles));
+        RCU(rs.ranges.ensure(65536));
         RCU(rs.frame.ensure((size_t)c.max_width * (c.max_height + kTile) * 16));
-        const size_t itiles = (rs.instance_capacity + kRadixTile - 1) / kRadixTile;
-        RCU(rs.lookback.ensure(itiles * kRadix * 3));
-        RCU(rs.scan_lookback.ensure((n + kScanTile - 1) / kScanTile + 1));
+        RCU(rs.lookback.ensure(radix_tile_hist_words(rs.instance_capacity, 2, &rs.hist_stride)));
     }
     return GS_OK;
 }
 
 static void raster_release(RasterState &rs) {
     rs.cc.release(); rs.cov.release(); rs.sh.release(); rs.scene_idx.release(); rs.records.release(); rs.rects.release();
-    rs.offsets.release(); rs.ikeys[0].release(); rs.ikeys[1].release(); rs.ivals[0].release(); rs.ivals[1].release();
-    rs.list.release(); rs.ranges.release(); rs.rctl.release(); rs.sctl.release(); rs.lookback.release(); rs.scan_lookback.release();
+    rs.block_sums.release(); rs.ikeys[0].release(); rs.ikeys[1].release(); rs.ivals[0].release(); rs.ivals[1].release();
+    rs.list.release(); rs.ranges.release(); rs.rctl.release(); rs.sctl.release(); rs.lookback.release();
     rs.dyn.release(); rs.frame.release(); rs.exported.release();
 }
 
@@ -718,14 +731,13 @@ static int raster_render(RasterState &rs, const gs_config &c, const gs_uniforms 
         RCU(cudaMemcpyAsync(rs.dyn.p, &du, sizeof(du), cudaMemcpyHostToDevice, st)); // pageable source: staged before return
     }
 
+    const int coarse_x = (tiles_x + kCoarseW - 1) / kCoarseW, coarse_y = (tiles_y + kCoarseH - 1) / kCoarseH;
+    const uint32_t ncoarse = (uint32_t)coarse_x * (uint32_t)coarse_y;
+    if (ncoarse > 65536u) { snprintf(raster_err(), 512, "frame %ux%u needs %u coarse tiles (> 65536)", p.width, p.height, ncoarse); return GS_ERR_BAD_ARG; }
     int tile_bits = 1;
-    while ((1u << tile_bits) < std::max(local_tiles, 2u)) ++tile_bits;
+    while ((1u << tile_bits) < std::max(ncoarse, 2u)) ++tile_bits;
     const PassPlan pl = make_plan_bits(tile_bits);
-    const size_t itiles = (rs.instance_capacity + kRadixTile - 1) / kRadixTile;
-    const uint32_t scan_tiles = (p.render_count + kScanTile - 1) / kScanTile;
-    // look-back words actually needed are bounded by the capacity; zero only what the instance count can touch (worst case)
-    k_raster_init<<<rs.sm_count * 2, 256, 0, st>>>(rs.rctl.p, rs.sctl.p, rs.ranges.p, local_tiles, rs.lookback.p, itiles * kRadix * pl.npasses,
-                                                 rs.scan_lookback.p, (size_t)scan_tiles + 1);
+    k_raster_init<<<8, 256, 0, st>>>(rs.rctl.p, rs.sctl.p, rs.ranges.p, ncoarse);
     ++launches;
     prof.mark("k_raster_init", st);
     const uint32_t count = rs.uploaded;
@@ -734,42 +746,30 @@ static int raster_render(RasterState &rs, const gs_config &c, const gs_uniforms 
     prof.mark("k_project", st);
     RCU(cudaEventRecord(ev_project, st));
     if (p.render_count && local_tiles) {
-        k_tile_count<<<scan_tiles, kScanThreads, 0, st>>>(d_order, p.render_count, rs.rects.p, rank, world, rs.offsets.p, rs.scan_lookback.p, rs.rctl.p, rs.instance_capacity);
+        const uint32_t chunks = (p.render_count + kBinTile - 1) / kBinTile;
+        k_tile_count<<<chunks, kBinThreads, 0, st>>>(d_order, p.render_count, rs.rects.p, rs.block_sums.p, rs.rctl.p);
         ++launches;
         prof.mark("k_tile_count", st);
-        const int eblocks = (int)std::min<uint64_t>(((uint64_t)p.render_count + kEmitThreads - 1) / kEmitThreads, (uint64_t)rs.sm_count * 8);
-        if (tile_bits <= 16) {
-            k_tile_emit<uint16_t><<<eblocks, kEmitThreads, 0, st>>>(d_order, p.render_count, rs.rects.p, rs.offsets.p, rank, world, tiles_x,
-                                                                  (uint16_t *)rs.ikeys[0].p, rs.ivals[0].p, rs.instance_capacity, pl, rs.sctl.p);
-        } else {
-            k_tile_emit<uint32_t><<<eblocks, kEmitThreads, 0, st>>>(d_order, p.render_count, rs.rects.p, rs.offsets.p, rank, world, tiles_x,
-                                                                  rs.ikeys[0].p, rs.ivals[0].p, rs.instance_capacity, pl, rs.sctl.p);
-        }
+        k_tile_emit<<<chunks, kBinThreads, 0, st>>>(d_order, p.render_count, rs.rects.p, rs.block_sums.p, coarse_x, rs.ikeys[0].p, rs.ivals[0].p,
+                                                   rs.instance_capacity, rs.rctl.p);
         ++launches;
         prof.mark("k_tile_emit", st);
-        static const char *const tile_pass_names[4] = {"k_radix_pass[tile,0]", "k_radix_pass[tile,1]", "k_radix_pass[tile,2]", "k_radix_pass[tile,3]"};
+        static const RadixNames names = {{"k_radix_hist[tile,0]", "k_radix_hist[tile,1]", "k_radix_hist[tile,2]", "k_radix_hist[tile,3]"},
+                                         {"k_radix_scan[tile,0]", "k_radix_scan[tile,1]", "k_radix_scan[tile,2]", "k_radix_scan[tile,3]"},
+                                         {"k_radix_scatter[tile,0]", "k_radix_scatter[tile,1]", "k_radix_scatter[tile,2]", "k_radix_scatter[tile,3]"}};
         // The instance count lives on the device only: the radix grids are sized for the capacity and surplus CTAs exit.
         const unsigned long long *n_dev = &rs.rctl.p->total_instances;
-        if (tile_bits <= 16) {
-            radix_sort_pairs<uint16_t>((uint16_t *)rs.ikeys[0].p, (uint16_t *)rs.ikeys[1].p, rs.ivals[0].p, 0u, kValArray, rs.ivals[1].p, rs.ivals[0].p,
-                                       rs.list.p, 0u, n_dev, rs.instance_capacity, pl, rs.sctl.p, rs.lookback.p, true, st, launches, &prof, tile_pass_names);
-            const uint16_t *sorted_keys = (pl.npasses & 1) ? (const uint16_t *)rs.ikeys[1].p : (const uint16_t *)rs.ikeys[0].p;
-            k_tile_ranges<uint16_t><<<rs.sm_count * 4, 256, 0, st>>>(sorted_keys, rs.rctl.p, rs.instance_capacity, rs.ranges.p);
-        } else {
-            radix_sort_pairs<uint32_t>(rs.ikeys[0].p, rs.ikeys[1].p, rs.ivals[0].p, 0u, kValArray, rs.ivals[1].p, rs.ivals[0].p, rs.list.p, 0u, n_dev,
-                                       rs.instance_capacity, pl, rs.sctl.p, rs.lookback.p, true, st, launches, &prof, tile_pass_names);
-            const uint32_t *sorted_keys = (pl.npasses & 1) ? rs.ikeys[1].p : rs.ikeys[0].p;
-            k_tile_ranges<uint32_t><<<rs.sm_count * 4, 256, 0, st>>>(sorted_keys, rs.rctl.p, rs.instance_capacity, rs.ranges.p);
-        }
-        ++launches;
-        prof.mark("k_tile_ranges", st);
+        radix_sort_pairs<uint16_t, unsigned long long>(rs.ikeys[0].p, rs.ikeys[1].p, rs.ivals[0].p, 0u, kValArray, rs.ivals[1].p, rs.ivals[0].p, rs.list.p, 0u,
+                                                       n_dev, rs.instance_capacity, pl, rs.sctl.p, rs.lookback.p, rs.hist_stride, false, rs.ranges.p, st, launches,
+                                                       &prof, names);
     }
     RCU(cudaEventRecord(ev_bin, st));
     if (local_tiles) {
+        const uint32_t grid = ncoarse * kFinePerCoarse;
         if (p.frame_format == GS_FRAME_RGBA8)
-            k_blend<GS_FRAME_RGBA8><<<local_tiles, kBlendThreads, 0, st>>>(rs.ranges.p, rs.list.p, rs.records.p, tiles_x, rank, world, (int)p.width, (int)p.height, p.flip_y, rs.frame.p);
+            k_blend<GS_FRAME_RGBA8><<<grid, kBlendThreads, 0, st>>>(rs.ranges.p, rs.list.p, rs.records.p, tiles_x, tiles_y, coarse_x, rank, world, (int)p.width, (int)p.height, p.flip_y, rs.frame.p);
         else
-            k_blend<GS_FRAME_RGBA32F><<<local_tiles, kBlendThreads, 0, st>>>(rs.ranges.p, rs.list.p, rs.records.p, tiles_x, rank, world, (int)p.width, (int)p.height, p.flip_y, rs.frame.p);
+            k_blend<GS_FRAME_RGBA32F><<<grid, kBlendThreads, 0, st>>>(rs.ranges.p, rs.list.p, rs.records.p, tiles_x, tiles_y, coarse_x, rank, world, (int)p.width, (int)p.height, p.flip_y, rs.frame.p);
         ++launches;
         prof.mark("k_blend", st);
     }

@@ -3,7 +3,7 @@
 // Replaces the reference's sortIndexes() (src/worker/sorter.cpp:17-168) stage by stage:
 //   k_depth      : distance pass, all six branches            sorter.cpp:29-140   (+ running min/max :24-25)
 //   k_bucket     : f32 range map + bucket                      sorter.cpp:142-149  (+ per-digit histograms)
-//   k_radix_pass : stable LSD one-sweep scatter, 8-bit digits  sorter.cpp:151-167  (prefix sum + backward scatter)
+//   k_radix_*    : stable LSD radix sort (hist/scan/scatter)   sorter.cpp:151-167  (prefix sum + backward scatter)
 // The reference's output is reverse(stable ascending by bucket); we sort key = (R-1-bucket) ascending, stably,
 // over the REVERSED input sequence, which is the same permutation.
 //
@@ -25,9 +25,8 @@ struct DepthParams {
 };
 
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void k_sort_init(SortControl *ctl, uint32_t *lookback, size_t lookback_words) {
-    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
+__global__ void k_sort_init(SortControl *ctl) {
+    const uint32_t tid = threadIdx.x;
     if (tid == 0) {
         ctl->dmin = 2147483640;
         ctl->dmax = -2147483640;
@@ -35,8 +34,7 @@ __global__ void k_sort_init(SortControl *ctl, uint32_t *lookback, size_t lookbac
         for (int i = 0; i < 4; ++i) ctl->ticket[i] = 0;
     }
     uint32_t *h = &ctl->hist[0][0];
-    for (size_t i = tid; i < 4 * kRadix; i += stride) h[i] = 0;
-    for (size_t i = tid; i < lookback_words; i += stride) lookback[i] = 0;
+    for (uint32_t i = tid; i < 4 * kRadix; i += blockDim.x) h[i] = 0;
 }
 
 // third row of (mvp * T_scene), f32, left-to-right, unfused (sorter.cpp:11-15)
@@ -144,62 +142,20 @@ k_depth(const uint32_t *__restrict__ indexes, const void *__restrict__ centers, 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Bucket + key.  key[j] = (R-1) - bucket(dist[i]) written at the REVERSED position j = rc-1-i, plus the digit
-// histograms of every radix pass.  Optionally leaves the bucket in dist[i] (the reference's mappedDistances).
+// Stable LSD radix sort, 8-bit digits, three kernels per pass and NO cross-CTA dependency chain:
+//   H  k_radix_hist    per-tile digit histogram            -> tile_hist[digit][tile]   (+ global digit totals)
+//   S  k_radix_scan    per digit: exclusive scan over tiles + global digit base (in place: counts become offsets)
+//   P  k_radix_scatter rank inside the tile (warp match), reorder through shared memory, coalesced scatter
+// A one-sweep (decoupled look-back) variant was measured first: at the sizes of this path (1M-16M keys, ~300 co-resident
+// CTAs) the look-back chain of the first wave costs ~k/2 L2 round trips for tile k and dominated the pass (profiles/).
+//   tile = kRadixThreads * kRadixItems consecutive elements; warp w owns a contiguous 32*ITEMS run, item k of lane l
+//   is element run_base + 32k + l, so (warp, k, lane) order == sequence order and ranks are stable.
 struct PassPlan {
     int npasses;
     int shift[4];
     int bits[4];
 };
 
-constexpr int kBucketThreads = 256;
-constexpr int kBucketItems = 4;
-
-template <typename KeyT>
-__global__ void __launch_bounds__(kBucketThreads)
-k_bucket(int32_t *__restrict__ dist, KeyT *__restrict__ keys, uint32_t s0, uint32_t rc, uint32_t R, PassPlan plan,
-         int write_buckets, SortControl *ctl) {
-    __shared__ uint32_t s_hist[4][kRadix];
-    for (int i = threadIdx.x; i < 4 * kRadix; i += kBucketThreads) (&s_hist[0][0])[i] = 0;
-    __syncthreads();
-    const int32_t dmin = ctl->dmin, dmax = ctl->dmax;
-    const float span = __fsub_rn(__int2float_rn(dmax), __int2float_rn(dmin)); // sorter.cpp:142
-    const float range_map = __fdiv_rn(__uint2float_rn(R - 1u), span);          // sorter.cpp:143
-    const bool degenerate = (dmax == dmin);
-    uint32_t err = 0;
-    const uint32_t tile = kBucketThreads * kBucketItems;
-    for (uint64_t base = (uint64_t)s0 + (uint64_t)blockIdx.x * tile; base < rc; base += (uint64_t)gridDim.x * tile) {
-#pragma unroll
-        for (int k = 0; k < kBucketItems; ++k) {
-            const uint64_t i = base + (uint64_t)k * kBucketThreads + threadIdx.x;
-            if (i < rc) {
-                const int32_t d = dist[i];
-                const int32_t rel = (int32_t)((uint32_t)d - (uint32_t)dmin);
-                int32_t b = __float2int_rz(__fmul_rn(__int2float_rn(rel), range_map)); // sorter.cpp:146
-                if (degenerate) b = 0;               // defined deviation: the reference traps / writes out of bounds
-                if (b < 0 || (uint32_t)b >= R) { err |= kErrBucketRange; b = b < 0 ? 0 : (int32_t)(R - 1u); }
-                if (write_buckets) dist[i] = b;
-                const uint32_t key = (R - 1u) - (uint32_t)b;
-                keys[(uint64_t)rc - 1u - i] = (KeyT)key;
-#pragma unroll
-                for (int p = 0; p < 4; ++p)
-                    if (p < plan.npasses) atomicAdd(&s_hist[p][(key >> plan.shift[p]) & ((1u << plan.bits[p]) - 1u)], 1u);
-            }
-        }
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < plan.npasses * kRadix; i += kBucketThreads) {
-        const uint32_t v = (&s_hist[0][0])[i];
-        if (v) atomicAdd(&ctl->hist[0][0] + i, v);
-    }
-    if (err) atomicOr(&ctl->error, err);
-    if (degenerate && blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&ctl->error, kErrDegenerate);
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// One-sweep radix pass (stable, 8-bit digit, decoupled look-back across tiles).
-//   tile = kRadixThreads * kRadixItems consecutive elements; warp w owns a contiguous 32*ITEMS run, item k of lane l
-//   is element run_base + 32k + l, so (warp, k, lane) order == sequence order and ranks are stable.
 constexpr int kRadixThreads = 512;
 constexpr int kRadixItems = 8;
 constexpr int kRadixTile = kRadixThreads * kRadixItems;
@@ -207,43 +163,143 @@ constexpr int kRadixWarps = kRadixThreads / 32;
 
 enum ValMode : int { kValArray = 0, kValArrayReversed = 1, kValIotaReversed = 2 };
 
-constexpr uint32_t kFlagAggregate = 1u << 30;
-constexpr uint32_t kFlagPrefix = 2u << 30;
-constexpr uint32_t kFlagMask = 3u << 30;
-
-template <typename KeyT, int VALMODE, bool WRITE_KEYS>
+// Bucket + key (sorter.cpp:142-149), one CTA per radix tile of the REVERSED sequence: key[j] = (R-1) - bucket(dist[i]) with
+// j = rc-1-i.  Also the pass-0 tile histogram (H of pass 0 fused here) and the global digit totals of EVERY pass.
+// Optionally leaves the bucket in dist[i] (the reference's mappedDistances).
+template <typename KeyT>
 __global__ void __launch_bounds__(kRadixThreads)
-k_radix_pass(const KeyT *__restrict__ keys_in, const uint32_t *__restrict__ vals_in, uint32_t iota_top,
-             KeyT *__restrict__ keys_out, uint32_t *__restrict__ vals_out, uint32_t n_host,
-             const unsigned long long *__restrict__ n_dev, unsigned long long n_cap, int shift, int bits,
-             const uint32_t *__restrict__ pass_hist, uint32_t *lookback, uint32_t *ticket) {
-    // element count: known on the host (depth sort) or only on the device (tile instances; grid sized for capacity)
+k_bucket(int32_t *__restrict__ dist, KeyT *__restrict__ keys, uint32_t s0, uint32_t rc, uint32_t R, PassPlan plan,
+         int write_buckets, SortControl *ctl, uint32_t *__restrict__ tile_hist, uint32_t stride) {
+    __shared__ uint32_t s_hist[4][kRadix];
+    for (int i = threadIdx.x; i < 4 * kRadix; i += kRadixThreads) (&s_hist[0][0])[i] = 0;
+    __syncthreads();
+    const int32_t dmin = ctl->dmin, dmax = ctl->dmax;
+    const float span = __fsub_rn(__int2float_rn(dmax), __int2float_rn(dmin)); // sorter.cpp:142
+    const float range_map = __fdiv_rn(__uint2float_rn(R - 1u), span);          // sorter.cpp:143
+    const bool degenerate = (dmax == dmin);
+    uint32_t err = 0;
+    const uint32_t n = rc - s0;
+    const uint64_t jbase = (uint64_t)blockIdx.x * kRadixTile;
+    int32_t d[kRadixItems];
+#pragma unroll
+    for (int k = 0; k < kRadixItems; ++k) {
+        const uint64_t j = jbase + (uint64_t)k * kRadixThreads + threadIdx.x;
+        d[k] = (j < n) ? dist[(uint64_t)rc - 1u - j] : 0;
+    }
+#pragma unroll
+    for (int k = 0; k < kRadixItems; ++k) {
+        const uint64_t j = jbase + (uint64_t)k * kRadixThreads + threadIdx.x;
+        if (j < n) {
+            const int32_t rel = (int32_t)((uint32_t)d[k] - (uint32_t)dmin);
+            int32_t b = __float2int_rz(__fmul_rn(__int2float_rn(rel), range_map)); // sorter.cpp:146
+            if (degenerate) b = 0;               // defined deviation: the reference traps / writes out of bounds
+            if (b < 0 || (uint32_t)b >= R) { err |= kErrBucketRange; b = b < 0 ? 0 : (int32_t)(R - 1u); }
+            if (write_buckets) dist[(uint64_t)rc - 1u - j] = b;
+            const uint32_t key = (R - 1u) - (uint32_t)b;
+            keys[j] = (KeyT)key;
+#pragma unroll
+            for (int p = 0; p < 4; ++p)
+                if (p < plan.npasses) atomicAdd(&s_hist[p][(key >> plan.shift[p]) & ((1u << plan.bits[p]) - 1u)], 1u);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < kRadix) tile_hist[(size_t)threadIdx.x * stride + blockIdx.x] = s_hist[0][threadIdx.x];
+    for (int i = threadIdx.x; i < plan.npasses * kRadix; i += kRadixThreads) {
+        const uint32_t v = (&s_hist[0][0])[i];
+        if (v) atomicAdd(&ctl->hist[0][0] + i, v);
+    }
+    if (err) atomicOr(&ctl->error, err);
+    if (degenerate && blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&ctl->error, kErrDegenerate);
+}
+
+// H: per-tile digit histogram; `add_global` also accumulates the pass's global digit totals.
+template <typename KeyT>
+__global__ void __launch_bounds__(kRadixThreads)
+k_radix_hist(const KeyT *__restrict__ keys, uint32_t n_host, const unsigned long long *__restrict__ n_dev, unsigned long long n_cap,
+             int shift, int bits, uint32_t *__restrict__ tile_hist, uint32_t stride, uint32_t *global_hist, int add_global) {
     const uint32_t n = n_dev ? (uint32_t)min(*n_dev, n_cap) : n_host;
+    const uint64_t base = (uint64_t)blockIdx.x * kRadixTile;
+    if (base >= n) return;
+    __shared__ uint32_t s_hist[kRadix];
+    if (threadIdx.x < kRadix) s_hist[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t dmask = (1u << bits) - 1u;
+#pragma unroll
+    for (int k = 0; k < kRadixItems; ++k) {
+        const uint64_t e = base + (uint64_t)k * kRadixThreads + threadIdx.x;
+        if (e < n) atomicAdd(&s_hist[((uint32_t)keys[e] >> shift) & dmask], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < kRadix) {
+        const uint32_t v = s_hist[threadIdx.x];
+        tile_hist[(size_t)threadIdx.x * stride + blockIdx.x] = v;
+        if (add_global && v) atomicAdd(global_hist + threadIdx.x, v);
+    }
+}
+
+// S: one CTA per digit.  tile_hist[d][t] (count) -> global output offset of tile t's first element with digit d.
+constexpr int kScanColThreads = 1024;
+__global__ void __launch_bounds__(kScanColThreads)
+k_radix_scan(uint32_t *__restrict__ tile_hist, uint32_t stride, uint32_t n_host, const unsigned long long *__restrict__ n_dev,
+             unsigned long long n_cap, const uint32_t *__restrict__ global_hist) {
+    __shared__ uint32_t s_scan[40];
+    __shared__ uint32_t s_carry;
+    const uint32_t n = n_dev ? (uint32_t)min(*n_dev, n_cap) : n_host;
+    const uint32_t ntiles = (uint32_t)(((uint64_t)n + kRadixTile - 1) / kRadixTile);
+    const uint32_t d = blockIdx.x;
+    {   // global base of this digit = total of all smaller digits
+        uint32_t total;
+        const uint32_t c = (threadIdx.x < kRadix && threadIdx.x < d) ? global_hist[threadIdx.x] : 0u;
+        (void)block_exclusive_scan<kScanColThreads>(c, s_scan, total);
+        if (threadIdx.x == 0) s_carry = total;
+    }
+    __syncthreads();
+    uint32_t *col = tile_hist + (size_t)d * stride;
+    for (uint32_t base = 0; base < ntiles; base += kScanColThreads) {
+        const uint32_t t = base + threadIdx.x;
+        const uint32_t v = t < ntiles ? col[t] : 0u;
+        uint32_t total;
+        const uint32_t ex = block_exclusive_scan<kScanColThreads>(v, s_scan, total);
+        const uint32_t carry = s_carry;
+        if (t < ntiles) col[t] = ex + carry;
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry = carry + total;
+        __syncthreads();
+    }
+}
+
+// P: stable scatter of one tile.  RANGES (final pass of the tile-instance sort): the tile's reorder buffer is fully sorted by
+// key, so [first, last+1) of every key's run is found from neighbours; runs may continue in other tiles -> atomicMin/Max.
+template <typename KeyT, typename ValT, int VALMODE, bool WRITE_KEYS, bool RANGES>
+__global__ void __launch_bounds__(kRadixThreads)
+k_radix_scatter(const KeyT *__restrict__ keys_in, const ValT *__restrict__ vals_in, uint32_t iota_top,
+                KeyT *__restrict__ keys_out, ValT *__restrict__ vals_out, uint32_t n_host,
+                const unsigned long long *__restrict__ n_dev, unsigned long long n_cap, int shift, int bits,
+                const uint32_t *__restrict__ tile_offsets, uint32_t stride, uint2 *ranges) {
+    const uint32_t n = n_dev ? (uint32_t)min(*n_dev, n_cap) : n_host;
+    const uint32_t tile = blockIdx.x;
+    const uint64_t tile_base = (uint64_t)tile * kRadixTile;
+    if (tile_base >= n) return; // surplus CTA of a capacity-sized grid (uniform exit)
     // phase A: per-warp digit counters; phase B: reorder buffers (aliased)
-    __shared__ __align__(16) unsigned char s_raw[kRadixTile * (sizeof(KeyT) + 4) > kRadixWarps * (kRadix + 1) * 4
-                                                     ? kRadixTile * (sizeof(KeyT) + 4)
+    __shared__ __align__(16) unsigned char s_raw[kRadixTile * (sizeof(KeyT) + sizeof(ValT)) > kRadixWarps * (kRadix + 1) * 4
+                                                     ? kRadixTile * (sizeof(KeyT) + sizeof(ValT))
                                                      : kRadixWarps * (kRadix + 1) * 4];
     __shared__ uint32_t s_tile_count[kRadix];  // digit totals of this tile
     __shared__ uint32_t s_tile_start[kRadix];  // exclusive scan of the above (slot in the reorder buffer)
     __shared__ uint32_t s_gbase[kRadix];       // global slot of reorder-slot 0 for each digit (wrapping arithmetic)
     __shared__ uint32_t s_scan[40];
-    __shared__ uint32_t s_tile_id;
 
     uint32_t(*s_whist)[kRadix + 1] = reinterpret_cast<uint32_t(*)[kRadix + 1]>(s_raw);
-    uint32_t *s_vals = reinterpret_cast<uint32_t *>(s_raw);
-    KeyT *s_keys = reinterpret_cast<KeyT *>(s_raw + (size_t)kRadixTile * 4);
+    ValT *s_vals = reinterpret_cast<ValT *>(s_raw);
+    KeyT *s_keys = reinterpret_cast<KeyT *>(s_raw + (size_t)kRadixTile * sizeof(ValT));
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_tile_id = atomicAdd(ticket, 1u);
     for (int i = tid; i < kRadixWarps * (kRadix + 1); i += kRadixThreads) (&s_whist[0][0])[i] = 0;
-    __syncthreads();
-    const uint32_t tile = s_tile_id;
-    const uint64_t tile_base = (uint64_t)tile * kRadixTile;
-    if (tile_base >= n) return; // surplus CTA of a capacity-sized grid (uniform exit)
     const uint32_t dmask = (1u << bits) - 1u;
 
     // ---- load keys (+ values), rank within the warp ----------------------------------------------------------
-    uint32_t key[kRadixItems], val[kRadixItems], rank[kRadixItems];
+    uint32_t key[kRadixItems], rank[kRadixItems];
+    ValT val[kRadixItems];
     const uint64_t run_base = tile_base + (uint64_t)warp * (32 * kRadixItems);
 #pragma unroll
     for (int k = 0; k < kRadixItems; ++k) {
@@ -254,11 +310,13 @@ k_radix_pass(const KeyT *__restrict__ keys_in, const uint32_t *__restrict__ vals
     for (int k = 0; k < kRadixItems; ++k) {
         const uint64_t e = run_base + (uint64_t)k * 32 + lane;
         if (e < n) {
-            if (VALMODE == kValArray) val[k] = ld_nc_u32(vals_in + e);
-            else if (VALMODE == kValArrayReversed) val[k] = ld_nc_u32(vals_in + ((uint64_t)n - 1u - e));
-            else val[k] = iota_top - (uint32_t)e;
+            if (VALMODE == kValArray) val[k] = __ldg(vals_in + e);
+            else if (VALMODE == kValArrayReversed) val[k] = __ldg(vals_in + ((uint64_t)n - 1u - e));
+            else val[k] = (ValT)(iota_top - (uint32_t)e);
         } else val[k] = 0;
     }
+    const uint32_t my_offset = tid < kRadix ? tile_offsets[(size_t)tid * stride + tile] : 0u;
+    __syncthreads();
 #pragma unroll
     for (int k = 0; k < kRadixItems; ++k) {
         const uint64_t e = run_base + (uint64_t)k * 32 + lane;
@@ -288,15 +346,9 @@ k_radix_pass(const KeyT *__restrict__ keys_in, const uint32_t *__restrict__ vals
         uint32_t total;
         const uint32_t c = tid < kRadix ? s_tile_count[tid] : 0u;
         const uint32_t ex = block_exclusive_scan<kRadixThreads>(c, s_scan, total);
-        if (tid < kRadix) s_tile_start[tid] = ex;
+        if (tid < kRadix) { s_tile_start[tid] = ex; s_gbase[tid] = my_offset - ex; }
     }
-    // global digit bases: exclusive scan of the pass histogram (recomputed by every tile, 256 values)
-    {
-        uint32_t total;
-        const uint32_t c = tid < kRadix ? pass_hist[tid] : 0u;
-        const uint32_t ex = block_exclusive_scan<kRadixThreads>(c, s_scan, total);
-        if (tid < kRadix) s_gbase[tid] = ex; // completed below
-    }
+    __syncthreads();
     // reorder slots for my items (must be read before the counters are overwritten by the reorder buffers)
     uint32_t slot[kRadixItems];
 #pragma unroll
@@ -306,29 +358,6 @@ k_radix_pass(const KeyT *__restrict__ keys_in, const uint32_t *__restrict__ vals
         slot[k] = (e < n) ? (s_tile_start[d] + s_whist[warp][d] + rank[k]) : 0xffffffffu;
     }
     __syncthreads();
-
-    // ---- decoupled look-back: one thread per digit -----------------------------------------------------------------
-    if (tid < kRadix) {
-        const uint32_t agg = s_tile_count[tid];
-        uint32_t excl = 0;
-        uint32_t *mine = lookback + (size_t)tile * kRadix + tid;
-        if (tile == 0) {
-            st_release_u32(mine, agg | kFlagPrefix);
-        } else {
-            st_release_u32(mine, agg | kFlagAggregate);
-            int64_t t = (int64_t)tile - 1;
-            while (true) {
-                const uint32_t v = ld_acquire_u32(lookback + (size_t)t * kRadix + tid);
-                const uint32_t f = v & kFlagMask;
-                if (f == 0) continue;
-                excl += v & ~kFlagMask;
-                if (f == kFlagPrefix) break;
-                --t;
-            }
-            st_release_u32(mine, (excl + agg) | kFlagPrefix);
-        }
-        s_gbase[tid] = s_gbase[tid] + excl - s_tile_start[tid];
-    }
     // ---- reorder through shared memory so each digit run is written contiguously --------------------------------------
 #pragma unroll
     for (int k = 0; k < kRadixItems; ++k)
@@ -347,6 +376,10 @@ k_radix_pass(const KeyT *__restrict__ keys_in, const uint32_t *__restrict__ vals
             const uint32_t dst = s_gbase[d] + q;
             vals_out[dst] = s_vals[q];
             if (WRITE_KEYS) keys_out[dst] = kk;
+            if (RANGES) {
+                if (q == 0 || s_keys[q - 1] != kk) atomicMin(&ranges[(uint32_t)kk].x, dst);
+                if (q + 1 == valid || s_keys[q + 1] != kk) atomicMax(&ranges[(uint32_t)kk].y, dst + 1u);
+            }
         }
     }
 }
@@ -422,45 +455,61 @@ static inline PassPlan make_plan_bits(int key_bits) {
     return pl;
 }
 
-template <typename KeyT>
-static void launch_radix_pass(uint32_t grid, bool first, bool write_keys, int valmode, const KeyT *kin, const uint32_t *vin, uint32_t iota_top,
-                              KeyT *kout, uint32_t *vout, uint32_t n, const unsigned long long *n_dev, unsigned long long n_cap, int shift, int bits,
-                              const uint32_t *hist, uint32_t *lookback, uint32_t *ticket, cudaStream_t st) {
-#define GS_PASS(VM, WK) k_radix_pass<KeyT, VM, WK><<<grid, kRadixThreads, 0, st>>>(kin, vin, iota_top, kout, vout, n, n_dev, n_cap, shift, bits, hist, lookback, ticket)
+template <typename KeyT, typename ValT>
+static void launch_radix_scatter(uint32_t grid, bool first, bool write_keys, bool want_ranges, int valmode, const KeyT *kin, const ValT *vin,
+                                 uint32_t iota_top, KeyT *kout, ValT *vout, uint32_t n, const unsigned long long *n_dev, unsigned long long n_cap,
+                                 int shift, int bits, const uint32_t *tile_offsets, uint32_t stride, uint2 *ranges, cudaStream_t st) {
+#define GS_PASS(VM, WK, RG) k_radix_scatter<KeyT, ValT, VM, WK, RG><<<grid, kRadixThreads, 0, st>>>(kin, vin, iota_top, kout, vout, n, n_dev, n_cap, shift, bits, tile_offsets, stride, ranges)
     if (!first) valmode = kValArray;
-    if (valmode == kValArray) { if (!write_keys) GS_PASS(kValArray, false); else GS_PASS(kValArray, true); }
-    else if (valmode == kValArrayReversed) { if (!write_keys) GS_PASS(kValArrayReversed, false); else GS_PASS(kValArrayReversed, true); }
-    else { if (!write_keys) GS_PASS(kValIotaReversed, false); else GS_PASS(kValIotaReversed, true); }
+    if (want_ranges) { GS_PASS(kValArray, false, true); }
+    else if (valmode == kValArray) { if (!write_keys) GS_PASS(kValArray, false, false); else GS_PASS(kValArray, true, false); }
+    else if (valmode == kValArrayReversed) { if (!write_keys) GS_PASS(kValArrayReversed, false, false); else GS_PASS(kValArrayReversed, true, false); }
+    else { if (!write_keys) GS_PASS(kValIotaReversed, false, false); else GS_PASS(kValIotaReversed, true, false); }
 #undef GS_PASS
 }
 
-// Stable LSD radix sort of (key, value) pairs.  `first_valmode` selects how the first pass obtains its values.
-// Sorted values land in vals_final; sorted keys (if write_keys_last) in keys1 when npasses is odd, else keys0.
-template <typename KeyT>
-static void radix_sort_pairs(KeyT *keys0, KeyT *keys1, const uint32_t *vals_src, uint32_t iota_top, int first_valmode, uint32_t *vtmp0,
-                             uint32_t *vtmp1, uint32_t *vals_final, uint32_t n, const unsigned long long *n_dev, unsigned long long n_cap,
-                             const PassPlan &pl, SortControl *ctl, uint32_t *lookback, bool write_keys_last, cudaStream_t st, uint32_t &launches,
-                             Profiler *prof = nullptr, const char *const *pass_names = nullptr) {
+struct RadixNames { const char *hist[4], *scan[4], *scatter[4]; };
+
+// Stable LSD radix sort of (key, value) pairs.  `first_valmode` selects how the first pass obtains its values;
+// `hist0_done`: the pass-0 tile histogram and all global digit totals were already produced by the key generator (k_bucket).
+// Sorted values land in vals_final.  `ranges` (optional): per-key [first, last+1) of the sorted output (final pass).
+// tile_hist: [npasses][kRadix][stride] words of scratch.
+template <typename KeyT, typename ValT>
+static void radix_sort_pairs(KeyT *keys0, KeyT *keys1, const ValT *vals_src, uint32_t iota_top, int first_valmode, ValT *vtmp0,
+                             ValT *vtmp1, ValT *vals_final, uint32_t n, const unsigned long long *n_dev, unsigned long long n_cap,
+                             const PassPlan &pl, SortControl *ctl, uint32_t *tile_hist, uint32_t stride, bool hist0_done, uint2 *ranges,
+                             cudaStream_t st, uint32_t &launches, Profiler *prof, const RadixNames &names) {
     const unsigned long long n_grid = n_dev ? n_cap : n;
     const uint32_t tiles = (uint32_t)((n_grid + kRadixTile - 1) / kRadixTile);
     if (!tiles) return;
     KeyT *kin = keys0, *kout = keys1;
-    const uint32_t *vin = vals_src;
-    uint32_t *vt[2] = {vtmp0, vtmp1};
+    const ValT *vin = vals_src;
+    ValT *vt[2] = {vtmp0, vtmp1};
     for (int p = 0; p < pl.npasses; ++p) {
         const bool last = (p == pl.npasses - 1);
-        uint32_t *vout = last ? vals_final : vt[p & 1];
-        launch_radix_pass<KeyT>(tiles, p == 0, !last || write_keys_last, first_valmode, kin, vin, iota_top, kout, vout, n, n_dev, n_cap, pl.shift[p],
-                                pl.bits[p], &ctl->hist[p][0], lookback + (size_t)p * tiles * kRadix, &ctl->ticket[p], st);
+        ValT *vout = last ? vals_final : vt[p & 1];
+        uint32_t *th = tile_hist + (size_t)p * kRadix * stride;
+        if (!(p == 0 && hist0_done)) {
+            k_radix_hist<KeyT><<<tiles, kRadixThreads, 0, st>>>(kin, n, n_dev, n_cap, pl.shift[p], pl.bits[p], th, stride, &ctl->hist[p][0], hist0_done ? 0 : 1);
+            ++launches;
+            if (prof) prof->mark(names.hist[p], st);
+        }
+        k_radix_scan<<<1u << pl.bits[p], kScanColThreads, 0, st>>>(th, stride, n, n_dev, n_cap, &ctl->hist[p][0]);
         ++launches;
-        if (prof) prof->mark(pass_names ? pass_names[p] : "k_radix_pass", st);
+        if (prof) prof->mark(names.scan[p], st);
+        launch_radix_scatter<KeyT, ValT>(tiles, p == 0, !last, last && ranges != nullptr, first_valmode, kin, vin, iota_top, kout, vout, n, n_dev, n_cap,
+                                   pl.shift[p], pl.bits[p], th, stride, ranges, st);
+        ++launches;
+        if (prof) prof->mark(names.scatter[p], st);
         vin = vout;
         KeyT *t = kin; kin = kout; kout = t;
     }
 }
-static inline size_t radix_lookback_words(unsigned long long n, int npasses) {
+static inline size_t radix_tile_hist_words(unsigned long long n, int npasses, uint32_t *stride_out) {
     const size_t tiles = (size_t)((n + kRadixTile - 1) / kRadixTile);
-    return tiles * kRadix * (size_t)npasses;
+    const size_t stride = (tiles + 31) & ~(size_t)31;
+    if (stride_out) *stride_out = (uint32_t)stride;
+    return stride * kRadix * (size_t)npasses;
 }
 
 } // namespace gs

@@ -111,7 +111,7 @@ EXPORTED_SYMBOLS = [
     "gs_create", "gs_destroy", "gs_upload_centers", "gs_sort", "gs_compute_distances", "gs_upload_splat_data",
     "gs_render", "gs_frame", "gs_buffer_dev", "gs_stream", "gs_synchronize", "gs_host_alloc", "gs_host_free",
     "gs_read_projected", "gs_last_timings", "gs_frame_async", "gs_flush_l2", "gs_event_create", "gs_event_record",
-    "gs_event_elapsed_ms", "gs_event_destroy", "gs_set_profiling", "gs_kernel_timings",
+    "gs_event_elapsed_ms", "gs_event_destroy", "gs_set_profiling", "gs_kernel_timings", "gs_set_graph_enabled",
 ]
 
 _lib = None
@@ -184,6 +184,8 @@ def load() -> C.CDLL:
     lib.gs_event_destroy.argtypes = [vp]
     lib.gs_set_profiling.restype = C.c_int
     lib.gs_set_profiling.argtypes = [vp, C.c_int]
+    lib.gs_set_graph_enabled.restype = C.c_int
+    lib.gs_set_graph_enabled.argtypes = [vp, C.c_int]
     lib.gs_kernel_timings.restype = C.c_int
     lib.gs_kernel_timings.argtypes = [vp, C.POINTER(gs_kernel_time), u32, C.POINTER(u32)]
     _ = i32

@@ -105,6 +105,7 @@ struct gs_engine {
     DevBuf<uint32_t> sorted;         // sortedIndexes
     DevBuf<float> transforms;        // 32 x mat4
     DevBuf<SortControl> ctl;
+    DevBuf<DepthParams> depthp;      // per-frame depth parameters (device copy read by k_depth)
     DevBuf<uint32_t> lookback;       // radix tile histograms / offsets [pass][digit][tile]
     DevBuf<uint32_t> freq;           // scratch reproduction for gs_sort_indexes
     uint32_t uploaded_splats = 0;    // 'uploadedSplatCount' SortWorker.js:97
@@ -121,6 +122,12 @@ struct gs_engine {
 
     gs_timings tm{};
     Profiler prof;
+    // CUDA graph of one frame (sort + render), replayed while its shape key is unchanged
+    cudaGraphExec_t graph_exec = nullptr;
+    unsigned long long graph_key[8] = {0};
+    bool graph_enabled = true;
+    bool last_frame_was_graph = false;
+    uint32_t graph_launches = 0;
     bool have_prof_begin = false;    // true while a frame's sort already opened the timeline
     bool pending_async = false;
     gs_render_params pending_rp{};
@@ -162,7 +169,7 @@ extern "C" int gs_create(const gs_config *cfg, gs_engine **out) {
     const size_t n = std::max<uint32_t>(c.max_splat_count, 1);
     if ((rc = e->centers.ensure(n)) || (rc = e->indexes.ensure(n)) || (rc = e->dist.ensure(n)) || (rc = e->sorted.ensure(n)) ||
         (rc = e->vals[0].ensure(n)) || (rc = e->vals[1].ensure(n)) || (rc = e->keys[0].ensure(n)) || (rc = e->keys[1].ensure(n)) ||
-        (rc = e->ctl.ensure(1)) || (rc = e->transforms.ensure(16 * GS_MAX_SCENES)) || (rc = e->h_ctl.ensure(sizeof(SortControl) / 4 + 64))) {
+        (rc = e->ctl.ensure(1)) || (rc = e->depthp.ensure(1)) || (rc = e->transforms.ensure(16 * GS_MAX_SCENES)) || (rc = e->h_ctl.ensure(sizeof(SortControl) / 4 + 64))) {
         gs_destroy(e);
         return rc;
     }
@@ -186,7 +193,7 @@ extern "C" void gs_destroy(gs_engine *e) {
     if (e->stream) cudaStreamSynchronize(e->stream);
     e->centers.release(); e->scene_idx.release(); e->indexes.release(); e->precomputed.release(); e->dist.release();
     e->keys[0].release(); e->keys[1].release(); e->vals[0].release(); e->vals[1].release(); e->sorted.release();
-    e->transforms.release(); e->ctl.release(); e->lookback.release(); e->freq.release();
+    e->transforms.release(); e->ctl.release(); e->depthp.release(); e->lookback.release(); e->freq.release();
     e->h_indexes.release(); e->h_sorted.release(); e->h_ctl.release(); e->h_frame.release(); e->flush.release(); e->prof.release();
     raster_release(e->rs);
     for (int i = 0; i < EV_COUNT; ++i) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
@@ -210,14 +217,14 @@ extern "C" int gs_upload_centers(gs_engine *e, const void *centers, const uint32
 // ---------------------------------------------------------------------------------------------------------------
 template <int MODE>
 static void launch_depth(bool identity, int blocks, cudaStream_t st, const uint32_t *idx, const void *centers, const void *pre,
-                         const uint32_t *scene, const float *tr, const DepthParams &P, uint32_t s0, uint32_t rc, int32_t *dist, SortControl *ctl) {
+                         const uint32_t *scene, const float *tr, const DepthParams *P, uint32_t s0, uint32_t rc, int32_t *dist, SortControl *ctl) {
     if (identity) k_depth<MODE, true><<<blocks, kDepthThreads, 0, st>>>(idx, centers, pre, scene, tr, P, s0, rc, dist, ctl);
     else k_depth<MODE, false><<<blocks, kDepthThreads, 0, st>>>(idx, centers, pre, scene, tr, P, s0, rc, dist, ctl);
 }
 
 // The sort proper, everything already on the device.  d_indexes == nullptr: identity.
 static int sort_on_device(gs_engine *e, const uint32_t *d_indexes, const float *mvp, uint32_t sort_count, uint32_t render_count,
-                          bool use_pre, bool write_buckets) {
+                          bool use_pre, bool write_buckets, bool capturing = false) {
     if (sort_count > render_count) return fail(GS_ERR_BAD_ARG, "sortCount %u > renderCount %u", sort_count, render_count);
     if (render_count > e->cfg.max_splat_count) return fail(GS_ERR_CAPACITY, "renderCount %u > max_splat_count %u", render_count, e->cfg.max_splat_count);
     cudaStream_t st = e->stream;
@@ -227,7 +234,7 @@ static int sort_on_device(gs_engine *e, const uint32_t *d_indexes, const float *
     uint32_t stride = 0;
     int rc = e->lookback.ensure(radix_tile_hist_words(std::max(n, 1u), pl.npasses, &stride));
     if (rc) return rc;
-    CU(cudaEventRecord(e->ev[EV_SORT0], st));
+    if (!capturing) CU(cudaEventRecord(e->ev[EV_SORT0], st));
     e->prof.begin(st);
     k_sort_init<<<1, 256, 0, st>>>(e->ctl.p);
     ++launches;
@@ -241,6 +248,7 @@ static int sort_on_device(gs_engine *e, const uint32_t *d_indexes, const float *
         P.irow[2] = (int32_t)((double)mvp[10] * 1000.0);
         P.irow[3] = 1;
         P.frow[0] = mvp[2]; P.frow[1] = mvp[6]; P.frow[2] = mvp[10]; P.frow[3] = 0.f;
+        if (!capturing) CU(cudaMemcpyAsync(e->depthp.p, &P, sizeof(P), cudaMemcpyHostToDevice, st)); // pageable source: staged before return
         const bool integer = e->cfg.integer_based_sort, dyn = e->cfg.dynamic_mode;
         const int mode = use_pre ? (integer ? kIntPrecomputed : kFloatPrecomputed)
                                  : (integer ? (dyn ? kIntDynamic : kIntStatic) : (dyn ? kFloatDynamic : kFloatStatic));
@@ -248,16 +256,16 @@ static int sort_on_device(gs_engine *e, const uint32_t *d_indexes, const float *
         const bool identity = (d_indexes == nullptr);
         const void *pre = e->precomputed.p;
         switch (mode) {
-            case kIntStatic: launch_depth<kIntStatic>(identity, dblocks, st, d_indexes, e->centers.p, pre, e->scene_idx.p, e->transforms.p, P, s0, render_count, e->dist.p, e->ctl.p); break;
-            case kIntDynamic: launch_depth<kIntDynamic>(identity, dblocks, st, d_indexes, e->centers.p, pre, e->scene_idx.p, e->transforms.p, P, s0, render_count, e->dist.p, e->ctl.p); break;
-            case kIntPrecomputed: launch_depth<kIntPrecomputed>(identity, dblocks, st, d_indexes, e->centers.p, pre, e->scene_idx.p, e->transforms.p, P, s0, render_count, e->dist.p, e->ctl.p); break;
-            case kFloatStatic: launch_depth<kFloatStatic>(identity, dblocks, st, d_indexes, e->centers.p, pre, e->scene_idx.p, e->transforms.p, P, s0, render_count, e->dist.p, e->ctl.p); break;
-            case kFloatDynamic: launch_depth<kFloatDynamic>(identity, dblocks, st, d_indexes, e->centers.p, pre, e->scene_idx.p, e->transforms.p, P, s0, render_count, e->dist.p, e->ctl.p); break;
-            default: launch_depth<kFloatPrecomputed>(identity, dblocks, st, d_indexes, e->centers.p, pre, e->scene_idx.p, e->transforms.p, P, s0, render_count, e->dist.p, e->ctl.p); break;
+            case kIntStatic: launch_depth<kIntStatic>(identity, dblocks, st, d_indexes, e->centers.p, pre, e->scene_idx.p, e->transforms.p, e->depthp.p, s0, render_count, e->dist.p, e->ctl.p); break;
+            case kIntDynamic: launch_depth<kIntDynamic>(identity, dblocks, st, d_indexes, e->centers.p, pre, e->scene_idx.p, e->transforms.p, e->depthp.p, s0, render_count, e->dist.p, e->ctl.p); break;
+            case kIntPrecomputed: launch_depth<kIntPrecomputed>(identity, dblocks, st, d_indexes, e->centers.p, pre, e->scene_idx.p, e->transforms.p, e->depthp.p, s0, render_count, e->dist.p, e->ctl.p); break;
+            case kFloatStatic: launch_depth<kFloatStatic>(identity, dblocks, st, d_indexes, e->centers.p, pre, e->scene_idx.p, e->transforms.p, e->depthp.p, s0, render_count, e->dist.p, e->ctl.p); break;
+            case kFloatDynamic: launch_depth<kFloatDynamic>(identity, dblocks, st, d_indexes, e->centers.p, pre, e->scene_idx.p, e->transforms.p, e->depthp.p, s0, render_count, e->dist.p, e->ctl.p); break;
+            default: launch_depth<kFloatPrecomputed>(identity, dblocks, st, d_indexes, e->centers.p, pre, e->scene_idx.p, e->transforms.p, e->depthp.p, s0, render_count, e->dist.p, e->ctl.p); break;
         }
         ++launches;
         e->prof.mark("k_depth", st);
-        CU(cudaEventRecord(e->ev[EV_DEPTH], st));
+        if (!capturing) CU(cudaEventRecord(e->ev[EV_DEPTH], st));
         const uint32_t tiles = (n + kRadixTile - 1) / kRadixTile;
         const uint32_t R = e->cfg.distance_map_range;
         const uint32_t *vsrc = identity ? nullptr : d_indexes + s0;
@@ -269,22 +277,22 @@ static int sort_on_device(gs_engine *e, const uint32_t *d_indexes, const float *
             k_bucket<uint16_t><<<tiles, kRadixThreads, 0, st>>>(e->dist.p, (uint16_t *)e->keys[0].p, s0, render_count, R, pl, write_buckets ? 1 : 0, e->ctl.p, e->lookback.p, stride);
             ++launches;
             e->prof.mark("k_bucket", st);
-            CU(cudaEventRecord(e->ev[EV_BUCKET], st));
+            if (!capturing) CU(cudaEventRecord(e->ev[EV_BUCKET], st));
             radix_sort_pairs<uint16_t, uint32_t>((uint16_t *)e->keys[0].p, (uint16_t *)e->keys[1].p, vsrc, render_count - 1u, vmode, e->vals[0].p, e->vals[1].p,
                                        e->sorted.p + s0, n, nullptr, 0ull, pl, e->ctl.p, e->lookback.p, stride, true, nullptr, st, launches, &e->prof, names);
         } else {
             k_bucket<uint32_t><<<tiles, kRadixThreads, 0, st>>>(e->dist.p, e->keys[0].p, s0, render_count, R, pl, write_buckets ? 1 : 0, e->ctl.p, e->lookback.p, stride);
             ++launches;
             e->prof.mark("k_bucket", st);
-            CU(cudaEventRecord(e->ev[EV_BUCKET], st));
+            if (!capturing) CU(cudaEventRecord(e->ev[EV_BUCKET], st));
             radix_sort_pairs<uint32_t, uint32_t>(e->keys[0].p, e->keys[1].p, vsrc, render_count - 1u, vmode, e->vals[0].p, e->vals[1].p, e->sorted.p + s0, n,
                                        nullptr, 0ull, pl, e->ctl.p, e->lookback.p, stride, true, nullptr, st, launches, &e->prof, names);
         }
-    } else {
+    } else if (!capturing) {
         CU(cudaEventRecord(e->ev[EV_DEPTH], st));
         CU(cudaEventRecord(e->ev[EV_BUCKET], st));
     }
-    CU(cudaEventRecord(e->ev[EV_SORT1], st));
+    if (!capturing) CU(cudaEventRecord(e->ev[EV_SORT1], st));
     CU(cudaGetLastError());
     e->tm.kernel_launches = launches;
     e->last_render_count = render_count;
@@ -297,10 +305,15 @@ static int finish_sort(gs_engine *e, float *sort_time_ms) {
     CU(cudaMemcpyAsync(e->h_ctl.p, e->ctl.p, 12, cudaMemcpyDeviceToHost, e->stream));
     CU(cudaStreamSynchronize(e->stream));
     float ms = 0.f;
-    cudaEventElapsedTime(&e->tm.depth_ms, e->ev[EV_SORT0], e->ev[EV_DEPTH]);
-    cudaEventElapsedTime(&e->tm.bucket_ms, e->ev[EV_DEPTH], e->ev[EV_BUCKET]);
-    cudaEventElapsedTime(&e->tm.scatter_ms, e->ev[EV_BUCKET], e->ev[EV_SORT1]);
-    cudaEventElapsedTime(&ms, e->ev[EV_SORT0], e->ev[EV_SORT1]);
+    if (e->last_frame_was_graph) {   // one graph launch: only the whole-frame time is observable
+        e->tm.depth_ms = e->tm.bucket_ms = e->tm.scatter_ms = 0.f;
+        cudaEventElapsedTime(&ms, e->ev[EV_SORT0], e->ev[EV_R1]);
+    } else {
+        cudaEventElapsedTime(&e->tm.depth_ms, e->ev[EV_SORT0], e->ev[EV_DEPTH]);
+        cudaEventElapsedTime(&e->tm.bucket_ms, e->ev[EV_DEPTH], e->ev[EV_BUCKET]);
+        cudaEventElapsedTime(&e->tm.scatter_ms, e->ev[EV_BUCKET], e->ev[EV_SORT1]);
+        cudaEventElapsedTime(&ms, e->ev[EV_SORT0], e->ev[EV_SORT1]);
+    }
     e->tm.sort_total_ms = ms;
     if (sort_time_ms) *sort_time_ms = ms;
     const uint32_t err = e->h_ctl.p[2];
@@ -338,6 +351,7 @@ extern "C" int gs_sort(gs_engine *e, const gs_sort_params *p, uint32_t *sorted_o
     q.sort_count = std::min(q.sort_count, e->uploaded_splats);
     if (q.sort_count > q.render_count) return fail(GS_ERR_BAD_ARG, "sortCount %u > renderCount %u", q.sort_count, q.render_count);
     const uint32_t *d_idx = nullptr;
+    e->last_frame_was_graph = false;
     if ((rc = stage_sort_inputs(e, &q, &d_idx))) return rc;
     if ((rc = sort_on_device(e, d_idx, q.model_view_proj, q.sort_count, q.render_count, q.use_precomputed_distances != 0, false))) return rc;
     CU(cudaEventRecord(e->ev[EV_D2H0], e->stream));
@@ -393,6 +407,7 @@ extern "C" int gs_sort_indexes(const uint32_t *indexes, const void *centers, con
     }
     if (renderCount) CU(cudaMemcpyAsync(e->indexes.p, indexes, (size_t)renderCount * 4, cudaMemcpyHostToDevice, st));
     e->uploaded_splats = splatCount;
+    e->last_frame_was_graph = false;
     const bool want_scratch = (mappedDistances != nullptr) || (frequencies != nullptr);
     if ((rc = sort_on_device(e, e->indexes.p, modelViewProj, sortCount, renderCount, usePrecomputedDistances, want_scratch))) return rc;
     // wasm-trap emulation: results are only written back when the device reported no range error
@@ -475,13 +490,13 @@ extern "C" int gs_upload_splat_data(gs_engine *e, const gs_splat_data *d) {
     return GS_OK;
 }
 
-static int render_on_device(gs_engine *e, const gs_uniforms *u, const gs_render_params *p, const uint32_t *d_order) {
+static int render_on_device(gs_engine *e, const gs_uniforms *u, const gs_render_params *p, const uint32_t *d_order, bool capturing = false) {
     cudaStream_t st = e->stream;
-    CU(cudaEventRecord(e->ev[EV_R0], st));
+    if (!capturing) CU(cudaEventRecord(e->ev[EV_R0], st));
     if (!e->have_prof_begin) e->prof.begin(st);
-    int rc = raster_render(e->rs, e->cfg, *u, *p, d_order, st, e->ev[EV_PROJECT], e->ev[EV_BIN], e->tm, e->prof);
+    int rc = raster_render(e->rs, e->cfg, *u, *p, d_order, st, e->ev[EV_PROJECT], e->ev[EV_BIN], e->tm, e->prof, !capturing, !capturing);
     if (rc) return rc;
-    CU(cudaEventRecord(e->ev[EV_R1], st));
+    if (!capturing) CU(cudaEventRecord(e->ev[EV_R1], st));
     CU(cudaGetLastError());
     return GS_OK;
 }
@@ -495,10 +510,15 @@ static int finish_render(gs_engine *e, const gs_render_params *p, void *frame_ou
     CU(cudaEventRecord(e->ev[EV_D2H1], st));
     CU(cudaMemcpyAsync(e->h_ctl.p + 16, e->rs.rctl.p, sizeof(RasterControl), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
-    cudaEventElapsedTime(&e->tm.project_ms, e->ev[EV_R0], e->ev[EV_PROJECT]);
-    cudaEventElapsedTime(&e->tm.bin_ms, e->ev[EV_PROJECT], e->ev[EV_BIN]);
-    cudaEventElapsedTime(&e->tm.blend_ms, e->ev[EV_BIN], e->ev[EV_R1]);
-    cudaEventElapsedTime(&e->tm.render_total_ms, e->ev[EV_R0], e->ev[EV_R1]);
+    if (e->last_frame_was_graph) {
+        e->tm.project_ms = e->tm.bin_ms = e->tm.blend_ms = 0.f;
+        cudaEventElapsedTime(&e->tm.render_total_ms, e->ev[EV_SORT0], e->ev[EV_R1]);   // whole frame (sort + render) in graph mode
+    } else {
+        cudaEventElapsedTime(&e->tm.project_ms, e->ev[EV_R0], e->ev[EV_PROJECT]);
+        cudaEventElapsedTime(&e->tm.bin_ms, e->ev[EV_PROJECT], e->ev[EV_BIN]);
+        cudaEventElapsedTime(&e->tm.blend_ms, e->ev[EV_BIN], e->ev[EV_R1]);
+        cudaEventElapsedTime(&e->tm.render_total_ms, e->ev[EV_R0], e->ev[EV_R1]);
+    }
     cudaEventElapsedTime(&e->tm.d2h_ms, e->ev[EV_D2H0], e->ev[EV_D2H1]);
     RasterControl rc;
     memcpy(&rc, e->h_ctl.p + 16, sizeof(rc));
@@ -530,9 +550,24 @@ extern "C" int gs_render(gs_engine *e, const gs_uniforms *u, const gs_render_par
     if (rc) return rc;
     if (!u || !p) return fail(GS_ERR_BAD_ARG, "gs_render: null argument");
     const uint32_t *d_order = nullptr;
+    e->last_frame_was_graph = false;
     if ((rc = stage_order(e, p, &d_order))) return rc;
     if ((rc = render_on_device(e, u, p, d_order))) return rc;
     return finish_render(e, p, frame_out);
+}
+
+// host-side parameter blocks of one frame -> device (outside any graph; pageable sources are staged by the driver before return)
+static int upload_frame_params(gs_engine *e, const float *mvp, const gs_uniforms &u, const gs_render_params &p) {
+    DepthParams P{};
+    memcpy(P.mvp, mvp, 64);
+    P.irow[0] = (int32_t)((double)mvp[2] * 1000.0);
+    P.irow[1] = (int32_t)((double)mvp[6] * 1000.0);
+    P.irow[2] = (int32_t)((double)mvp[10] * 1000.0);
+    P.irow[3] = 1;
+    P.frow[0] = mvp[2]; P.frow[1] = mvp[6]; P.frow[2] = mvp[10]; P.frow[3] = 0.f;
+    CU(cudaMemcpyAsync(e->depthp.p, &P, sizeof(P), cudaMemcpyHostToDevice, e->stream));
+    int rc = raster_upload_params(e->rs, e->cfg, u, p, e->stream);
+    return rc;
 }
 
 static int enqueue_frame(gs_engine *e, const gs_sort_params *s, const gs_uniforms *u, const gs_render_params *p, gs_sort_params &q, gs_render_params &rp) {
@@ -542,12 +577,50 @@ static int enqueue_frame(gs_engine *e, const gs_sort_params *s, const gs_uniform
     const uint32_t *d_idx = nullptr;
     int rc;
     if ((rc = stage_sort_inputs(e, &q, &d_idx))) return rc;
-    if ((rc = sort_on_device(e, d_idx, q.model_view_proj, q.sort_count, q.render_count, q.use_precomputed_distances != 0, false))) return rc;
-    const uint32_t sort_launches = e->tm.kernel_launches;
-    e->have_prof_begin = true;
     rp = *p;
     rp.sorted_indexes = nullptr; rp.sorted_indexes_dev = nullptr;
     rp.render_count = std::min(rp.render_count, q.render_count);
+    cudaStream_t st = e->stream;
+    e->last_frame_was_graph = false;
+    const bool use_graph = e->graph_enabled && !e->prof.on && q.sort_count <= q.render_count && q.render_count <= e->cfg.max_splat_count && e->rs.uploaded;
+    if (use_graph) {
+        const unsigned long long key[8] = {q.render_count, q.sort_count, ((unsigned long long)rp.width << 32) | rp.height,
+                                           ((unsigned long long)rp.frame_format << 8) | (unsigned long long)(rp.flip_y ? 1 : 0) | ((unsigned long long)q.use_precomputed_distances << 4),
+                                           (unsigned long long)(uintptr_t)d_idx, ((unsigned long long)e->rs.cov_format << 16) | ((unsigned long long)e->rs.sh_format << 8) | e->rs.sh_degree,
+                                           e->rs.uploaded, rp.render_count};
+        if ((rc = upload_frame_params(e, q.model_view_proj, *u, rp))) return rc;
+        if (!e->graph_exec || memcmp(key, e->graph_key, sizeof(key)) != 0) {
+            if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
+            // buffers that the enqueue path may grow must be sized BEFORE capture (no allocation inside a capture)
+            uint32_t stride = 0;
+            const PassPlan pl = make_plan_bits(e->key_bits);
+            if ((rc = e->lookback.ensure(radix_tile_hist_words(std::max(q.sort_count, 1u), pl.npasses, &stride)))) return rc;
+            CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            rc = sort_on_device(e, d_idx, q.model_view_proj, q.sort_count, q.render_count, q.use_precomputed_distances != 0, false, true);
+            const uint32_t sort_launches = e->tm.kernel_launches;
+            int rc2 = rc ? rc : render_on_device(e, u, &rp, e->sorted.p, true);
+            e->graph_launches = e->tm.kernel_launches + sort_launches;
+            cudaGraph_t g = nullptr;
+            cudaError_t ce = cudaStreamEndCapture(st, &g);
+            if (rc2) { if (g) cudaGraphDestroy(g); return rc2; }
+            if (ce != cudaSuccess) return fail(GS_ERR_CUDA, "cudaStreamEndCapture -> %s", cudaGetErrorString(ce));
+            ce = cudaGraphInstantiate(&e->graph_exec, g, 0);
+            cudaGraphDestroy(g);
+            if (ce != cudaSuccess) { e->graph_exec = nullptr; return fail(GS_ERR_CUDA, "cudaGraphInstantiate -> %s", cudaGetErrorString(ce)); }
+            memcpy(e->graph_key, key, sizeof(key));
+        }
+        CU(cudaEventRecord(e->ev[EV_SORT0], st));
+        CU(cudaGraphLaunch(e->graph_exec, st));
+        CU(cudaEventRecord(e->ev[EV_R1], st));
+        e->tm.kernel_launches = e->graph_launches;
+        e->last_render_count = q.render_count;
+        e->have_sorted = true;
+        e->last_frame_was_graph = true;
+        return GS_OK;
+    }
+    if ((rc = sort_on_device(e, d_idx, q.model_view_proj, q.sort_count, q.render_count, q.use_precomputed_distances != 0, false))) return rc;
+    const uint32_t sort_launches = e->tm.kernel_launches;
+    e->have_prof_begin = true;
     rc = render_on_device(e, u, &rp, e->sorted.p);
     e->have_prof_begin = false;
     if (rc) return rc;
@@ -636,6 +709,11 @@ extern "C" int gs_flush_l2(gs_engine *e) { // overwrite a buffer larger than L2 
     static uint32_t tick = 0;
     k_flush_l2<<<e->sm_count * 8, 512, 0, e->stream>>>(e->flush.p, words, ++tick);
     CU(cudaGetLastError());
+    return GS_OK;
+}
+extern "C" int gs_set_graph_enabled(gs_engine *e, int on) {
+    if (!e) return fail(GS_ERR_BAD_ARG, "gs_set_graph_enabled: null");
+    e->graph_enabled = on != 0;
     return GS_OK;
 }
 extern "C" int gs_set_profiling(gs_engine *e, int on) {

@@ -110,8 +110,17 @@ constexpr int kProjThreads = 128;
 template <bool COVF16, int SHFMT>
 __global__ void __launch_bounds__(kProjThreads)
 k_project(const uint4 *__restrict__ cc, const void *__restrict__ cov, const void *__restrict__ sh, int sh_data_degree,
-          const uint32_t *__restrict__ scene_idx, const DynamicUniforms *__restrict__ dyn, ProjParams P, uint32_t count,
+          const uint32_t *__restrict__ scene_idx, const DynamicUniforms *__restrict__ dyn, const ProjParams *__restrict__ Pp, uint32_t count,
           SplatRecord *__restrict__ rec, ushort4 *__restrict__ rects, RasterControl *rctl) {
+    // per-frame parameters: device memory -> shared memory once per CTA (graph-replayable, broadcast reads afterwards)
+    __shared__ ProjParams s_P;
+    {
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(Pp);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(&s_P);
+        for (int i = threadIdx.x; i < (int)(sizeof(ProjParams) / 4); i += kProjThreads) dst[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    const ProjParams &P = s_P;
     const uint32_t s = blockIdx.x * kProjThreads + threadIdx.x;
     uint32_t visible = 0;
     if (s < count) {
@@ -453,6 +462,8 @@ k_blend(const uint2 *__restrict__ ranges, const unsigned long long *__restrict__
     const int lx = lane & 15, ly0 = ((lane >> 4) + 2 * warp) * kBlendPix;     // column lx, rows ly0 .. ly0+3 of the tile
     const int x = tx * kTile + lx, y0 = ty * kTile + ly0;
     const float pxc = (float)x + 0.5f, pyc = (float)y0 + 0.5f;
+    const float tile_y0 = (float)(ty * kTile);
+    const uint32_t my_bit = 1u << warp;
     const uint2 rg = ranges[coarse];
     float T[kBlendPix], Cr[kBlendPix], Cg[kBlendPix], Cb[kBlendPix];
 #pragma unroll
@@ -492,35 +503,46 @@ k_blend(const uint2 *__restrict__ ranges, const unsigned long long *__restrict__
             const uint32_t j = c0 + threadIdx.x;
             if (j < nsurv) {
                 const float4 *src = reinterpret_cast<const float4 *>(rec + s_ids[j]);
-                s_rec[threadIdx.x][0] = __ldg(src);
-                s_rec[threadIdx.x][1] = __ldg(src + 1);
-                s_rec[threadIdx.x][2] = __ldg(src + 2);
+                const float4 a0 = __ldg(src);
+                float4 a1 = __ldg(src + 1), a2 = __ldg(src + 2);
+                // which warps (rows 0-7 / 8-15 of the tile) can the splat's AABB reach?  pixel-row index range of the AABB:
+                const uint32_t hb = __float_as_uint(a1.z);
+                const float hy = __high2float(*reinterpret_cast<const __half2 *>(&hb));
+                const float yl = a0.y - hy - tile_y0 - 0.5f, yh = a0.y + hy - tile_y0 - 0.5f;
+                const uint32_t wm = ((yl <= 7.0f && yh >= 0.0f) ? 1u : 0u) | ((yl <= 15.0f && yh >= 8.0f) ? 2u : 0u);
+                a1.z = a0.w * a0.w + a1.y * a1.y;     // h = |d(u,w)/dy|^2 : second difference of q down a pixel column is 2h
+                a2.w = __uint_as_float(wm);
+                s_rec[threadIdx.x][0] = a0;
+                s_rec[threadIdx.x][1] = a1;
+                s_rec[threadIdx.x][2] = a2;
             }
             __syncthreads();
             const int nb = (int)min((uint32_t)kBlendThreads, nsurv - c0);
             if (!done) {
 #pragma unroll 2
                 for (int jj = 0; jj < nb; ++jj) {
+                    const float4 r2 = s_rec[jj][2];
+                    if (!(__float_as_uint(r2.w) & my_bit)) continue;     // warp-uniform: my 8 rows are outside the splat's AABB
                     const float4 r0 = s_rec[jj][0], r1 = s_rec[jj][1];
                     const float dx = pxc - r0.x, dy = pyc - r0.y;
-                    float u = dx * r0.z + dy * r0.w;          // quad-local coordinates of the top pixel of my column
-                    float w = dx * r1.x + dy * r1.y;
+                    const float u = dx * r0.z + dy * r0.w;    // quad-local coordinates of the first pixel of my column
+                    const float w = dx * r1.x + dy * r1.y;
+                    // q = u^2 + w^2 (A = 8 q; the fragment shader discards A > 8), stepped up the column by forward differences:
+                    // q(y+1) - q(y) = 2 (u g1.y + w g2.y) + h,  second difference 2 h
                     float q[kBlendPix];
+                    q[0] = u * u + w * w;
+                    float dq = 2.0f * (u * r0.w + w * r1.y) + r1.z;
+                    const float ddq = r1.z + r1.z;
 #pragma unroll
-                    for (int k = 0; k < kBlendPix; ++k) {
-                        q[k] = u * u + w * w;                 // A = 8 q ; the fragment shader discards A > 8
-                        u += r0.w; w += r1.y;                 // one pixel up the column: d/dy of (u, w) = (g1.y, g2.y)
-                    }
+                    for (int k = 1; k < kBlendPix; ++k) { q[k] = q[k - 1] + dq; dq += ddq; }
                     if (fminf(fminf(q[0], q[1]), fminf(q[2], q[3])) > 1.0f) continue;
-                    const float4 r2 = s_rec[jj][2];
 #pragma unroll
                     for (int k = 0; k < kBlendPix; ++k) {
-                        if (q[k] <= 1.0f) {
-                            const float alpha = ex2_approx(q[k] * -5.770780163555854f) * r1.w;   // exp(-0.5 A) * vColor.a, A = 8 q
-                            const float wgt = T[k] * alpha;
-                            Cr[k] += wgt * r2.x; Cg[k] += wgt * r2.y; Cb[k] += wgt * r2.z;
-                            T[k] *= (1.0f - alpha);
-                        }
+                        // exp(-0.5 A) * vColor.a with A = 8 q; zero outside the quad's inscribed disc (branch-free)
+                        const float alpha = (q[k] <= 1.0f) ? ex2_approx(q[k] * -5.770780163555854f) * r1.w : 0.0f;
+                        const float wgt = T[k] * alpha;
+                        Cr[k] += wgt * r2.x; Cg[k] += wgt * r2.y; Cb[k] += wgt * r2.z;
+                        T[k] -= wgt;                           // T *= (1 - alpha)
                     }
                     if (fmaxf(fmaxf(T[0], T[1]), fmaxf(T[2], T[3])) < kTransmittanceCutoff) { done = true; break; }
                 }
@@ -600,6 +622,7 @@ struct RasterState {
     RBuf<SortControl> sctl;
     RBuf<uint32_t> lookback;   // radix tile histograms
     RBuf<DynamicUniforms> dyn;
+    RBuf<ProjParams> projp;     // per-frame projection parameters (device copy read by k_project)
     RBuf<unsigned char> frame;
     RBuf<gs_projected_splat> exported;
     unsigned long long instance_capacity = 0;
@@ -623,6 +646,7 @@ static int raster_init(RasterState &rs, const gs_config &c, int sm_count) {
     RCU(rs.rctl.ensure(1));
     RCU(rs.sctl.ensure(1));
     RCU(rs.dyn.ensure(1));
+    RCU(rs.projp.ensure(1));
     RCU(cudaMemset(rs.dyn.p, 0, sizeof(DynamicUniforms)));
     if (c.max_width && c.max_height) {
         RCU(rs.cc.ensure(n));
@@ -647,7 +671,7 @@ static void raster_release(RasterState &rs) {
     rs.cc.release(); rs.cov.release(); rs.sh.release(); rs.scene_idx.release(); rs.records.release(); rs.rects.release();
     rs.block_sums.release(); rs.ikeys[0].release(); rs.ikeys[1].release(); rs.ivals[0].release(); rs.ivals[1].release();
     rs.list.release(); rs.ranges.release(); rs.rctl.release(); rs.sctl.release(); rs.lookback.release();
-    rs.dyn.release(); rs.frame.release(); rs.exported.release();
+    rs.dyn.release(); rs.projp.release(); rs.frame.release(); rs.exported.release();
 }
 
 static int raster_upload(RasterState &rs, const gs_config &c, const gs_splat_data &d, cudaStream_t st) {
@@ -686,10 +710,10 @@ static int raster_upload(RasterState &rs, const gs_config &c, const gs_splat_dat
 static void *raster_frame_ptr(RasterState &rs, int) { return rs.frame.p; }
 
 template <bool COVF16>
-static void launch_project(RasterState &rs, const ProjParams &P, uint32_t count, cudaStream_t st) {
+static void launch_project(RasterState &rs, uint32_t count, cudaStream_t st) {
     const int blocks = (int)((count + kProjThreads - 1) / kProjThreads);
     const uint32_t *sc = rs.have_scene_idx ? rs.scene_idx.p : nullptr;
-#define GS_PROJ(FMT) k_project<COVF16, FMT><<<blocks, kProjThreads, 0, st>>>(rs.cc.p, rs.cov.p, rs.sh.p, (int)rs.sh_degree, sc, rs.dyn.p, P, count, rs.records.p, rs.rects.p, rs.rctl.p)
+#define GS_PROJ(FMT) k_project<COVF16, FMT><<<blocks, kProjThreads, 0, st>>>(rs.cc.p, rs.cov.p, rs.sh.p, (int)rs.sh_degree, sc, rs.dyn.p, rs.projp.p, count, rs.records.p, rs.rects.p, rs.rctl.p)
     switch (rs.sh_format) {
         case GS_SH_F16: GS_PROJ(GS_SH_F16); break;
         case GS_SH_U8: GS_PROJ(GS_SH_U8); break;
@@ -699,8 +723,35 @@ static void launch_project(RasterState &rs, const ProjParams &P, uint32_t count,
 #undef GS_PROJ
 }
 
+static int raster_upload_params(RasterState &rs, const gs_config &c, const gs_uniforms &u, const gs_render_params &p, cudaStream_t st) {
+    const int tiles_x = (p.width + kTile - 1) / kTile, tiles_y = (p.height + kTile - 1) / kTile;
+    const uint32_t world = c.world_size, rank = c.rank;
+    const bool upload_params = true;
+    ProjParams P{};
+    memcpy(P.mv, u.model_view, 64); memcpy(P.proj, u.projection, 64);
+    memcpy(P.cam, u.camera_position, 12);
+    P.focal[0] = u.focal[0]; P.focal[1] = u.focal[1]; P.viewport[0] = u.viewport[0]; P.viewport[1] = u.viewport[1];
+    P.inv_focal_adj = u.inverse_focal_adjustment; P.ortho_zoom = u.ortho_zoom; P.orthographic = u.orthographic_mode;
+    P.splat_scale = u.splat_scale; P.point_cloud = u.point_cloud_mode; P.sh_degree = u.sh_degree; P.antialiased = u.antialiased;
+    P.kernel2d = u.kernel_2d_size; P.max_size = u.max_screen_space_splat_size; P.fade_in_complete = u.fade_in_complete;
+    memcpy(P.scene_center, u.scene_center, 12); P.fade_start = u.visible_region_fade_start_radius;
+    P.dynamic = u.dynamic_mode; P.optional_effects = u.enable_optional_effects; P.scene_count = (int)u.scene_count;
+    P.tiles_x = tiles_x; P.tiles_y = tiles_y; P.rank = rank; P.world = world; P.width = (int)p.width; P.height = (int)p.height;
+    if (upload_params) RCU(cudaMemcpyAsync(rs.projp.p, &P, sizeof(P), cudaMemcpyHostToDevice, st)); // pageable source: staged before return
+    if (upload_params && (u.dynamic_mode || u.enable_optional_effects || rs.sh_format == GS_SH_U8)) {
+        DynamicUniforms du;
+        memcpy(du.view, u.view_matrix, 64);
+        memcpy(du.transforms, u.scene_transforms, sizeof(du.transforms));
+        memcpy(du.sh8_min, u.sh8_min, sizeof(du.sh8_min)); memcpy(du.sh8_max, u.sh8_max, sizeof(du.sh8_max));
+        memcpy(du.opacity, u.scene_opacity, sizeof(du.opacity)); memcpy(du.visibility, u.scene_visibility, sizeof(du.visibility));
+        RCU(cudaMemcpyAsync(rs.dyn.p, &du, sizeof(du), cudaMemcpyHostToDevice, st)); // pageable source: staged before return
+    }
+
+    return GS_OK;
+}
+
 static int raster_render(RasterState &rs, const gs_config &c, const gs_uniforms &u, const gs_render_params &p, const uint32_t *d_order,
-                         cudaStream_t st, cudaEvent_t ev_project, cudaEvent_t ev_bin, gs_timings &tm, Profiler &prof) {
+                         cudaStream_t st, cudaEvent_t ev_project, cudaEvent_t ev_bin, gs_timings &tm, Profiler &prof, bool upload_params, bool record_events) {
     if (!rs.uploaded) { snprintf(raster_err(), 512, "gs_render before gs_upload_splat_data"); return GS_ERR_NOT_READY; }
     if (p.width == 0 || p.height == 0 || p.width > c.max_width || p.height > c.max_height) {
         snprintf(raster_err(), 512, "frame %ux%u outside the engine's %ux%u", p.width, p.height, c.max_width, c.max_height); return GS_ERR_BAD_ARG;
@@ -712,25 +763,7 @@ static int raster_render(RasterState &rs, const gs_config &c, const gs_uniforms 
     const uint32_t local_tiles = (uint32_t)local_rows * (uint32_t)tiles_x;
     uint32_t launches = 0;
 
-    ProjParams P{};
-    memcpy(P.mv, u.model_view, 64); memcpy(P.proj, u.projection, 64);
-    memcpy(P.cam, u.camera_position, 12);
-    P.focal[0] = u.focal[0]; P.focal[1] = u.focal[1]; P.viewport[0] = u.viewport[0]; P.viewport[1] = u.viewport[1];
-    P.inv_focal_adj = u.inverse_focal_adjustment; P.ortho_zoom = u.ortho_zoom; P.orthographic = u.orthographic_mode;
-    P.splat_scale = u.splat_scale; P.point_cloud = u.point_cloud_mode; P.sh_degree = u.sh_degree; P.antialiased = u.antialiased;
-    P.kernel2d = u.kernel_2d_size; P.max_size = u.max_screen_space_splat_size; P.fade_in_complete = u.fade_in_complete;
-    memcpy(P.scene_center, u.scene_center, 12); P.fade_start = u.visible_region_fade_start_radius;
-    P.dynamic = u.dynamic_mode; P.optional_effects = u.enable_optional_effects; P.scene_count = (int)u.scene_count;
-    P.tiles_x = tiles_x; P.tiles_y = tiles_y; P.rank = rank; P.world = world; P.width = (int)p.width; P.height = (int)p.height;
-    if (u.dynamic_mode || u.enable_optional_effects || rs.sh_format == GS_SH_U8) {
-        DynamicUniforms du;
-        memcpy(du.view, u.view_matrix, 64);
-        memcpy(du.transforms, u.scene_transforms, sizeof(du.transforms));
-        memcpy(du.sh8_min, u.sh8_min, sizeof(du.sh8_min)); memcpy(du.sh8_max, u.sh8_max, sizeof(du.sh8_max));
-        memcpy(du.opacity, u.scene_opacity, sizeof(du.opacity)); memcpy(du.visibility, u.scene_visibility, sizeof(du.visibility));
-        RCU(cudaMemcpyAsync(rs.dyn.p, &du, sizeof(du), cudaMemcpyHostToDevice, st)); // pageable source: staged before return
-    }
-
+    if (upload_params) { int prc = raster_upload_params(rs, c, u, p, st); if (prc) return prc; }
     const int coarse_x = (tiles_x + kCoarseW - 1) / kCoarseW, coarse_y = (tiles_y + kCoarseH - 1) / kCoarseH;
     const uint32_t ncoarse = (uint32_t)coarse_x * (uint32_t)coarse_y;
     if (ncoarse > 65536u) { snprintf(raster_err(), 512, "frame %ux%u needs %u coarse tiles (> 65536)", p.width, p.height, ncoarse); return GS_ERR_BAD_ARG; }
@@ -741,10 +774,10 @@ static int raster_render(RasterState &rs, const gs_config &c, const gs_uniforms 
     ++launches;
     prof.mark("k_raster_init", st);
     const uint32_t count = rs.uploaded;
-    if (rs.cov_format == GS_COV_F16) launch_project<true>(rs, P, count, st); else launch_project<false>(rs, P, count, st);
+    if (rs.cov_format == GS_COV_F16) launch_project<true>(rs, count, st); else launch_project<false>(rs, count, st);
     ++launches;
     prof.mark("k_project", st);
-    RCU(cudaEventRecord(ev_project, st));
+    if (record_events) RCU(cudaEventRecord(ev_project, st));
     if (p.render_count && local_tiles) {
         const uint32_t chunks = (p.render_count + kBinTile - 1) / kBinTile;
         k_tile_count<<<chunks, kBinThreads, 0, st>>>(d_order, p.render_count, rs.rects.p, rs.block_sums.p, rs.rctl.p);
@@ -763,7 +796,7 @@ static int raster_render(RasterState &rs, const gs_config &c, const gs_uniforms 
                                                        n_dev, rs.instance_capacity, pl, rs.sctl.p, rs.lookback.p, rs.hist_stride, false, rs.ranges.p, st, launches,
                                                        &prof, names);
     }
-    RCU(cudaEventRecord(ev_bin, st));
+    if (record_events) RCU(cudaEventRecord(ev_bin, st));
     if (local_tiles) {
         const uint32_t grid = ncoarse * kFinePerCoarse;
         if (p.frame_format == GS_FRAME_RGBA8)

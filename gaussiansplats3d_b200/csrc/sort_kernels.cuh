@@ -85,8 +85,16 @@ constexpr int kDepthItems = 4;
 template <int MODE, bool IDENTITY>
 __global__ void __launch_bounds__(kDepthThreads)
 k_depth(const uint32_t *__restrict__ indexes, const void *__restrict__ centers, const void *__restrict__ pre,
-        const uint32_t *__restrict__ scene_idx, const float *__restrict__ transforms, DepthParams P, uint32_t s0,
+        const uint32_t *__restrict__ scene_idx, const float *__restrict__ transforms, const DepthParams *__restrict__ Pp, uint32_t s0,
         uint32_t rc, int32_t *__restrict__ dist, SortControl *ctl) {
+    // per-frame parameters live in device memory so that a captured CUDA graph of the frame can be replayed unchanged
+    DepthParams P;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { P.irow[i] = __ldg(&Pp->irow[i]); P.frow[i] = __ldg(&Pp->frow[i]); }
+    if (MODE == kIntDynamic || MODE == kFloatDynamic) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) P.mvp[i] = __ldg(&Pp->mvp[i]);
+    }
     __shared__ int32_t s_irow[GS_MAX_SCENES_DEV][4];
     __shared__ float s_frow[GS_MAX_SCENES_DEV][4];
     __shared__ int s_min[kDepthThreads / 32], s_max[kDepthThreads / 32];

@@ -273,6 +273,9 @@ class Engine:
         sp, u, rp = prepared
         N.check(self._lib.gs_frame(self._h, C.byref(sp), C.byref(u), C.byref(rp), N.ptr(sorted_out), N.ptr(frame_out)), "gs_frame")
 
+    def set_graph_enabled(self, on: bool) -> None:
+        N.check(self._lib.gs_set_graph_enabled(self._h, 1 if on else 0), "gs_set_graph_enabled")
+
     def set_profiling(self, on: bool) -> None:
         N.check(self._lib.gs_set_profiling(self._h, 1 if on else 0), "gs_set_profiling")
 

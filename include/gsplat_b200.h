@@ -250,6 +250,8 @@ GS_API int gs_flush_l2(gs_engine *e);
  * returns {kernel name, device ms} for the last gs_sort / gs_render / gs_frame in launch order.                      */
 typedef struct gs_kernel_time { char name[40]; float ms; } gs_kernel_time;
 GS_API int gs_set_profiling(gs_engine *e, int on);
+/* gs_frame / gs_frame_async replay a captured CUDA graph of the frame while its shape is unchanged (default on).      */
+GS_API int gs_set_graph_enabled(gs_engine *e, int on);
 GS_API int gs_kernel_timings(gs_engine *e, gs_kernel_time *out, uint32_t capacity, uint32_t *count);
 GS_API int gs_event_create(void **event);
 GS_API int gs_event_record(gs_engine *e, void *event);

@@ -31,8 +31,8 @@ def assemble_frame(strips: list, width: int, height: int, flip_y: bool = True):
     v = out.reshape(tiles_y, TILE, width, 4) if not hasattr(out, "view") or isinstance(out, np.ndarray) else out.view(tiles_y, TILE, width, 4)
     for r, s in enumerate(strips):
         rows = len(owned_tile_rows(tiles_y, r, world))
-        sv = s.reshape(rows, TILE, width, 4)
-        v[r::world] = sv[:rows]
+        sv = s[: rows * TILE].reshape(rows, TILE, width, 4)   # strips may be padded to the longest rank's length
+        v[r::world] = sv
     out = out[:height]
     if flip_y:
         out = out.flip(0) if hasattr(out, "flip") and not isinstance(out, np.ndarray) else out[::-1]

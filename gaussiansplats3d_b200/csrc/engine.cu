@@ -506,7 +506,8 @@ static size_t frame_bytes(const gs_render_params *p) { return (size_t)p->width *
 static int finish_render(gs_engine *e, const gs_render_params *p, void *frame_out) {
     cudaStream_t st = e->stream;
     CU(cudaEventRecord(e->ev[EV_D2H0], st));
-    if (frame_out) CU(cudaMemcpyAsync(frame_out, raster_frame_ptr(e->rs, p->frame_format), frame_bytes(p), cudaMemcpyDeviceToHost, st));
+    // world_size > 1: the engine holds (and returns) only its own compact strip of tile rows
+    if (frame_out) CU(cudaMemcpyAsync(frame_out, raster_frame_ptr(e->rs, p->frame_format), e->cfg.world_size > 1 ? e->rs.last_frame_bytes : frame_bytes(p), cudaMemcpyDeviceToHost, st));
     CU(cudaEventRecord(e->ev[EV_D2H1], st));
     CU(cudaMemcpyAsync(e->h_ctl.p + 16, e->rs.rctl.p, sizeof(RasterControl), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));

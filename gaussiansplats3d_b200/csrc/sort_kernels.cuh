@@ -201,7 +201,10 @@ k_bucket(int32_t *__restrict__ dist, KeyT *__restrict__ keys, uint32_t s0, uint3
             const int32_t rel = (int32_t)((uint32_t)d[k] - (uint32_t)dmin);
             int32_t b = __float2int_rz(__fmul_rn(__int2float_rn(rel), range_map)); // sorter.cpp:146
             if (degenerate) b = 0;               // defined deviation: the reference traps / writes out of bounds
-            if (b < 0 || (uint32_t)b >= R) { err |= kErrBucketRange; b = b < 0 ? 0 : (int32_t)(R - 1u); }
+            // f32 rounding can push the farthest splat's bucket to exactly R at 2^22..2^24 ranges (the reference then writes
+            // frequencies[R], outside its prefix sum): clamp.  A negative (d - min) means int32 wrap-around: report.
+            if (rel < 0 || b < 0) { err |= kErrBucketRange; b = 0; }
+            else if ((uint32_t)b >= R) b = (int32_t)(R - 1u);
             if (write_buckets) dist[(uint64_t)rc - 1u - j] = b;
             const uint32_t key = (R - 1u) - (uint32_t)b;
             keys[j] = (KeyT)key;

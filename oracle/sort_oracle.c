@@ -144,8 +144,13 @@ GS_ORACLE_API int gso_sort_indexes(const uint32_t *indexes, const void *centers,
     if (rc != GSO_OK) { free(dist); free(start); return rc; }
     const float rm = gso_range_map(dmin, dmax, range);
     for (uint32_t i = s0; i < render_count; ++i) {
-        const int32_t b = gso_bucket(dist[i], dmin, rm);
-        if (b < 0 || (uint32_t)b >= range) { free(dist); free(start); return GSO_BUCKET_RANGE; }
+        int32_t b = gso_bucket(dist[i], dmin, rm);
+        const int32_t rel = (int32_t)((uint32_t)dist[i] - (uint32_t)dmin);
+        /* the reference has no defined behaviour here (it writes frequencies[>= R]); the engine's documented choice:
+           int32 wrap-around of (d - min) is an error, an f32-rounding overshoot to exactly R clamps to R-1 */
+        if (dmax == dmin) b = 0;
+        if (rel < 0 || b < 0) { free(dist); free(start); return GSO_BUCKET_RANGE; }
+        if ((uint32_t)b >= range) b = (int32_t)range - 1;
         dist[i] = b;
         start[b]++;
     }

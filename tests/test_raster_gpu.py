@@ -145,3 +145,60 @@ def test_render_options(gs, oracle_mod):
         want, _ = _oracle_frame(oracle_mod, v, order)
         _check_frame(got, want)
         v.dispose()
+
+
+def test_dynamic_scenes_and_optional_effects(gs, oracle_mod):
+    """per-scene transforms in the vertex stage (SplatMaterial.js:136-146, :181-183), scene opacity / visibility
+    (SplatMaterial.js:124-133, SplatMaterial3D.js:198-202), 3 scenes, SH1 so the per-scene camera transform matters."""
+    from gaussiansplats3d_b200 import three_math as TM
+    from gaussiansplats3d_b200.engine import Engine, Uniforms
+    from gaussiansplats3d_b200.scenes import pack_scene, synthetic_scene
+    n, w, h = 60_000, 512, 300
+    raw = synthetic_scene(n, seed=6, kind="uniform", sh_degree=1)
+    p = pack_scene(raw)
+    rng = np.random.default_rng(3)
+    scene_idx = rng.integers(0, 3, n, dtype=np.uint32)
+    transforms = np.tile(np.eye(4, dtype=np.float64).T.reshape(16), (32, 1))
+    transforms[1] = TM.compose((1.5, 0.0, -1.0), (0.0, np.sin(0.3), 0.0, np.cos(0.3)), (1.2, 1.2, 1.2))
+    transforms[2] = TM.compose((-2.0, 0.5, 0.5), (np.sin(0.2), 0.0, 0.0, np.cos(0.2)), (0.7, 0.7, 0.7))
+    cam = TM.PerspectiveCamera(50, w / h, 0.1, 1000)
+    cam.position = np.array([0.0, 4.0, 12.0]); cam.look_at((0, 0, 0))
+    opacity = np.ones(32, np.float32); opacity[1] = 0.6
+    vis = np.ones(32, np.int32)
+    for effects, hide in ((0, False), (1, False), (1, True)):
+        v = vis.copy()
+        if hide:
+            v[2] = 0
+        u = Uniforms(model_view=cam.matrixWorldInverse.astype(np.float32), projection=cam.projectionMatrix.astype(np.float32),
+                     camera_position=cam.position.astype(np.float32), focal=(cam.projectionMatrix[0] * 0.5 * w, cam.projectionMatrix[5] * 0.5 * h),
+                     viewport=(w, h), sh_degree=1, scene_count=3, scene_transforms=transforms.astype(np.float32), view_matrix=cam.matrixWorldInverse.astype(np.float32),
+                     scene_opacity=opacity, scene_visibility=v, enable_optional_effects=effects, dynamic_mode=1)
+        order = rng.permutation(n).astype(np.uint32)     # any order: the blend must honour it
+        with Engine(n, max_width=w, max_height=h, dynamic_mode=True) as e:
+            e.upload_splat_data(p.centers_colors, p.covariances, p.sh, p.sh_degree, scene_indexes=scene_idx)
+            got = e.render(u, w, h, n, order, flip_y=False)
+            proj = e.read_projected(n)
+        want, wproj = oracle_mod.render(u, p.centers_colors, p.covariances, order, w, h, sh=p.sh, sh_degree=p.sh_degree, scene_indexes=scene_idx)
+        assert (proj["valid"] != wproj["valid"]).mean() < 1e-4
+        m = (proj["valid"] == 1) & (wproj["valid"] == 1)
+        assert np.abs(proj["cx"][m] - wproj["cx"][m]).max() < 5e-3 and np.abs(proj["a"][m] - wproj["a"][m]).max() < 5e-4
+        _check_frame(got, want)
+        if hide:
+            assert (wproj["valid"][scene_idx == 2] == 0).all()
+
+
+def test_precision_20bit_and_float_sort_feed_the_same_frame(gs, oracle_mod):
+    """splatSortDistanceMapPrecision 20 (3 radix passes) and the float sort mode drive the renderer like the default."""
+    from gaussiansplats3d_b200.scenes import synthetic_scene
+    raw = synthetic_scene(80_000, seed=13, kind="bonsai")
+    for opts in (dict(splatSortDistanceMapPrecision=20), dict(integerBasedSort=False, splatSortDistanceMapPrecision=22)):
+        v = _viewer(gs, raw, 480, 270, **opts)
+        got = v.frame(frame_format=gs._native.GS_FRAME_RGBA32F, flip_y=False)
+        order, _ = v.engine.sort(v.mvp_matrix().astype(np.float32), raw.count, raw.count, None)
+        centers = v.splatMesh.getIntegerCenters(0, raw.count - 1, True) if v.integerBasedSort else v.splatMesh.getFloatCenters(0, raw.count - 1, True)
+        want_order = oracle_mod.port_sort_indexes(np.arange(raw.count, dtype=np.uint32), centers, None, v.mvp_matrix().astype(np.float32), None, None,
+                                                  1 << v.splatSortDistanceMapPrecision, raw.count, raw.count, raw.count, False, v.integerBasedSort, False)
+        assert np.array_equal(order, want_order)
+        want, _ = _oracle_frame(oracle_mod, v, order)
+        _check_frame(got, want)
+        v.dispose()

@@ -130,3 +130,18 @@ def test_edge_cases(gs, oracle_mod):
     # bad arguments are reported, not executed
     with pytest.raises(gs.GsError):
         gs.sort_indexes(c["indexes"], c["centers"], None, c["mvp"], None, None, 1 << 16, 2000, 1000, 1000, False, True, False)
+
+
+def test_float_24bit_precision_overshoot_is_clamped(gs, oracle_mod):
+    """Float mode allows 24-bit precision (Viewer.js:208-210); there (R-1)/range * (max-min) can round to exactly R for the
+    farthest splat.  The reference then increments frequencies[R] (outside its prefix sum); we clamp to R-1."""
+    R = 1 << 24
+    hit = 0
+    for seed in range(6):
+        c = cases.sort_case(seed=seed, n=20000, integer=False)
+        got = gs.sort_indexes(*cases.call_args(c, R))
+        want, buckets = oracle_mod.port_sort_indexes(*cases.call_args(c, R), want_buckets=True)
+        assert np.array_equal(got, want)
+        assert np.array_equal(np.sort(got), np.sort(c["indexes"]))
+        hit += int(buckets.max() == R - 1)
+    assert hit > 0

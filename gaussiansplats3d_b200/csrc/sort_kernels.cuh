@@ -171,15 +171,28 @@ constexpr int kRadixWarps = kRadixThreads / 32;
 
 enum ValMode : int { kValArray = 0, kValArrayReversed = 1, kValIotaReversed = 2 };
 
+// Lanes of the warp holding the same (<= 9-bit) value, from 9 warp votes.  MATCH.ANY does this in one instruction but retires only
+// about one per ~50 cycles per SM on sm_100 (measured: it was the limiter of the scatter kernel); VOTE is full rate.
+__device__ __forceinline__ uint32_t warp_peers9(uint32_t d) {
+    uint32_t peers = 0xffffffffu;
+#pragma unroll
+    for (int b = 0; b < 9; ++b) {
+        const bool bit = (d >> b) & 1u;
+        const uint32_t vote = __ballot_sync(0xffffffffu, bit);
+        peers &= bit ? vote : ~vote;
+    }
+    return peers;
+}
+
 // Bucket + key (sorter.cpp:142-149), one CTA per radix tile of the REVERSED sequence: key[j] = (R-1) - bucket(dist[i]) with
-// j = rc-1-i.  Also the pass-0 tile histogram (H of pass 0 fused here) and the global digit totals of EVERY pass.
+// j = rc-1-i.  Also the pass-0 tile histogram and pass-0 global digit totals (H of pass 0 fused here).
 // Optionally leaves the bucket in dist[i] (the reference's mappedDistances).
 template <typename KeyT>
 __global__ void __launch_bounds__(kRadixThreads)
 k_bucket(int32_t *__restrict__ dist, KeyT *__restrict__ keys, uint32_t s0, uint32_t rc, uint32_t R, PassPlan plan,
          int write_buckets, SortControl *ctl, uint32_t *__restrict__ tile_hist, uint32_t stride) {
-    __shared__ uint32_t s_hist[4][kRadix];
-    for (int i = threadIdx.x; i < 4 * kRadix; i += kRadixThreads) (&s_hist[0][0])[i] = 0;
+    __shared__ uint32_t s_hist[kRadix];
+    if (threadIdx.x < kRadix) s_hist[threadIdx.x] = 0;
     __syncthreads();
     const int32_t dmin = ctl->dmin, dmax = ctl->dmax;
     const float span = __fsub_rn(__int2float_rn(dmax), __int2float_rn(dmin)); // sorter.cpp:142
@@ -208,16 +221,15 @@ k_bucket(int32_t *__restrict__ dist, KeyT *__restrict__ keys, uint32_t s0, uint3
             if (write_buckets) dist[(uint64_t)rc - 1u - j] = b;
             const uint32_t key = (R - 1u) - (uint32_t)b;
             keys[j] = (KeyT)key;
-#pragma unroll
-            for (int p = 0; p < 4; ++p)
-                if (p < plan.npasses) atomicAdd(&s_hist[p][(key >> plan.shift[p]) & ((1u << plan.bits[p]) - 1u)], 1u);
+            // shared-memory atomics: measured faster here than grouping equal digits with MATCH.ANY (2x slower) or ballots (1.4x)
+            atomicAdd(&s_hist[(key >> plan.shift[0]) & ((1u << plan.bits[0]) - 1u)], 1u);
         }
     }
     __syncthreads();
-    if (threadIdx.x < kRadix) tile_hist[(size_t)threadIdx.x * stride + blockIdx.x] = s_hist[0][threadIdx.x];
-    for (int i = threadIdx.x; i < plan.npasses * kRadix; i += kRadixThreads) {
-        const uint32_t v = (&s_hist[0][0])[i];
-        if (v) atomicAdd(&ctl->hist[0][0] + i, v);
+    if (threadIdx.x < kRadix) {
+        const uint32_t v = s_hist[threadIdx.x];
+        tile_hist[(size_t)threadIdx.x * stride + blockIdx.x] = v;
+        if (v) atomicAdd(&ctl->hist[0][threadIdx.x], v);
     }
     if (err) atomicOr(&ctl->error, err);
     if (degenerate && blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&ctl->error, kErrDegenerate);
@@ -235,11 +247,15 @@ k_radix_hist(const KeyT *__restrict__ keys, uint32_t n_host, const unsigned long
     if (threadIdx.x < kRadix) s_hist[threadIdx.x] = 0;
     __syncthreads();
     const uint32_t dmask = (1u << bits) - 1u;
+    uint32_t kk[kRadixItems];
 #pragma unroll
     for (int k = 0; k < kRadixItems; ++k) {
         const uint64_t e = base + (uint64_t)k * kRadixThreads + threadIdx.x;
-        if (e < n) atomicAdd(&s_hist[((uint32_t)keys[e] >> shift) & dmask], 1u);
+        kk[k] = (e < n) ? (((uint32_t)keys[e] >> shift) & dmask) : 0xffffffffu;
     }
+#pragma unroll
+    for (int k = 0; k < kRadixItems; ++k)
+        if (kk[k] != 0xffffffffu) atomicAdd(&s_hist[kk[k]], 1u);
     __syncthreads();
     if (threadIdx.x < kRadix) {
         const uint32_t v = s_hist[threadIdx.x];
@@ -281,66 +297,48 @@ k_radix_scan(uint32_t *__restrict__ tile_hist, uint32_t stride, uint32_t n_host,
 
 // P: stable scatter of one tile.  RANGES (final pass of the tile-instance sort): the tile's reorder buffer is fully sorted by
 // key, so [first, last+1) of every key's run is found from neighbours; runs may continue in other tiles -> atomicMin/Max.
-template <typename KeyT, typename ValT, int VALMODE, bool WRITE_KEYS, bool RANGES>
-__global__ void __launch_bounds__(kRadixThreads)
-k_radix_scatter(const KeyT *__restrict__ keys_in, const ValT *__restrict__ vals_in, uint32_t iota_top,
-                KeyT *__restrict__ keys_out, ValT *__restrict__ vals_out, uint32_t n_host,
-                const unsigned long long *__restrict__ n_dev, unsigned long long n_cap, int shift, int bits,
-                const uint32_t *__restrict__ tile_offsets, uint32_t stride, uint2 *ranges) {
-    const uint32_t n = n_dev ? (uint32_t)min(*n_dev, n_cap) : n_host;
-    const uint32_t tile = blockIdx.x;
-    const uint64_t tile_base = (uint64_t)tile * kRadixTile;
-    if (tile_base >= n) return; // surplus CTA of a capacity-sized grid (uniform exit)
-    // phase A: per-warp digit counters; phase B: reorder buffers (aliased)
-    __shared__ __align__(16) unsigned char s_raw[kRadixTile * (sizeof(KeyT) + sizeof(ValT)) > kRadixWarps * (kRadix + 1) * 4
-                                                     ? kRadixTile * (sizeof(KeyT) + sizeof(ValT))
-                                                     : kRadixWarps * (kRadix + 1) * 4];
-    __shared__ uint32_t s_tile_count[kRadix];  // digit totals of this tile
-    __shared__ uint32_t s_tile_start[kRadix];  // exclusive scan of the above (slot in the reorder buffer)
-    __shared__ uint32_t s_gbase[kRadix];       // global slot of reorder-slot 0 for each digit (wrapping arithmetic)
-    __shared__ uint32_t s_scan[40];
-
+// Register diet (3 CTAs/SM): values are loaded only after ranking, element indices are 32-bit, full tiles skip bounds checks,
+// and the 8 MATCH.ANY of a thread are issued back to back before the serial counter updates that consume them.
+template <typename KeyT, typename ValT, int VALMODE, bool WRITE_KEYS, bool RANGES, bool FULL>
+__device__ __forceinline__ void radix_scatter_tile(const KeyT *__restrict__ keys_in, const ValT *__restrict__ vals_in, uint32_t iota_top,
+                                                   KeyT *__restrict__ keys_out, ValT *__restrict__ vals_out, uint32_t n, uint32_t tile,
+                                                   int shift, uint32_t dmask, const uint32_t *__restrict__ tile_offsets, uint32_t stride,
+                                                   uint2 *ranges, unsigned char *s_raw, uint32_t *s_tile_count, uint32_t *s_tile_start,
+                                                   uint32_t *s_gbase, uint32_t *s_scan) {
     uint32_t(*s_whist)[kRadix + 1] = reinterpret_cast<uint32_t(*)[kRadix + 1]>(s_raw);
     ValT *s_vals = reinterpret_cast<ValT *>(s_raw);
     KeyT *s_keys = reinterpret_cast<KeyT *>(s_raw + (size_t)kRadixTile * sizeof(ValT));
-
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t tile_base = tile * (uint32_t)kRadixTile;
+    const uint32_t run_base = tile_base + (uint32_t)warp * (32 * kRadixItems) + lane;
     for (int i = tid; i < kRadixWarps * (kRadix + 1); i += kRadixThreads) (&s_whist[0][0])[i] = 0;
-    const uint32_t dmask = (1u << bits) - 1u;
 
-    // ---- load keys (+ values), rank within the warp ----------------------------------------------------------
-    uint32_t key[kRadixItems], rank[kRadixItems];
-    ValT val[kRadixItems];
-    const uint64_t run_base = tile_base + (uint64_t)warp * (32 * kRadixItems);
+    uint32_t key[kRadixItems];
 #pragma unroll
     for (int k = 0; k < kRadixItems; ++k) {
-        const uint64_t e = run_base + (uint64_t)k * 32 + lane;
-        key[k] = (e < n) ? (uint32_t)keys_in[e] : 0u;
-    }
-#pragma unroll
-    for (int k = 0; k < kRadixItems; ++k) {
-        const uint64_t e = run_base + (uint64_t)k * 32 + lane;
-        if (e < n) {
-            if (VALMODE == kValArray) val[k] = __ldg(vals_in + e);
-            else if (VALMODE == kValArrayReversed) val[k] = __ldg(vals_in + ((uint64_t)n - 1u - e));
-            else val[k] = (ValT)(iota_top - (uint32_t)e);
-        } else val[k] = 0;
+        const uint32_t e = run_base + (uint32_t)k * 32;
+        key[k] = (FULL || e < n) ? (uint32_t)keys_in[e] : 0xffffffffu;
     }
     const uint32_t my_offset = tid < kRadix ? tile_offsets[(size_t)tid * stride + tile] : 0u;
-    __syncthreads();
+    uint32_t peers[kRadixItems];
 #pragma unroll
     for (int k = 0; k < kRadixItems; ++k) {
-        const uint64_t e = run_base + (uint64_t)k * 32 + lane;
-        const uint32_t d = (e < n) ? ((key[k] >> shift) & dmask) : (uint32_t)kRadix; // tail items: private bin
-        const uint32_t peers = __match_any_sync(0xffffffffu, d);
+        const uint32_t d = (FULL || key[k] != 0xffffffffu) ? ((key[k] >> shift) & dmask) : (uint32_t)kRadix; // tail items: private bin
+        peers[k] = warp_peers9(d);
+    }
+    __syncthreads();
+    uint32_t rank[kRadixItems];
+    const uint32_t lt = lanemask_lt();
+#pragma unroll
+    for (int k = 0; k < kRadixItems; ++k) {
+        const uint32_t d = (FULL || key[k] != 0xffffffffu) ? ((key[k] >> shift) & dmask) : (uint32_t)kRadix;
         const uint32_t before = s_whist[warp][d];
-        rank[k] = before + __popc(peers & lanemask_lt());
+        rank[k] = before + __popc(peers[k] & lt);
         __syncwarp();
-        if ((peers & lanemask_lt()) == 0) s_whist[warp][d] = before + __popc(peers);
+        if ((peers[k] & lt) == 0) s_whist[warp][d] = before + __popc(peers[k]);
         __syncwarp();
     }
     __syncthreads();
-
     // ---- per digit: exclusive scan over warps, tile totals -------------------------------------------------------
     if (tid < kRadix) {
         uint32_t run = 0;
@@ -360,28 +358,32 @@ k_radix_scatter(const KeyT *__restrict__ keys_in, const ValT *__restrict__ vals_
         if (tid < kRadix) { s_tile_start[tid] = ex; s_gbase[tid] = my_offset - ex; }
     }
     __syncthreads();
-    // reorder slots for my items (must be read before the counters are overwritten by the reorder buffers)
-    uint32_t slot[kRadixItems];
+    // reorder slots for my items (read the counters before the reorder buffers overwrite them)
 #pragma unroll
     for (int k = 0; k < kRadixItems; ++k) {
-        const uint64_t e = run_base + (uint64_t)k * 32 + lane;
         const uint32_t d = (key[k] >> shift) & dmask;
-        slot[k] = (e < n) ? (s_tile_start[d] + s_whist[warp][d] + rank[k]) : 0xffffffffu;
+        rank[k] = (FULL || key[k] != 0xffffffffu) ? (s_tile_start[d] + s_whist[warp][d] + rank[k]) : 0xffffffffu;
     }
     __syncthreads();
-    // ---- reorder through shared memory so each digit run is written contiguously --------------------------------------
+    // ---- values are fetched only now (keeps 8 registers free during ranking), then reordered through shared memory -------------
 #pragma unroll
-    for (int k = 0; k < kRadixItems; ++k)
-        if (slot[k] != 0xffffffffu) {
-            s_vals[slot[k]] = val[k];
-            s_keys[slot[k]] = (KeyT)key[k];
+    for (int k = 0; k < kRadixItems; ++k) {
+        const uint32_t e = run_base + (uint32_t)k * 32;
+        if (FULL || rank[k] != 0xffffffffu) {
+            ValT v;
+            if (VALMODE == kValArray) v = __ldg(vals_in + e);
+            else if (VALMODE == kValArrayReversed) v = __ldg(vals_in + (n - 1u - e));
+            else v = (ValT)(iota_top - e);
+            s_vals[rank[k]] = v;
+            s_keys[rank[k]] = (KeyT)key[k];
         }
+    }
     __syncthreads();
-    const uint32_t valid = (uint32_t)min((uint64_t)kRadixTile, (uint64_t)n - tile_base);
+    const uint32_t valid = FULL ? (uint32_t)kRadixTile : (n - tile_base);
 #pragma unroll
     for (int k = 0; k < kRadixItems; ++k) {
         const uint32_t q = (uint32_t)k * kRadixThreads + tid;
-        if (q < valid) {
+        if (FULL || q < valid) {
             const KeyT kk = s_keys[q];
             const uint32_t d = ((uint32_t)kk >> shift) & dmask;
             const uint32_t dst = s_gbase[d] + q;
@@ -393,6 +395,33 @@ k_radix_scatter(const KeyT *__restrict__ keys_in, const ValT *__restrict__ vals_
             }
         }
     }
+}
+
+template <typename KeyT, typename ValT, int VALMODE, bool WRITE_KEYS, bool RANGES>
+__global__ void __launch_bounds__(kRadixThreads, 2)
+k_radix_scatter(const KeyT *__restrict__ keys_in, const ValT *__restrict__ vals_in, uint32_t iota_top,
+                KeyT *__restrict__ keys_out, ValT *__restrict__ vals_out, uint32_t n_host,
+                const unsigned long long *__restrict__ n_dev, unsigned long long n_cap, int shift, int bits,
+                const uint32_t *__restrict__ tile_offsets, uint32_t stride, uint2 *ranges) {
+    const uint32_t n = n_dev ? (uint32_t)min(*n_dev, n_cap) : n_host;
+    const uint32_t tile = blockIdx.x;
+    const uint64_t tile_base = (uint64_t)tile * kRadixTile;
+    if (tile_base >= n) return; // surplus CTA of a capacity-sized grid (uniform exit)
+    // phase A: per-warp digit counters; phase B: reorder buffers (aliased)
+    __shared__ __align__(16) unsigned char s_raw[kRadixTile * (sizeof(KeyT) + sizeof(ValT)) > kRadixWarps * (kRadix + 1) * 4
+                                                     ? kRadixTile * (sizeof(KeyT) + sizeof(ValT))
+                                                     : kRadixWarps * (kRadix + 1) * 4];
+    __shared__ uint32_t s_tile_count[kRadix];  // digit totals of this tile
+    __shared__ uint32_t s_tile_start[kRadix];  // exclusive scan of the above (slot in the reorder buffer)
+    __shared__ uint32_t s_gbase[kRadix];       // global slot of reorder-slot 0 for each digit (wrapping arithmetic)
+    __shared__ uint32_t s_scan[40];
+    const uint32_t dmask = (1u << bits) - 1u;
+    if (tile_base + kRadixTile <= n)
+        radix_scatter_tile<KeyT, ValT, VALMODE, WRITE_KEYS, RANGES, true>(keys_in, vals_in, iota_top, keys_out, vals_out, n, tile, shift, dmask, tile_offsets, stride,
+                                                                          ranges, s_raw, s_tile_count, s_tile_start, s_gbase, s_scan);
+    else
+        radix_scatter_tile<KeyT, ValT, VALMODE, WRITE_KEYS, RANGES, false>(keys_in, vals_in, iota_top, keys_out, vals_out, n, tile, shift, dmask, tile_offsets, stride,
+                                                                           ranges, s_raw, s_tile_count, s_tile_start, s_gbase, s_scan);
 }
 
 // out[0..s0) = indexes[0..s0)   (sorter.cpp:158-160)
@@ -501,7 +530,7 @@ static void radix_sort_pairs(KeyT *keys0, KeyT *keys1, const ValT *vals_src, uin
         ValT *vout = last ? vals_final : vt[p & 1];
         uint32_t *th = tile_hist + (size_t)p * kRadix * stride;
         if (!(p == 0 && hist0_done)) {
-            k_radix_hist<KeyT><<<tiles, kRadixThreads, 0, st>>>(kin, n, n_dev, n_cap, pl.shift[p], pl.bits[p], th, stride, &ctl->hist[p][0], hist0_done ? 0 : 1);
+            k_radix_hist<KeyT><<<tiles, kRadixThreads, 0, st>>>(kin, n, n_dev, n_cap, pl.shift[p], pl.bits[p], th, stride, &ctl->hist[p][0], 1);
             ++launches;
             if (prof) prof->mark(names.hist[p], st);
         }

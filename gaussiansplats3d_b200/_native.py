@@ -27,7 +27,7 @@ GS_OK, GS_ERR_BAD_ARG, GS_ERR_NO_DEVICE, GS_ERR_CUDA, GS_ERR_DEGENERATE, GS_ERR_
 GS_COV_F32, GS_COV_F16 = 0, 1
 GS_SH_NONE, GS_SH_F16, GS_SH_U8, GS_SH_F32 = 0, 1, 2, 3
 GS_FRAME_RGBA32F, GS_FRAME_RGBA8 = 0, 1
-GS_BUF_SORTED_INDEXES, GS_BUF_FRAME, GS_BUF_CENTERS, GS_BUF_DISTANCES, GS_BUF_SPLAT_RECORDS, GS_BUF_INDEXES_TO_SORT = range(6)
+GS_BUF_SORTED_INDEXES, GS_BUF_FRAME, GS_BUF_CENTERS, GS_BUF_DISTANCES, GS_BUF_SPLAT_RECORDS, GS_BUF_INDEXES_TO_SORT, GS_BUF_CENTERS_COLORS, GS_BUF_COVARIANCES, GS_BUF_SH = range(9)
 
 
 class gs_config(C.Structure):
@@ -102,6 +102,16 @@ class gs_timings(C.Structure):
         return {n: getattr(self, n) for n, _ in self._fields_}
 
 
+class gs_ksplat_options(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("minimum_alpha", C.c_uint32), ("half_covariances", C.c_uint8), ("upload_sort_centers", C.c_uint8),
+                ("reserved", C.c_uint8 * 2)]
+
+
+class gs_ksplat_info(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("splat_count", C.c_uint32), ("sh_degree", C.c_uint32), ("compression_level", C.c_uint32),
+                ("section_count", C.c_uint32), ("scene_center", C.c_float * 3), ("min_sh_coeff", C.c_float), ("max_sh_coeff", C.c_float)]
+
+
 class gs_kernel_time(C.Structure):
     _fields_ = [("name", C.c_char * 40), ("ms", C.c_float)]
 
@@ -111,7 +121,7 @@ EXPORTED_SYMBOLS = [
     "gs_create", "gs_destroy", "gs_upload_centers", "gs_sort", "gs_compute_distances", "gs_upload_splat_data",
     "gs_render", "gs_frame", "gs_buffer_dev", "gs_stream", "gs_synchronize", "gs_host_alloc", "gs_host_free",
     "gs_read_projected", "gs_last_timings", "gs_frame_async", "gs_flush_l2", "gs_event_create", "gs_event_record",
-    "gs_event_elapsed_ms", "gs_event_destroy", "gs_set_profiling", "gs_kernel_timings", "gs_set_graph_enabled",
+    "gs_event_elapsed_ms", "gs_event_destroy", "gs_set_profiling", "gs_kernel_timings", "gs_set_graph_enabled", "gs_upload_ksplat", "gs_read_buffer",
 ]
 
 _lib = None
@@ -184,6 +194,10 @@ def load() -> C.CDLL:
     lib.gs_event_destroy.argtypes = [vp]
     lib.gs_set_profiling.restype = C.c_int
     lib.gs_set_profiling.argtypes = [vp, C.c_int]
+    lib.gs_upload_ksplat.restype = C.c_int
+    lib.gs_upload_ksplat.argtypes = [vp, vp, C.c_size_t, C.POINTER(gs_ksplat_options), C.POINTER(gs_ksplat_info)]
+    lib.gs_read_buffer.restype = C.c_int
+    lib.gs_read_buffer.argtypes = [vp, C.c_int, vp, C.c_size_t, C.c_size_t]
     lib.gs_set_graph_enabled.restype = C.c_int
     lib.gs_set_graph_enabled.argtypes = [vp, C.c_int]
     lib.gs_kernel_timings.restype = C.c_int

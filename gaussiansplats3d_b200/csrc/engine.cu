@@ -7,6 +7,7 @@
 #include "common.cuh"
 #include "sort_kernels.cuh"
 #include "raster_kernels.cuh"
+#include "ksplat_kernels.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -124,6 +125,8 @@ struct gs_engine {
     Profiler prof;
     // CUDA graph of one frame (sort + render), replayed while its shape key is unchanged
     cudaGraphExec_t graph_exec = nullptr;
+    cudaStream_t stream2 = nullptr;  // second capture branch (projection beside the depth sort)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     unsigned long long graph_key[8] = {0};
     bool graph_enabled = true;
     bool last_frame_was_graph = false;
@@ -161,6 +164,9 @@ extern "C" int gs_create(const gs_config *cfg, gs_engine **out) {
     CU(cudaGetDeviceProperties(&prop, c.device));
     e->sm_count = prop.multiProcessorCount;
     CU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
     for (int i = 0; i < EV_COUNT; ++i) CU(cudaEventCreate(&e->ev[i]));
     int kb = 0;
     while ((1u << kb) < c.distance_map_range) ++kb;
@@ -198,6 +204,9 @@ extern "C" void gs_destroy(gs_engine *e) {
     raster_release(e->rs);
     for (int i = 0; i < EV_COUNT; ++i) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
     if (e->stream) cudaStreamDestroy(e->stream);
+    if (e->stream2) cudaStreamDestroy(e->stream2);
+    if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+    if (e->ev_join) cudaEventDestroy(e->ev_join);
     delete e;
 }
 
@@ -490,11 +499,11 @@ extern "C" int gs_upload_splat_data(gs_engine *e, const gs_splat_data *d) {
     return GS_OK;
 }
 
-static int render_on_device(gs_engine *e, const gs_uniforms *u, const gs_render_params *p, const uint32_t *d_order, bool capturing = false) {
+static int render_on_device(gs_engine *e, const gs_uniforms *u, const gs_render_params *p, const uint32_t *d_order, bool capturing = false, int phases = 3) {
     cudaStream_t st = e->stream;
     if (!capturing) CU(cudaEventRecord(e->ev[EV_R0], st));
     if (!e->have_prof_begin) e->prof.begin(st);
-    int rc = raster_render(e->rs, e->cfg, *u, *p, d_order, st, e->ev[EV_PROJECT], e->ev[EV_BIN], e->tm, e->prof, !capturing, !capturing);
+    int rc = raster_render(e->rs, e->cfg, *u, *p, d_order, st, e->ev[EV_PROJECT], e->ev[EV_BIN], e->tm, e->prof, !capturing, !capturing, phases);
     if (rc) return rc;
     if (!capturing) CU(cudaEventRecord(e->ev[EV_R1], st));
     CU(cudaGetLastError());
@@ -597,10 +606,24 @@ static int enqueue_frame(gs_engine *e, const gs_sort_params *s, const gs_uniform
             const PassPlan pl = make_plan_bits(e->key_bits);
             if ((rc = e->lookback.ensure(radix_tile_hist_words(std::max(q.sort_count, 1u), pl.npasses, &stride)))) return rc;
             CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            // fork: the projection does not depend on the draw order, so it runs beside the (latency-bound) depth sort
+            CU(cudaEventRecord(e->ev_fork, st));
+            CU(cudaStreamWaitEvent(e->stream2, e->ev_fork, 0));
+            int rc2 = GS_OK;
+            uint32_t proj_launches = 0;
+            {
+                cudaStream_t keep = e->stream;
+                e->stream = e->stream2;
+                rc2 = render_on_device(e, u, &rp, e->sorted.p, true, 1);
+                proj_launches = e->tm.kernel_launches;
+                e->stream = keep;
+            }
+            CU(cudaEventRecord(e->ev_join, e->stream2));
             rc = sort_on_device(e, d_idx, q.model_view_proj, q.sort_count, q.render_count, q.use_precomputed_distances != 0, false, true);
             const uint32_t sort_launches = e->tm.kernel_launches;
-            int rc2 = rc ? rc : render_on_device(e, u, &rp, e->sorted.p, true);
-            e->graph_launches = e->tm.kernel_launches + sort_launches;
+            CU(cudaStreamWaitEvent(st, e->ev_join, 0));
+            if (!rc2) rc2 = rc ? rc : render_on_device(e, u, &rp, e->sorted.p, true, 2);
+            e->graph_launches = e->tm.kernel_launches + sort_launches + proj_launches;
             cudaGraph_t g = nullptr;
             cudaError_t ce = cudaStreamEndCapture(st, &g);
             if (rc2) { if (g) cudaGraphDestroy(g); return rc2; }
@@ -652,6 +675,123 @@ extern "C" int gs_frame_async(gs_engine *e, const gs_sort_params *s, const gs_un
     if ((rc = enqueue_frame(e, s, u, p, q, rp))) return rc;
     e->pending_async = true;
     e->pending_rp = rp;
+    return GS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// .ksplat -> engine, decoded on the GPU.  Header/section parsing is host logic (SplatBuffer.js:819-941).
+static uint32_t rd32(const unsigned char *p) { uint32_t v; memcpy(&v, p, 4); return v; }
+static uint16_t rd16(const unsigned char *p) { uint16_t v; memcpy(&v, p, 2); return v; }
+static float rdf(const unsigned char *p) { float v; memcpy(&v, p, 4); return v; }
+
+extern "C" int gs_upload_ksplat(gs_engine *e, const void *data, size_t bytes, const gs_ksplat_options *opt, gs_ksplat_info *info) {
+    int rc = check_engine(e);
+    if (rc) return rc;
+    if (!data || bytes < 4096) return fail(GS_ERR_BAD_ARG, "gs_upload_ksplat: buffer shorter than the 4096-byte header");
+    if (!e->cfg.max_width || !e->cfg.max_height) return fail(GS_ERR_NOT_READY, "engine created without a framebuffer (max_width/max_height = 0)");
+    gs_ksplat_options o{};
+    o.minimum_alpha = 1; o.upload_sort_centers = 1;
+    if (opt) memcpy(&o, opt, std::min<size_t>(opt->struct_size ? opt->struct_size : sizeof(o), sizeof(o)));
+    const unsigned char *f = (const unsigned char *)data;
+    const uint32_t max_sections = rd32(f + 4), max_splats = rd32(f + 12), level = rd16(f + 20);
+    if (f[0] == 0 && f[1] < 1) return fail(GS_ERR_BAD_ARG, "unsupported .ksplat version %u.%u", f[0], f[1]);
+    if (level > 2) return fail(GS_ERR_BAD_ARG, ".ksplat compression level %u unknown", level);
+    if (max_splats > e->cfg.max_splat_count) return fail(GS_ERR_CAPACITY, ".ksplat holds %u splats, engine capacity %u", max_splats, e->cfg.max_splat_count);
+    if (4096ull + 1024ull * max_sections > bytes) return fail(GS_ERR_BAD_ARG, ".ksplat truncated (section headers)");
+    static const uint32_t kC[3] = {12, 6, 6}, kS[3] = {12, 6, 6}, kR[3] = {16, 8, 8}, kSH[3] = {4, 2, 1}, kRange[3] = {1, 32767, 32767};
+    std::vector<KSectionParams> secs;
+    std::vector<std::vector<uint32_t>> prefixes;
+    unsigned long long base = 4096ull + 1024ull * max_sections;
+    uint32_t offset = 0, min_degree = 2;
+    for (uint32_t i = 0; i < max_sections; ++i) {
+        const unsigned char *h = f + 4096 + 1024ull * i;
+        KSectionParams P{};
+        P.count = rd32(h + 4);
+        P.bucket_size = rd32(h + 8);
+        const uint32_t bucket_count = rd32(h + 12);
+        const float block = rdf(h + 16);
+        const uint32_t storage = rd16(h + 20);
+        P.scale_range = rd32(h + 24) ? rd32(h + 24) : kRange[level];
+        P.full_bucket_count = rd32(h + 32);
+        P.partial_count = rd32(h + 36);
+        P.sh_degree_file = rd16(h + 40);
+        if (P.sh_degree_file > 2) return fail(GS_ERR_BAD_ARG, ".ksplat section %u: SH degree %d", i, P.sh_degree_file);
+        const uint32_t ncomp = P.sh_degree_file == 2 ? 24 : (P.sh_degree_file == 1 ? 9 : 0);
+        P.bytes_per_splat = kC[level] + kS[level] + kR[level] + 4 + kSH[level] * ncomp;
+        const unsigned long long meta = 4ull * P.partial_count, buckets_bytes = (unsigned long long)storage * bucket_count + meta;
+        P.base = base; P.buckets_base = base + meta; P.data_base = base + buckets_bytes;
+        P.splat_offset = offset; P.level = (int)level;
+        P.scale_factor = ((double)block / 2.0) / (double)P.scale_range;
+        if (P.data_base + (unsigned long long)P.bytes_per_splat * P.count > bytes) return fail(GS_ERR_BAD_ARG, ".ksplat truncated (section %u data)", i);
+        if (level >= 1 && P.partial_count == 0 && (unsigned long long)P.full_bucket_count * P.bucket_size < P.count) return fail(GS_ERR_BAD_ARG, ".ksplat section %u: buckets do not cover its splats", i);
+        std::vector<uint32_t> pre(P.partial_count + 1, 0);
+        for (uint32_t k = 0; k < P.partial_count; ++k) pre[k + 1] = pre[k] + rd32(f + P.base + 4ull * k);
+        prefixes.push_back(pre);
+        min_degree = std::min<uint32_t>(min_degree, (uint32_t)P.sh_degree_file);
+        base += (unsigned long long)P.bytes_per_splat * P.count + buckets_bytes;
+        offset += P.count;
+        secs.push_back(P);
+    }
+    if (secs.empty()) min_degree = 0;
+    const uint32_t total = offset;
+    // storage formats of the "textures" (SplatMesh.js:1064-1066: SH kept at compression level max(1, file level))
+    RasterState &rs = e->rs;
+    rs.uploaded = 0;
+    rs.cov_format = o.half_covariances ? GS_COV_F16 : GS_COV_F32;
+    rs.sh_degree = min_degree;
+    rs.sh_format = min_degree ? (level == 2 ? GS_SH_U8 : GS_SH_F16) : GS_SH_NONE;
+    const size_t n = e->cfg.max_splat_count, ncomp_out = min_degree == 2 ? 24 : (min_degree == 1 ? 9 : 0);
+    cudaError_t ce;
+    if ((ce = rs.cov.ensure(n * (o.half_covariances ? 12 : 24) + 16)) != cudaSuccess) return fail(GS_ERR_CUDA, "cudaMalloc -> %s", cudaGetErrorString(ce));
+    if (ncomp_out && (ce = rs.sh.ensure(n * ncomp_out * (level == 2 ? 1 : 2) + 16)) != cudaSuccess) return fail(GS_ERR_CUDA, "cudaMalloc -> %s", cudaGetErrorString(ce));
+    DevBuf<unsigned char> d_file; DevBuf<uint32_t> d_pre;
+    if ((rc = d_file.ensure(bytes))) return rc;
+    cudaStream_t st = e->stream;
+    CU(cudaMemcpyAsync(d_file.p, data, bytes, cudaMemcpyHostToDevice, st));
+    size_t pre_words = 0;
+    for (auto &p : prefixes) pre_words += p.size();
+    if ((rc = d_pre.ensure(pre_words))) { d_file.release(); return rc; }
+    size_t at = 0;
+    for (size_t i = 0; i < secs.size(); ++i) {
+        CU(cudaMemcpyAsync(d_pre.p + at, prefixes[i].data(), prefixes[i].size() * 4, cudaMemcpyHostToDevice, st));
+        KSectionParams P = secs[i];
+        P.sh_degree_out = (int)min_degree;
+        P.minimum_alpha = o.minimum_alpha; P.half_cov = o.half_covariances; P.integer_centers = e->cfg.integer_based_sort; P.write_sort_centers = o.upload_sort_centers;
+        if (P.count) k_ksplat_decode<<<(P.count + 127) / 128, 128, 0, st>>>(d_file.p, P, d_pre.p + at, rs.cc.p, rs.cov.p, rs.sh.p, e->centers.p);
+        at += prefixes[i].size();
+    }
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    d_file.release(); d_pre.release();
+    rs.uploaded = total;
+    rs.have_scene_idx = false;
+    if (o.upload_sort_centers) e->uploaded_splats = total;
+    if (info) {
+        memset(info, 0, sizeof(*info));
+        info->struct_size = sizeof(*info);
+        info->splat_count = total; info->sh_degree = min_degree; info->compression_level = level; info->section_count = (uint32_t)secs.size();
+        info->scene_center[0] = rdf(f + 24); info->scene_center[1] = rdf(f + 28); info->scene_center[2] = rdf(f + 32);
+        const float lo = rdf(f + 36), hi = rdf(f + 40);
+        info->min_sh_coeff = lo != 0.f ? lo : -1.5f; info->max_sh_coeff = hi != 0.f ? hi : 1.5f;   // SplatBuffer.js:833-834
+    }
+    return GS_OK;
+}
+
+// Debug / test read-back of an engine buffer (see gs_buffer_id) into host memory.
+extern "C" int gs_read_buffer(gs_engine *e, int id, void *out, size_t offset, size_t bytes) {
+    int rc = check_engine(e);
+    if (rc) return rc;
+    if (!out) return fail(GS_ERR_BAD_ARG, "gs_read_buffer: null");
+    const unsigned char *p = nullptr; size_t cap = 0;
+    switch (id) {
+        case GS_BUF_CENTERS_COLORS: p = (const unsigned char *)e->rs.cc.p; cap = e->rs.cc.n * 16; break;
+        case GS_BUF_COVARIANCES: p = e->rs.cov.p; cap = e->rs.cov.n; break;
+        case GS_BUF_SH: p = e->rs.sh.p; cap = e->rs.sh.n; break;
+        default: { void *q = nullptr; if ((rc = gs_buffer_dev(e, id, &q, &cap))) return rc; p = (const unsigned char *)q; }
+    }
+    if (!p || offset + bytes > cap) return fail(GS_ERR_CAPACITY, "gs_read_buffer: [%zu,%zu) outside the %zu-byte buffer", offset, offset + bytes, cap);
+    CU(cudaMemcpyAsync(out, p + offset, bytes, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
     return GS_OK;
 }
 

@@ -394,9 +394,22 @@ k_tile_emit(const uint32_t *__restrict__ order, uint32_t render_count, const ush
         const uint32_t inc = warp_inclusive_scan(cnt[k]);
         unsigned long long w = w0 + (inc - cnt[k]);
         w0 += __shfl_sync(0xffffffffu, inc, 31);
-        if (cnt[k] == 0) continue;
         const ushort4 r = rr[k];
         const int cx0 = r.x >> kCoarseShiftX, cx1 = r.z >> kCoarseShiftX, cy0 = r.y >> kCoarseShiftY, cy1 = r.w >> kCoarseShiftY;
+        if (__all_sync(0xffffffffu, cnt[k] <= 1u)) {
+            // common case (about 9 in 10 warps): every lane's splat sits inside one coarse tile -> no loops, no divergence
+            if (cnt[k]) {
+                const int fx0 = (int)r.x - cx0 * kCoarseW, fx1 = (int)r.z - cx0 * kCoarseW, fy0 = (int)r.y - cy0 * kCoarseH, fy1 = (int)r.w - cy0 * kCoarseH;
+                const uint32_t rowsel = (0x01010101u >> (8 * (kCoarseH - 1 - (fy1 - fy0)))) << (8 * fy0);
+                const uint32_t mask = (((1u << (fx1 - fx0 + 1)) - 1u) << fx0) * rowsel;
+                if (w < capacity) {
+                    keys[w] = (uint16_t)(cy0 * coarse_x + cx0);
+                    vals[w] = ((unsigned long long)mask << 32) | sid[k];
+                } else overflow = true;
+            }
+            continue;
+        }
+        if (cnt[k] == 0) continue;
 #pragma unroll 1
         for (int cy = cy0; cy <= cy1; ++cy) {
             const int fy0 = max((int)r.y, cy * kCoarseH) - cy * kCoarseH, fy1 = min((int)r.w, cy * kCoarseH + kCoarseH - 1) - cy * kCoarseH;
@@ -751,7 +764,8 @@ static int raster_upload_params(RasterState &rs, const gs_config &c, const gs_un
 }
 
 static int raster_render(RasterState &rs, const gs_config &c, const gs_uniforms &u, const gs_render_params &p, const uint32_t *d_order,
-                         cudaStream_t st, cudaEvent_t ev_project, cudaEvent_t ev_bin, gs_timings &tm, Profiler &prof, bool upload_params, bool record_events) {
+                         cudaStream_t st, cudaEvent_t ev_project, cudaEvent_t ev_bin, gs_timings &tm, Profiler &prof, bool upload_params, bool record_events,
+                         int phases = 3) {
     if (!rs.uploaded) { snprintf(raster_err(), 512, "gs_render before gs_upload_splat_data"); return GS_ERR_NOT_READY; }
     if (p.width == 0 || p.height == 0 || p.width > c.max_width || p.height > c.max_height) {
         snprintf(raster_err(), 512, "frame %ux%u outside the engine's %ux%u", p.width, p.height, c.max_width, c.max_height); return GS_ERR_BAD_ARG;
@@ -770,14 +784,17 @@ static int raster_render(RasterState &rs, const gs_config &c, const gs_uniforms 
     int tile_bits = 1;
     while ((1u << tile_bits) < std::max(ncoarse, 2u)) ++tile_bits;
     const PassPlan pl = make_plan_bits(tile_bits);
-    k_raster_init<<<8, 256, 0, st>>>(rs.rctl.p, rs.sctl.p, rs.ranges.p, ncoarse);
-    ++launches;
-    prof.mark("k_raster_init", st);
-    const uint32_t count = rs.uploaded;
-    if (rs.cov_format == GS_COV_F16) launch_project<true>(rs, count, st); else launch_project<false>(rs, count, st);
-    ++launches;
-    prof.mark("k_project", st);
-    if (record_events) RCU(cudaEventRecord(ev_project, st));
+    if (phases & 1) {
+        k_raster_init<<<8, 256, 0, st>>>(rs.rctl.p, rs.sctl.p, rs.ranges.p, ncoarse);
+        ++launches;
+        prof.mark("k_raster_init", st);
+        const uint32_t count = rs.uploaded;
+        if (rs.cov_format == GS_COV_F16) launch_project<true>(rs, count, st); else launch_project<false>(rs, count, st);
+        ++launches;
+        prof.mark("k_project", st);
+        if (record_events) RCU(cudaEventRecord(ev_project, st));
+    }
+    if (!(phases & 2)) { tm.kernel_launches = launches; return GS_OK; }
     if (p.render_count && local_tiles) {
         const uint32_t chunks = (p.render_count + kBinTile - 1) / kBinTile;
         k_tile_count<<<chunks, kBinThreads, 0, st>>>(d_order, p.render_count, rs.rects.p, rs.block_sums.p, rs.rctl.p);

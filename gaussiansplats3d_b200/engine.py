@@ -209,6 +209,22 @@ class Engine:
             keep.append(si)
         N.check(self._lib.gs_upload_splat_data(self._h, C.byref(d)), "gs_upload_splat_data")
 
+    def upload_ksplat(self, data: bytes, *, minimum_alpha: int = 1, half_covariances: bool = False, upload_sort_centers: bool = True) -> dict:
+        """Decode a .ksplat buffer on the GPU into the splat data AND the sorter's centres (gs_upload_ksplat)."""
+        o = N.gs_ksplat_options()
+        o.struct_size = C.sizeof(N.gs_ksplat_options)
+        o.minimum_alpha, o.half_covariances, o.upload_sort_centers = minimum_alpha, 1 if half_covariances else 0, 1 if upload_sort_centers else 0
+        info = N.gs_ksplat_info()
+        buf = np.frombuffer(data, dtype=np.uint8)
+        N.check(self._lib.gs_upload_ksplat(self._h, N.ptr(buf), buf.size, C.byref(o), C.byref(info)), "gs_upload_ksplat")
+        return dict(splat_count=info.splat_count, sh_degree=info.sh_degree, compression_level=info.compression_level, section_count=info.section_count,
+                    scene_center=tuple(info.scene_center), min_sh_coeff=info.min_sh_coeff, max_sh_coeff=info.max_sh_coeff)
+
+    def read_buffer(self, buffer_id: int, dtype, count: int, offset_bytes: int = 0) -> np.ndarray:
+        out = np.empty(count, dtype)
+        N.check(self._lib.gs_read_buffer(self._h, buffer_id, N.ptr(out), offset_bytes, out.nbytes), "gs_read_buffer")
+        return out
+
     @staticmethod
     def _render_params(width, height, render_count, sorted_indexes, fmt, flip_y):
         p = N.gs_render_params()

@@ -158,6 +158,28 @@ class Viewer:
             self.engine.upload_centers(centers)
         self.splatRenderCount = n
 
+    def addSplatSceneFromKSplat(self, data: bytes) -> dict:  # noqa: N802
+        """Viewer.addSplatScene for a `.ksplat` buffer (KSplatLoader.loadFromFileData -> new SplatBuffer -> SplatMesh.build ->
+        'centers' message, Viewer.js:736-868, 1094-1167): header parsing on the host, every per-splat decode on the GPU."""
+        from . import ksplat as K
+        hdr = K.parse(data)
+        n = hdr.max_splat_count
+        self.splatMesh = SplatMesh(dynamicMode=False, halfPrecisionCovariancesOnGPU=self.halfPrecisionCovariancesOnGPU,
+                                   devicePixelRatio=self.devicePixelRatio, antialiased=self.antialiased,
+                                   maxScreenSpaceSplatSize=self.maxScreenSpaceSplatSize, sphericalHarmonicsDegree=self.sphericalHarmonicsDegree,
+                                   kernel2DSize=self.kernel2DSize)
+        self.engine = Engine(n, device=self.device, distance_map_range=1 << self.splatSortDistanceMapPrecision,
+                             integer_based_sort=self.integerBasedSort, dynamic_mode=False, max_width=self.renderWidth, max_height=self.renderHeight,
+                             rank=self.rank, world_size=self.world_size)
+        info = self.engine.upload_ksplat(data, half_covariances=self.halfPrecisionCovariancesOnGPU)
+        self.splatMesh.engine = self.engine
+        degree = min(self.sphericalHarmonicsDegree, info["sh_degree"])
+        self.splatMesh.packed = PackedScene(None, None, None, degree, None, info["splat_count"])
+        self.splatMesh.sceneCenter = info["scene_center"]
+        self._ksplat_info = info
+        self.splatRenderCount = info["splat_count"]
+        return info
+
     def _on_worker_message(self, e) -> None:  # Viewer.js:1243-1298
         d = e.data
         if d.get("sortDone"):
@@ -198,6 +220,8 @@ class Viewer:
                         splat_scale=sm.splatScale, point_cloud_mode=1 if sm.pointCloudModeEnabled else 0,
                         sh_degree=sm.packed.sh_degree, antialiased=1 if sm.antialiased else 0, kernel_2d_size=sm.kernel2DSize,
                         max_screen_space_splat_size=sm.maxScreenSpaceSplatSize, fade_in_complete=1 if sm.fadeInComplete else 0,
+                        sh8_min=np.full(N.GS_MAX_SCENES, getattr(self, "_ksplat_info", {}).get("min_sh_coeff", -1.5), np.float32),
+                        sh8_max=np.full(N.GS_MAX_SCENES, getattr(self, "_ksplat_info", {}).get("max_sh_coeff", 1.5), np.float32),
                         scene_center=sm.sceneCenter, visible_region_fade_start_radius=sm.visibleRegionFadeStartRadius)
 
     # -- the per-frame path --------------------------------------------------------------------------------------------------------

@@ -141,6 +141,24 @@ typedef struct gs_splat_data {
 
 GS_API int gs_upload_splat_data(gs_engine *e, const gs_splat_data *d);
 
+/* `.ksplat` buffer (the SplatBuffer container, src/loaders/SplatBuffer.js:819-941, KSplatLoader.loadFromFileData) decoded ON THE
+ * GPU into everything above at once: centres+colours, covariances, spherical harmonics AND the sorter's centres
+ * (= new SplatBuffer(fileData) + SplatMesh.build + the 'centers' message).  Compression levels 0/1/2, SH degree 0/1/2.        */
+typedef struct gs_ksplat_options {
+    uint32_t struct_size;
+    uint32_t minimum_alpha;          /* splatAlphaRemovalThreshold (Viewer.js), default 1: alpha below it renders as 0            */
+    uint8_t half_covariances;        /* halfPrecisionCovariancesOnGPU                                                            */
+    uint8_t upload_sort_centers;     /* also fill the sorter's centres (integer or float per gs_config), default 1              */
+    uint8_t reserved[2];
+} gs_ksplat_options;
+typedef struct gs_ksplat_info {
+    uint32_t struct_size;
+    uint32_t splat_count, sh_degree, compression_level, section_count;
+    float scene_center[3];
+    float min_sh_coeff, max_sh_coeff; /* 8-bit SH range -> gs_uniforms.sh8_min/max                                                */
+} gs_ksplat_info;
+GS_API int gs_upload_ksplat(gs_engine *e, const void *data, size_t bytes, const gs_ksplat_options *opt, gs_ksplat_info *info);
+
 typedef struct gs_uniforms {
     uint32_t struct_size;
     float model_view[16];             /* three: modelViewMatrix = camera.matrixWorldInverse * mesh.matrixWorld    */
@@ -210,9 +228,11 @@ typedef enum gs_buffer_id {
     GS_BUF_CENTERS = 2,
     GS_BUF_DISTANCES = 3,      /* i32[render_count] scratch (= mappedDistances)                                   */
     GS_BUF_SPLAT_RECORDS = 4,  /* per-splat projected records (engine-internal 48-byte layout)                    */
-    GS_BUF_INDEXES_TO_SORT = 5 /* u32[max_splat_count] staging for indexesToSort                                  */
+    GS_BUF_INDEXES_TO_SORT = 5,/* u32[max_splat_count] staging for indexesToSort                                  */
+    GS_BUF_CENTERS_COLORS = 6, GS_BUF_COVARIANCES = 7, GS_BUF_SH = 8   /* the uploaded / decoded splat data (gs_read_buffer only) */
 } gs_buffer_id;
 GS_API int gs_buffer_dev(gs_engine *e, int buffer_id, void **ptr_dev, size_t *bytes);
+GS_API int gs_read_buffer(gs_engine *e, int buffer_id, void *out, size_t offset, size_t bytes); /* D2H copy, for tests / tools */
 GS_API int gs_stream(gs_engine *e, void **cuda_stream); /* cudaStream_t of the engine */
 GS_API int gs_synchronize(gs_engine *e);
 

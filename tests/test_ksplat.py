@@ -1,0 +1,104 @@
+"""`.ksplat` container: writer/reader round trip (CPU) and the GPU decode (gs_upload_ksplat) against the NumPy restatement of the
+reference's SplatBuffer decode (oracle/ksplat_oracle.py).  Bit-exact for centres, colours, sorter centres, covariances and SH."""
+import numpy as np
+import pytest
+
+LEVELS_DEGREES = [(l, d) for l in (0, 1, 2) for d in (0, 1, 2)]
+
+
+def _scene(n=6000, seed=3, deg=2):
+    from gaussiansplats3d_b200.scenes import synthetic_scene
+    raw = synthetic_scene(n, seed, "bonsai", 2)
+    sh = None if deg == 0 else raw.sh[:, : (3 if deg == 1 else 8)]
+    return raw, sh
+
+
+@pytest.mark.parametrize("level,deg", LEVELS_DEGREES)
+def test_writer_reader_round_trip(level, deg):
+    from gaussiansplats3d_b200 import ksplat as K
+    from oracle import ksplat_oracle as KO
+    raw, sh = _scene(deg=deg)
+    data = K.write(raw.centers, raw.scales, raw.rotations, raw.colors, sh, deg, compression_level=level)
+    h = K.parse(data)
+    assert h.compression_level == level and h.sections[0].sh_degree == deg and h.sections[0].bytes_per_splat == K.bytes_per_splat(level, deg)
+    assert len(data) == K.HEADER_BYTES + K.SECTION_HEADER_BYTES + h.sections[0].data_base - h.sections[0].base + h.splat_count * h.sections[0].bytes_per_splat
+    d = KO.decode(data)
+    keep = raw.colors[:, 3] >= 1
+    assert d["count"] == keep.sum()
+    if level == 0:
+        assert np.array_equal(d["centers"], raw.centers[keep]) and np.array_equal(d["scales"], raw.scales[keep])
+        assert np.array_equal(d["colors"], raw.colors[keep])
+    else:
+        # bucket-relative u16 centres: |error| <= half a quantisation step of (blockSize/2)/32767, as a set (buckets reorder the splats)
+        step = (K.BUCKET_BLOCK_SIZE / 2) / 32767
+        a = np.sort(d["centers"].astype(np.float64), 0); b = np.sort(raw.centers[keep].astype(np.float64), 0)
+        assert np.abs(a - b).max() <= 0.5 * step + 1e-6
+        assert h.sections[0].full_bucket_count * K.BUCKET_SIZE + sum(np.frombuffer(data, np.uint8)[h.sections[0].base:h.sections[0].buckets_base].view(np.uint32)) == d["count"]
+    q = d["rotations"].astype(np.float64)
+    assert np.abs(np.linalg.norm(q, axis=1) - 1).max() < 2e-3
+    if deg:
+        assert d["sh"].shape == (d["count"], 9 if deg == 1 else 24)
+
+
+def test_to_half_three_truncates():
+    from gaussiansplats3d_b200 import ksplat as K
+    x = np.array([0.1, -0.1, 1.0009765625, 65504.0, 1e9, 6e-8, 3e-5, 0.0, -2.5], np.float32)
+    h = K.to_half_three(x).view(np.float16).astype(np.float32)
+    assert np.all(np.abs(h) <= np.abs(np.clip(x, -65504, 65504)))          # truncation toward zero, never rounds up in magnitude
+    rne = np.clip(x, -65504, 65504).astype(np.float16).astype(np.float32)
+    assert np.all(np.abs(h - rne) <= np.abs(rne) * 2.0 ** -10 + 6e-8)
+    assert h[3] == 65504.0 and h[4] == 65504.0 and h[7] == 0.0 and h[8] == -2.5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("level,deg", LEVELS_DEGREES)
+@pytest.mark.parametrize("integer", [True, False])
+def test_gpu_decode_matches_splatbuffer_semantics(gs, level, deg, integer):
+    from gaussiansplats3d_b200 import ksplat as K
+    from gaussiansplats3d_b200 import _native as N
+    from oracle import ksplat_oracle as KO
+    if not integer and (level, deg) not in ((0, 0), (1, 2), (2, 1)):
+        pytest.skip("float-centre variant checked on a subset")
+    raw, sh = _scene(n=20000, seed=4 + level, deg=deg)
+    half_cov = (level == 1)
+    data = K.write(raw.centers, raw.scales, raw.rotations, raw.colors, sh, deg, compression_level=level, bucket_size=100 if level else K.BUCKET_SIZE)
+    want = KO.decode(data, half_covariances=half_cov)
+    n = want["count"]
+    with gs.Engine(n + 7, max_width=64, max_height=64, integer_based_sort=integer) as e:
+        info = e.upload_ksplat(data, half_covariances=half_cov)
+        assert info["splat_count"] == n and info["sh_degree"] == deg and info["compression_level"] == level
+        cc = e.read_buffer(N.GS_BUF_CENTERS_COLORS, np.uint32, 4 * n).reshape(n, 4)
+        assert np.array_equal(cc, want["centers_colors"])
+        cov = e.read_buffer(N.GS_BUF_COVARIANCES, np.float16 if half_cov else np.float32, 6 * n).reshape(n, 6)
+        assert np.array_equal(cov.view(np.uint16 if half_cov else np.uint32), want["covariances"].view(np.uint16 if half_cov else np.uint32))
+        if deg:
+            ncomp = 9 if deg == 1 else 24
+            shd = e.read_buffer(N.GS_BUF_SH, np.uint8 if level == 2 else np.uint16, ncomp * n).reshape(n, ncomp)
+            assert np.array_equal(shd, want["sh"].view(np.uint8 if level == 2 else np.uint16).reshape(n, ncomp))
+        cen = e.read_buffer(N.GS_BUF_CENTERS, np.int32 if integer else np.float32, 4 * n).reshape(n, 4)
+        assert np.array_equal(cen, want["int_centers"] if integer else want["float_centers"])
+
+
+@pytest.mark.gpu
+def test_frame_from_ksplat_equals_frame_from_arrays(gs, oracle_mod):
+    """End to end: a level-1 SH2 .ksplat decoded on the GPU renders exactly like the same data uploaded as arrays."""
+    from gaussiansplats3d_b200 import ksplat as K
+    from gaussiansplats3d_b200.scenes import CAMERAS
+    from gaussiansplats3d_b200.viewer import Viewer
+    from oracle import ksplat_oracle as KO
+    raw, sh = _scene(n=60000, seed=9, deg=2)
+    data = K.write(raw.centers, raw.scales, raw.rotations, raw.colors, sh, 2, compression_level=1)
+    d = KO.decode(data)
+    n, w, h = d["count"], 640, 360
+    c = CAMERAS["bonsai"]
+    v = Viewer(dict(cameraUp=c["up"], initialCameraPosition=c["position"], initialCameraLookAt=c["look_at"], width=w, height=h, sphericalHarmonicsDegree=2))
+    info = v.addSplatSceneFromKSplat(data)
+    assert info["splat_count"] == n
+    got = v.frame(frame_format=gs._native.GS_FRAME_RGBA32F, flip_y=False)
+    order, _ = v.engine.sort(v.mvp_matrix().astype(np.float32), n, n, None)
+    want_order = oracle_mod.port_sort_indexes(np.arange(n, dtype=np.uint32), d["int_centers"], None, v.mvp_matrix().astype(np.float32), None, None, 1 << 16, n, n, n, False, True, False)
+    assert np.array_equal(order, want_order)
+    want, _ = oracle_mod.render(v.uniforms(), d["centers_colors"], d["covariances"], order, w, h, sh=d["sh"], sh_degree=2)
+    err = np.abs(got - want)
+    assert err.max() <= 8 / 255 and (err <= 2 / 255).mean() >= 0.999
+    v.dispose()

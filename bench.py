@@ -11,8 +11,8 @@ RGBA8 1920x1080 frame (Viewer.update + Viewer.render of the reference).  Prints 
 value   device-timed (CUDA events on the engine's stream), scene resident in HBM, L2 flushed between steps.
 e2e     the same frame through the C ABI with HOST buffers: indexesToSort + camera uniforms go host->device from pinned
         memory, the RGBA8 frame comes back device->host, all inside the timed region.
-N > 1   strong scaling of ONE frame: rank r rasterises tile rows r, r+N, ...; every rank sorts (replicated scene, no
-        splat exchange); the finished strips are all-gathered with NCCL (the only collective).
+N > 1   strong scaling of ONE frame: rank r rasterises the 128x64-px coarse tiles with (cx+cy) % N == r; every rank sorts
+        (replicated scene, no splat exchange); the per-rank frames are summed with one NCCL all-reduce (the only collective).
 """
 from __future__ import annotations
 
@@ -211,9 +211,24 @@ def run_ours(args):
     prepared = e.prepare_frame(mvp, v.uniforms(), width, height, n, frame_format=N.GS_FRAME_RGBA8, flip_y=True)
 
     gather = None
+    gather_kind = None
     if world > 1:
-        from gaussiansplats3d_b200.parallel import TileGather
-        gather = TileGather(e, width, height, rank, world, fmt=N.GS_FRAME_RGBA8)
+        from gaussiansplats3d_b200.parallel import PeerGather, TileGather
+        want = os.environ.get("GS_GATHER", "peer")
+        if want == "peer":
+            try:   # fused: ranks > 0 blend straight into rank 0's frame over NVLink (CUDA IPC); no collective on the data path
+                gather = PeerGather(e, rank, world)
+                gather_kind = "peer-memory stores from the blend kernel into rank 0's frame (CUDA IPC over NVLink)"
+            except Exception as ex:   # e.g. IPC not permitted in this container: fall back to NCCL
+                print(f"[rank {rank}] peer gather unavailable ({ex}); using NCCL all-reduce", file=sys.stderr)
+                gather = None
+        ok = torch.tensor([1 if gather is not None else 0], device="cuda")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            if gather is not None:
+                raise SystemExit("peer gather attached on some ranks only")
+            gather = TileGather(e, width, height, rank, world, fmt=N.GS_FRAME_RGBA8)
+            gather_kind = "NCCL all-reduce (SUM) of per-rank frames"
 
     def step_async():
         e.frame_async(None, None, width, height, n, prepared=prepared)
@@ -271,6 +286,13 @@ def run_ours(args):
     inst, vis = int(tm["tile_instances"]), int(tm["visible_splats"])
     ab = algorithmic_bytes(dominant, n, sh, width, height, inst, vis)
     achieved = (ab / (kernels[dominant] * 1e-3) / 1e9) if ab else None
+    # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this same command (profiles/)
+    traffic = None
+    tfile = ROOT / "profiles" / "r1_top_kernels_traffic.json"
+    if tfile.exists():
+        tj = json.loads(tfile.read_text())
+        key = next((k for k in tj if k.split("<")[0] == dominant.split("[")[0]), None)
+        traffic = tj.get(key) if key else None
     path_bytes = n * (44 + SH_BYTES[sh]) + width * height * 4       # per rendered splat + framebuffer
     sort_bytes = n * 24                                             # 16 B centre + 4 B index in + 4 B index out
 
@@ -296,18 +318,26 @@ def run_ours(args):
     else:
         # N GPUs: the frame is assembled on every rank by the NCCL gather; rank 0 copies it to pinned host memory
         frame_host = None
+        peer = not hasattr(gather, "image")
         if rank == 0:
-            frame_host = torch.empty((gather.padded_rows * world, width, 4), dtype=torch.uint8).pin_memory()
+            frame_host = N.pinned_empty((height, width, 4), np.uint8) if peer else torch.empty((height, width, 4), dtype=torch.uint8).pin_memory()
         t_e2e = []
         for i in range(W + K):
             e.flush_l2()
             barrier()
             t0 = time.perf_counter()
-            step_async()
-            gather.sync_to_torch()
-            if rank == 0:
-                frame_host.copy_(gather.gathered.view(-1, width, 4), non_blocking=True)
-            torch.cuda.synchronize()
+            if peer:
+                if rank == 0:
+                    e.frame_prepared(prepared, frame_host)       # returns when all ranks' tiles are in and the frame is in host memory
+                else:
+                    step_async()
+                    e.synchronize()
+            else:
+                step_async()
+                gather.sync_to_torch()
+                if rank == 0:
+                    frame_host.copy_(gather.image(), non_blocking=True)
+                torch.cuda.synchronize()
             dt = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
             if i >= W:
@@ -333,12 +363,14 @@ def run_ours(args):
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "int32 sort keys / f32 raster", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {n} splats SH{sh} {width}x{height} fixed camera (synthetic stand-in for the .ksplat, seed {seed})",
-                       "l2": "flushed between steps (192 MiB write)", "parallelism": f"tile-row interleave x{world}" if world > 1 else "single GPU",
-                       "distance_map_range": 65536},
+                       "l2": "flushed between steps (192 MiB write)", "parallelism": f"coarse-tile diagonal interleave x{world}, replicated sort, 1 NCCL all-reduce" if world > 1 else "single GPU",
+                       "distance_map_range": 65536, "gather": gather_kind},
             "sorted_msplats_per_sec": n / (sort_ms * 1e-3) / 1e6 if sort_ms > 0 else None,
             "sort_ms": sort_ms, "kernel_ms": kernels, "tile_instances": inst, "visible_splats": vis,
             "roofline": {"kernel": dominant, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-                         "traffic": None, "peak_source": peak_src, "launch_ms": kernels[dominant]},
+                         "traffic": traffic, "peak_source": peak_src, "launch_ms": kernels[dominant], "algorithmic_bytes": ab,
+                         "note": "k_blend is FP32-issue bound (ncu: issue active ~80%, DRAM ~1%); its HBM fraction is low by construction"
+                         if dominant == "k_blend" else None},
             "path_roofline": {"bound": "hbm", "frame_bytes": path_bytes, "frame_gbs": path_bytes / (frame_kernel_ms * 1e-3) / 1e9,
                               "frame_frac": path_bytes / (frame_kernel_ms * 1e-3) / 1e9 / peak,
                               "sort_bytes": sort_bytes, "sort_gbs": sort_bytes / (sort_ms * 1e-3) / 1e9 if sort_ms else None,

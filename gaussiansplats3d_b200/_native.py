@@ -121,7 +121,7 @@ EXPORTED_SYMBOLS = [
     "gs_create", "gs_destroy", "gs_upload_centers", "gs_sort", "gs_compute_distances", "gs_upload_splat_data",
     "gs_render", "gs_frame", "gs_buffer_dev", "gs_stream", "gs_synchronize", "gs_host_alloc", "gs_host_free",
     "gs_read_projected", "gs_last_timings", "gs_frame_async", "gs_flush_l2", "gs_event_create", "gs_event_record",
-    "gs_event_elapsed_ms", "gs_event_destroy", "gs_set_profiling", "gs_kernel_timings", "gs_set_graph_enabled", "gs_upload_ksplat", "gs_read_buffer",
+    "gs_event_elapsed_ms", "gs_event_destroy", "gs_set_profiling", "gs_kernel_timings", "gs_set_graph_enabled", "gs_upload_ksplat", "gs_read_buffer", "gs_peer_export", "gs_peer_attach",
 ]
 
 _lib = None
@@ -198,6 +198,10 @@ def load() -> C.CDLL:
     lib.gs_upload_ksplat.argtypes = [vp, vp, C.c_size_t, C.POINTER(gs_ksplat_options), C.POINTER(gs_ksplat_info)]
     lib.gs_read_buffer.restype = C.c_int
     lib.gs_read_buffer.argtypes = [vp, C.c_int, vp, C.c_size_t, C.c_size_t]
+    lib.gs_peer_export.restype = C.c_int
+    lib.gs_peer_export.argtypes = [vp, vp, vp]
+    lib.gs_peer_attach.restype = C.c_int
+    lib.gs_peer_attach.argtypes = [vp, vp, vp]
     lib.gs_set_graph_enabled.restype = C.c_int
     lib.gs_set_graph_enabled.argtypes = [vp, C.c_int]
     lib.gs_kernel_timings.restype = C.c_int

@@ -201,6 +201,7 @@ extern "C" void gs_destroy(gs_engine *e) {
     e->keys[0].release(); e->keys[1].release(); e->vals[0].release(); e->vals[1].release(); e->sorted.release();
     e->transforms.release(); e->ctl.release(); e->depthp.release(); e->lookback.release(); e->freq.release();
     e->h_indexes.release(); e->h_sorted.release(); e->h_ctl.release(); e->h_frame.release(); e->flush.release(); e->prof.release();
+    if (e->rs.peer_attached) { if (e->rs.peer_frame) cudaIpcCloseMemHandle(e->rs.peer_frame); if (e->rs.peer_sync) cudaIpcCloseMemHandle(e->rs.peer_sync); }
     raster_release(e->rs);
     for (int i = 0; i < EV_COUNT; ++i) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
     if (e->stream) cudaStreamDestroy(e->stream);
@@ -515,8 +516,8 @@ static size_t frame_bytes(const gs_render_params *p) { return (size_t)p->width *
 static int finish_render(gs_engine *e, const gs_render_params *p, void *frame_out) {
     cudaStream_t st = e->stream;
     CU(cudaEventRecord(e->ev[EV_D2H0], st));
-    // world_size > 1: the engine holds (and returns) only its own compact strip of tile rows
-    if (frame_out) CU(cudaMemcpyAsync(frame_out, raster_frame_ptr(e->rs, p->frame_format), e->cfg.world_size > 1 ? e->rs.last_frame_bytes : frame_bytes(p), cudaMemcpyDeviceToHost, st));
+    // world_size > 1: a full-size frame whose pixels outside this rank's coarse tiles are zero
+    if (frame_out) CU(cudaMemcpyAsync(frame_out, raster_frame_ptr(e->rs, p->frame_format), frame_bytes(p), cudaMemcpyDeviceToHost, st));
     CU(cudaEventRecord(e->ev[EV_D2H1], st));
     CU(cudaMemcpyAsync(e->h_ctl.p + 16, e->rs.rctl.p, sizeof(RasterControl), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
@@ -534,6 +535,7 @@ static int finish_render(gs_engine *e, const gs_render_params *p, void *frame_ou
     memcpy(&rc, e->h_ctl.p + 16, sizeof(rc));
     e->tm.tile_instances = rc.total_instances;
     e->tm.visible_splats = rc.visible;
+    if (rc.peer_timeout) return fail(GS_ERR_CUDA, "multi-GPU tile gather: a peer did not arrive within the time limit (ranks must render the same frames)");
     if (rc.overflow) return fail(GS_ERR_CAPACITY, "tile-instance buffer overflow: %llu instances needed, capacity %llu (raise GS_INSTANCE_FACTOR)",
                                  (unsigned long long)rc.total_instances, (unsigned long long)e->rs.instance_capacity);
     return GS_OK;
@@ -852,6 +854,47 @@ extern "C" int gs_flush_l2(gs_engine *e) { // overwrite a buffer larger than L2 
     CU(cudaGetLastError());
     return GS_OK;
 }
+// ---- fused tile gather: rank 0's frame buffer + handshake block shared with the other ranks through CUDA IPC -------------------------
+extern "C" int gs_peer_export(gs_engine *e, void *frame_handle, void *sync_handle) {
+    int rc = check_engine(e);
+    if (rc) return rc;
+    if (!frame_handle || !sync_handle) return fail(GS_ERR_BAD_ARG, "gs_peer_export: null");
+    if (e->cfg.world_size < 2 || e->cfg.rank != 0) return fail(GS_ERR_BAD_ARG, "gs_peer_export: only rank 0 of a multi-GPU group exports");
+    if (!e->rs.frame.p) return fail(GS_ERR_NOT_READY, "engine created without a framebuffer");
+    cudaError_t ce = e->rs.peer_sync_local.ensure(1);
+    if (ce != cudaSuccess) return fail(GS_ERR_CUDA, "cudaMalloc -> %s", cudaGetErrorString(ce));
+    CU(cudaMemset(e->rs.peer_sync_local.p, 0, sizeof(PeerSync)));
+    static_assert(sizeof(cudaIpcMemHandle_t) == GS_IPC_HANDLE_BYTES, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, e->rs.frame.p));
+    memcpy(frame_handle, &h, sizeof(h));
+    CU(cudaIpcGetMemHandle(&h, e->rs.peer_sync_local.p));
+    memcpy(sync_handle, &h, sizeof(h));
+    CU(cudaMemset(&e->rs.rctl.p->frame_seq, 0, 4));   // ranks count frames in lockstep from here on
+    e->rs.peer_sync = e->rs.peer_sync_local.p;
+    e->rs.peer_root = true;
+    if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
+    return GS_OK;
+}
+extern "C" int gs_peer_attach(gs_engine *e, const void *frame_handle, const void *sync_handle) {
+    int rc = check_engine(e);
+    if (rc) return rc;
+    if (!frame_handle || !sync_handle) return fail(GS_ERR_BAD_ARG, "gs_peer_attach: null");
+    if (e->cfg.world_size < 2 || e->cfg.rank == 0) return fail(GS_ERR_BAD_ARG, "gs_peer_attach: only ranks > 0 of a multi-GPU group attach");
+    cudaIpcMemHandle_t h;
+    void *pf = nullptr, *ps = nullptr;
+    memcpy(&h, frame_handle, sizeof(h));
+    CU(cudaIpcOpenMemHandle(&pf, h, cudaIpcMemLazyEnablePeerAccess));
+    memcpy(&h, sync_handle, sizeof(h));
+    CU(cudaIpcOpenMemHandle(&ps, h, cudaIpcMemLazyEnablePeerAccess));
+    CU(cudaMemset(&e->rs.rctl.p->frame_seq, 0, 4));
+    e->rs.peer_frame = pf;
+    e->rs.peer_sync = (PeerSync *)ps;
+    e->rs.peer_attached = true;
+    if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
+    return GS_OK;
+}
+
 extern "C" int gs_set_graph_enabled(gs_engine *e, int on) {
     if (!e) return fail(GS_ERR_BAD_ARG, "gs_set_graph_enabled: null");
     e->graph_enabled = on != 0;

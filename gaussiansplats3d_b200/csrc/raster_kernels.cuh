@@ -33,8 +33,52 @@ struct RasterControl {
     uint32_t overflow;
     uint32_t visible;
     uint32_t scan_ticket;
-    uint32_t pad[3];
+    uint32_t frame_seq;      // frames rendered so far (never reset): the peer-gather handshake counts in frames
+    uint32_t peer_timeout;   // a peer handshake gave up waiting
+    uint32_t pad[1];
 };
+
+// Block in rank 0's memory that the other ranks map through CUDA IPC: the fused tile gather's handshake.
+//   released = f : rank 0 has finished with frame f-1's picture; peers may write frame f's tiles into rank 0's frame buffer
+//   arrived      : += 1 by every peer once its tiles of the current frame are in rank 0's buffer
+struct PeerSync { uint32_t released; uint32_t arrived; uint32_t pad[2]; };
+
+__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+constexpr long long kPeerTimeoutCycles = 4000000000ll;   // ~2 s: a missing peer must never hang the GPU
+
+// rank 0, start of frame f: the picture of frame f-1 has been consumed (stream order) -> peers may overwrite the buffer
+__global__ void k_peer_release(PeerSync *sync, const RasterControl *rctl) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(&sync->released), "r"(rctl->frame_seq) : "memory");
+}
+// rank r > 0, before its blend of frame f: wait until rank 0 released frame f
+__global__ void k_peer_wait_release(const PeerSync *sync, RasterControl *rctl) {
+    const uint32_t f = rctl->frame_seq;
+    const long long t0 = clock64();
+    while ((int32_t)(ld_acquire_sys_u32(&sync->released) - f) < 0) {
+        if (clock64() - t0 > kPeerTimeoutCycles) { rctl->peer_timeout = 1; break; }
+        __nanosleep(200);
+    }
+}
+// rank r > 0, after its blend: tiles are in rank 0's frame
+__global__ void k_peer_signal(PeerSync *sync) {
+    __threadfence_system();
+    atomicAdd_system(&sync->arrived, 1u);
+}
+// rank 0, end of frame f: wait for the tiles of all world-1 peers
+__global__ void k_peer_wait_arrived(const PeerSync *sync, RasterControl *rctl, uint32_t peers) {
+    const uint32_t want = rctl->frame_seq * peers;
+    const long long t0 = clock64();
+    while ((int32_t)(ld_acquire_sys_u32(&sync->arrived) - want) < 0) {
+        if (clock64() - t0 > kPeerTimeoutCycles) { rctl->peer_timeout = 1; break; }
+        __nanosleep(200);
+    }
+    __threadfence_system();
+}
 
 struct ProjParams {
     float mv[16], proj[16];
@@ -61,14 +105,10 @@ struct DynamicUniforms {               // only read in dynamic / optional-effect
     int visibility[GS_MAX_SCENES_DEV];
 };
 
-// number of tile rows in [ty0, ty1] owned by `rank` under row-interleaved ownership (row % world == rank)
-__host__ __device__ __forceinline__ int owned_rows(int ty0, int ty1, uint32_t rank, uint32_t world) {
-    if (ty1 < ty0) return 0;
-    if (world == 1) return ty1 - ty0 + 1;
-    // first owned row >= ty0
-    int r = ty0 + (int)(((int)rank - (ty0 % (int)world) + (int)world) % (int)world);
-    if (r > ty1) return 0;
-    return (ty1 - r) / (int)world + 1;
+// Multi-GPU ownership: COARSE tile (cx, cy) belongs to rank (cx + cy) % world -- a diagonal interleave, so every rank gets tiles from
+// all over the picture (dense centre and empty border alike) and any `world` horizontally adjacent coarse tiles cover every rank.
+__host__ __device__ __forceinline__ bool owns_coarse(int cx, int cy, uint32_t rank, uint32_t world) {
+    return world <= 1 || (uint32_t)(cx + cy) % world == rank;
 }
 
 __device__ __forceinline__ void mat4_mul_dev(const float *a, const float *b, float *o) {
@@ -321,43 +361,71 @@ k_project(const uint4 *__restrict__ cc, const void *__restrict__ cov, const void
 constexpr int kCoarseW = 8, kCoarseH = 4, kCoarseShiftX = 3, kCoarseShiftY = 2;
 constexpr int kFinePerCoarse = kCoarseW * kCoarseH;   // 32 = bits of the mask
 
-__device__ __forceinline__ uint32_t coarse_instances(ushort4 r) {
+// Ownership as a bitmask over the diagonal index cx + cy (< 128 for frames up to 8K): bit set = this rank's tile.  Avoids integer
+// division by a run-time world size in the per-splat binning kernels.
+struct OwnMask { unsigned long long lo, hi; };
+__host__ __device__ __forceinline__ bool own_diag(const OwnMask &m, int diag) {
+    return ((diag < 64 ? m.lo >> diag : m.hi >> (diag - 64)) & 1ull) != 0ull;
+}
+static inline OwnMask make_own_mask(uint32_t rank, uint32_t world) {
+    OwnMask m{~0ull, ~0ull};
+    if (world > 1) {
+        m.lo = m.hi = 0;
+        for (int d = 0; d < 128; ++d)
+            if ((uint32_t)d % world == rank) { if (d < 64) m.lo |= 1ull << d; else m.hi |= 1ull << (d - 64); }
+    }
+    return m;
+}
+
+__device__ __forceinline__ uint32_t coarse_instances(ushort4 r, const OwnMask &own, bool sharded) {
     if (r.z < r.x || r.w < r.y) return 0;
-    return (uint32_t)((r.z >> kCoarseShiftX) - (r.x >> kCoarseShiftX) + 1) * (uint32_t)((r.w >> kCoarseShiftY) - (r.y >> kCoarseShiftY) + 1);
+    const int cx0 = r.x >> kCoarseShiftX, cx1 = r.z >> kCoarseShiftX, cy0 = r.y >> kCoarseShiftY, cy1 = r.w >> kCoarseShiftY;
+    if (!sharded) return (uint32_t)(cx1 - cx0 + 1) * (uint32_t)(cy1 - cy0 + 1);
+    if (cx0 == cx1 && cy0 == cy1) return own_diag(own, cx0 + cy0) ? 1u : 0u;
+    uint32_t n = 0;
+    for (int cy = cy0; cy <= cy1; ++cy)
+        for (int cx = cx0; cx <= cx1; ++cx) n += own_diag(own, cx + cy) ? 1u : 0u;
+    return n;
 }
 
 constexpr int kBinThreads = 256;
 constexpr int kBinItems = 8;
 constexpr int kBinTile = kBinThreads * kBinItems;   // draw ranks per CTA
 
-// pass 1: instances per CTA-chunk of draw ranks (rank p = 0 is the NEAREST splat = last in the reference's draw order)
+// pass 1: instances per warp (256 consecutive draw ranks) and per CTA chunk (rank p = 0 is the NEAREST splat = last in the
+// reference's draw order).  Warp-striped like pass 2: warp w of a CTA owns ranks [chunk + 256 w, +256), item k of lane l = +32k + l.
 __global__ void __launch_bounds__(kBinThreads)
 k_tile_count(const uint32_t *__restrict__ order, uint32_t render_count, const ushort4 *__restrict__ rects,
-             uint32_t *__restrict__ block_sums, RasterControl *rctl) {
-    __shared__ uint32_t s_scan[40];
-    const uint32_t base = blockIdx.x * kBinTile;
+             uint32_t *__restrict__ block_sums, uint32_t *__restrict__ warp_sums, RasterControl *rctl, OwnMask own, int sharded) {
+    __shared__ uint32_t s_w[kBinThreads / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t run = blockIdx.x * kBinTile + (uint32_t)warp * (32 * kBinItems) + lane;
     uint32_t mine = 0;
 #pragma unroll
     for (int k = 0; k < kBinItems; ++k) {
-        const uint32_t p = base + (uint32_t)k * kBinThreads + threadIdx.x;
-        if (p < render_count) mine += coarse_instances(rects[ld_nc_u32(order + (render_count - 1u - p))]);
+        const uint32_t p = run + (uint32_t)k * 32;
+        if (p < render_count) mine += coarse_instances(rects[ld_nc_u32(order + (render_count - 1u - p))], own, sharded != 0);
     }
-    uint32_t total;
-    (void)block_exclusive_scan<kBinThreads>(mine, s_scan, total);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+    if (lane == 0) { s_w[warp] = mine; warp_sums[blockIdx.x * (kBinThreads / 32) + warp] = mine; }
+    __syncthreads();
     if (threadIdx.x == 0) {
+        uint32_t total = 0;
+#pragma unroll
+        for (int w = 0; w < kBinThreads / 32; ++w) total += s_w[w];
         block_sums[blockIdx.x] = total;
         atomicAdd(&rctl->total_instances, (unsigned long long)total);
     }
 }
 
-// pass 2: write (coarse tile id, {fine mask, splat id}) for every instance, in draw order.  Warp-striped: warp w owns 256
-// consecutive draw ranks, item k of lane l is rank run + 32k + l, so loads are coalesced and (warp, k, lane) order = draw order.
+// pass 2: write (coarse tile id, {fine mask, splat id}) for every instance, in draw order.  One item at a time (rolled loop, no
+// per-thread arrays): the warp's base offset comes from pass 1's sums, the offsets inside an item from a warp scan.
 __global__ void __launch_bounds__(kBinThreads)
 k_tile_emit(const uint32_t *__restrict__ order, uint32_t render_count, const ushort4 *__restrict__ rects,
-            const uint32_t *__restrict__ block_sums, int coarse_x, uint16_t *__restrict__ keys,
-            unsigned long long *__restrict__ vals, unsigned long long capacity, RasterControl *rctl) {
+            const uint32_t *__restrict__ block_sums, const uint32_t *__restrict__ warp_sums, int coarse_x, uint16_t *__restrict__ keys,
+            unsigned long long *__restrict__ vals, unsigned long long capacity, RasterControl *rctl, OwnMask own, int sharded) {
     __shared__ unsigned long long s_prefix;
-    __shared__ uint32_t s_wsum[kBinThreads / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // instances of all earlier chunks
     unsigned long long before = 0;
@@ -367,64 +435,87 @@ k_tile_emit(const uint32_t *__restrict__ order, uint32_t render_count, const ush
     if (threadIdx.x == 0) s_prefix = 0;
     __syncthreads();
     if (lane == 0 && before) atomicAdd(&s_prefix, before);
-    const uint32_t run = blockIdx.x * kBinTile + (uint32_t)warp * (32 * kBinItems);
-    uint32_t sid[kBinItems], cnt[kBinItems], mine = 0;
-    ushort4 rr[kBinItems];
-#pragma unroll
-    for (int k = 0; k < kBinItems; ++k) {
-        const uint32_t p = run + (uint32_t)k * 32 + lane;
-        sid[k] = (p < render_count) ? ld_nc_u32(order + (render_count - 1u - p)) : 0xffffffffu;
-    }
-#pragma unroll
-    for (int k = 0; k < kBinItems; ++k) {
-        cnt[k] = 0; rr[k] = make_ushort4(1, 1, 0, 0);
-        if (sid[k] != 0xffffffffu) { rr[k] = rects[sid[k]]; cnt[k] = coarse_instances(rr[k]); }
-        mine += cnt[k];
-    }
-    uint32_t wtot = mine;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) wtot += __shfl_xor_sync(0xffffffffu, wtot, o);
-    if (lane == 0) s_wsum[warp] = wtot;
     __syncthreads();
     unsigned long long w0 = s_prefix;
-    for (int w = 0; w < warp; ++w) w0 += s_wsum[w];
+    for (int w = 0; w < warp; ++w) w0 += warp_sums[blockIdx.x * (kBinThreads / 32) + w];
+    const uint32_t run = blockIdx.x * kBinTile + (uint32_t)warp * (32 * kBinItems) + lane;
     bool overflow = false;
-#pragma unroll
+#pragma unroll 2
     for (int k = 0; k < kBinItems; ++k) {
-        const uint32_t inc = warp_inclusive_scan(cnt[k]);
-        unsigned long long w = w0 + (inc - cnt[k]);
-        w0 += __shfl_sync(0xffffffffu, inc, 31);
-        const ushort4 r = rr[k];
-        const int cx0 = r.x >> kCoarseShiftX, cx1 = r.z >> kCoarseShiftX, cy0 = r.y >> kCoarseShiftY, cy1 = r.w >> kCoarseShiftY;
-        if (__all_sync(0xffffffffu, cnt[k] <= 1u)) {
-            // common case (about 9 in 10 warps): every lane's splat sits inside one coarse tile -> no loops, no divergence
-            if (cnt[k]) {
-                const int fx0 = (int)r.x - cx0 * kCoarseW, fx1 = (int)r.z - cx0 * kCoarseW, fy0 = (int)r.y - cy0 * kCoarseH, fy1 = (int)r.w - cy0 * kCoarseH;
-                const uint32_t rowsel = (0x01010101u >> (8 * (kCoarseH - 1 - (fy1 - fy0)))) << (8 * fy0);
-                const uint32_t mask = (((1u << (fx1 - fx0 + 1)) - 1u) << fx0) * rowsel;
-                if (w < capacity) {
-                    keys[w] = (uint16_t)(cy0 * coarse_x + cx0);
-                    vals[w] = ((unsigned long long)mask << 32) | sid[k];
-                } else overflow = true;
-            }
-            continue;
+        const uint32_t p = run + (uint32_t)k * 32;
+        uint32_t sid = 0, cnt = 0;
+        ushort4 r = make_ushort4(1, 1, 0, 0);
+        if (p < render_count) {
+            sid = ld_nc_u32(order + (render_count - 1u - p));
+            r = rects[sid];
+            cnt = coarse_instances(r, own, sharded != 0);
         }
-        if (cnt[k] == 0) continue;
-#pragma unroll 1
-        for (int cy = cy0; cy <= cy1; ++cy) {
-            const int fy0 = max((int)r.y, cy * kCoarseH) - cy * kCoarseH, fy1 = min((int)r.w, cy * kCoarseH + kCoarseH - 1) - cy * kCoarseH;
-            // rows fy0..fy1 selected: one bit per byte, then multiplied by the 8-bit column pattern (no carries)
+        const uint32_t inc = warp_inclusive_scan(cnt);
+        unsigned long long w = w0 + (inc - cnt);
+        w0 += __shfl_sync(0xffffffffu, inc, 31);
+        const int cx0 = r.x >> kCoarseShiftX, cx1 = r.z >> kCoarseShiftX, cy0 = r.y >> kCoarseShiftY, cy1 = r.w >> kCoarseShiftY;
+        const bool single = (cx0 == cx1 && cy0 == cy1);
+        if (cnt && single) {   // the common case: the splat sits inside one coarse tile
+            const int fx0 = (int)r.x - cx0 * kCoarseW, fx1 = (int)r.z - cx0 * kCoarseW, fy0 = (int)r.y - cy0 * kCoarseH, fy1 = (int)r.w - cy0 * kCoarseH;
             const uint32_t rowsel = (0x01010101u >> (8 * (kCoarseH - 1 - (fy1 - fy0)))) << (8 * fy0);
+            const uint32_t mask = (((1u << (fx1 - fx0 + 1)) - 1u) << fx0) * rowsel;
+            if (w < capacity) {
+                keys[w] = (uint16_t)(cy0 * coarse_x + cx0);
+                vals[w] = ((unsigned long long)mask << 32) | sid;
+            } else overflow = true;
+        }
+        // splats spanning MANY coarse tiles (a few huge ones cover the whole screen): the WARP walks each one's rect together,
+        // 32 coarse tiles per step.  Instances of one splat land in different lists, so their mutual order is free.
+        if (cnt && !single && cnt <= 32u) {   // a handful of coarse tiles: each lane walks its own rect
 #pragma unroll 1
-            for (int cx = cx0; cx <= cx1; ++cx) {
-                const int fx0 = max((int)r.x, cx * kCoarseW) - cx * kCoarseW, fx1 = min((int)r.z, cx * kCoarseW + kCoarseW - 1) - cx * kCoarseW;
-                const uint32_t row = ((1u << (fx1 - fx0 + 1)) - 1u) << fx0;
-                const uint32_t mask = row * rowsel;
-                if (w < capacity) {
-                    keys[w] = (uint16_t)(cy * coarse_x + cx);
-                    vals[w] = ((unsigned long long)mask << 32) | sid[k];
-                } else overflow = true;
-                ++w;
+            for (int cy = cy0; cy <= cy1; ++cy) {
+                const int fy0 = max((int)r.y, cy * kCoarseH) - cy * kCoarseH, fy1 = min((int)r.w, cy * kCoarseH + kCoarseH - 1) - cy * kCoarseH;
+                const uint32_t rowsel = (0x01010101u >> (8 * (kCoarseH - 1 - (fy1 - fy0)))) << (8 * fy0);
+#pragma unroll 1
+                for (int cx = cx0; cx <= cx1; ++cx) {
+                    if (sharded && !own_diag(own, cx + cy)) continue;
+                    const int fx0 = max((int)r.x, cx * kCoarseW) - cx * kCoarseW, fx1 = min((int)r.z, cx * kCoarseW + kCoarseW - 1) - cx * kCoarseW;
+                    const uint32_t mask = (((1u << (fx1 - fx0 + 1)) - 1u) << fx0) * rowsel;
+                    if (w < capacity) {
+                        keys[w] = (uint16_t)(cy * coarse_x + cx);
+                        vals[w] = ((unsigned long long)mask << 32) | sid;
+                    } else overflow = true;
+                    ++w;
+                }
+            }
+        }
+        uint32_t multi = __ballot_sync(0xffffffffu, cnt > 32u);
+        while (multi) {
+            const int src = __ffs(multi) - 1;
+            multi &= multi - 1;
+            const uint32_t bsid = __shfl_sync(0xffffffffu, sid, src);
+            unsigned long long bw = __shfl_sync(0xffffffffu, w, src);
+            const int bx0 = __shfl_sync(0xffffffffu, (int)r.x, src), by0 = __shfl_sync(0xffffffffu, (int)r.y, src);
+            const int bx1 = __shfl_sync(0xffffffffu, (int)r.z, src), by1 = __shfl_sync(0xffffffffu, (int)r.w, src);
+            const int ccx0 = bx0 >> kCoarseShiftX, ccy0 = by0 >> kCoarseShiftY;
+            const int cw = (bx1 >> kCoarseShiftX) - ccx0 + 1, chh = (by1 >> kCoarseShiftY) - ccy0 + 1;
+            const int ntile = cw * chh;
+            for (int i0 = 0; i0 < ntile; i0 += 32) {
+                const int i = i0 + lane;
+                bool mineq = false;
+                int cx = 0, cy = 0;
+                if (i < ntile) {
+                    cy = ccy0 + i / cw; cx = ccx0 + i % cw;
+                    mineq = !sharded || own_diag(own, cx + cy);
+                }
+                const uint32_t bal = __ballot_sync(0xffffffffu, mineq);
+                if (mineq) {
+                    const unsigned long long at = bw + __popc(bal & lanemask_lt());
+                    const int fx0 = max(bx0, cx * kCoarseW) - cx * kCoarseW, fx1 = min(bx1, cx * kCoarseW + kCoarseW - 1) - cx * kCoarseW;
+                    const int fy0 = max(by0, cy * kCoarseH) - cy * kCoarseH, fy1 = min(by1, cy * kCoarseH + kCoarseH - 1) - cy * kCoarseH;
+                    const uint32_t rowsel = (0x01010101u >> (8 * (kCoarseH - 1 - (fy1 - fy0)))) << (8 * fy0);
+                    const uint32_t mask = (((1u << (fx1 - fx0 + 1)) - 1u) << fx0) * rowsel;
+                    if (at < capacity) {
+                        keys[at] = (uint16_t)(cy * coarse_x + cx);
+                        vals[at] = ((unsigned long long)mask << 32) | bsid;
+                    } else overflow = true;
+                }
+                bw += __popc(bal);
             }
         }
     }
@@ -436,6 +527,7 @@ __global__ void k_raster_init(RasterControl *rctl, SortControl *ctl, uint2 *rang
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     if (tid == 0) {
         rctl->total_instances = 0; rctl->overflow = 0; rctl->visible = 0; rctl->scan_ticket = 0;
+        rctl->frame_seq += 1;
         ctl->error = 0;
         for (int i = 0; i < 4; ++i) ctl->ticket[i] = 0;
     }
@@ -470,7 +562,7 @@ k_blend(const uint2 *__restrict__ ranges, const unsigned long long *__restrict__
     const int tx = (int)(coarse % (uint32_t)coarse_x) * kCoarseW + (int)(sub & (kCoarseW - 1));
     const int ty = (int)(coarse / (uint32_t)coarse_x) * kCoarseH + (int)(sub >> kCoarseShiftX);
     if (tx >= tiles_x || ty >= tiles_y) return;
-    if (world > 1 && (uint32_t)ty % world != rank) return;
+    if (!owns_coarse((int)(coarse % (uint32_t)coarse_x), (int)(coarse / (uint32_t)coarse_x), rank, world)) return;   // another GPU's tile
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int lx = lane & 15, ly0 = ((lane >> 4) + 2 * warp) * kBlendPix;     // column lx, rows ly0 .. ly0+3 of the tile
     const int x = tx * kTile + lx, y0 = ty * kTile + ly0;
@@ -569,9 +661,7 @@ k_blend(const uint2 *__restrict__ ranges, const unsigned long long *__restrict__
             const int y = y0 + k;
             if (y >= height) break;
             const float A = 1.0f - T[k]; // alpha accumulates as 1 - prod(1 - alpha_i)
-            int out_row;
-            if (world == 1) out_row = flip_y ? (height - 1 - y) : y;
-            else out_row = (ty / (int)world) * kTile + ly0 + k;   // compact strip layout; assembled (and flipped) by the caller after the gather
+            const int out_row = flip_y ? (height - 1 - y) : y;   // every rank writes its tiles into a full-size frame (others stay 0)
             const size_t at = (size_t)out_row * width + x;
             if (FORMAT == GS_FRAME_RGBA32F) {
                 reinterpret_cast<float4 *>(frame)[at] = make_float4(Cr[k], Cg[k], Cb[k], A);
@@ -582,6 +672,7 @@ k_blend(const uint2 *__restrict__ ranges, const unsigned long long *__restrict__
             }
         }
     }
+    if (world > 1) __threadfence_system();   // the frame may live in a peer GPU's memory (fused tile gather): publish before the signal
 }
 
 // records -> the ABI's gs_projected_splat (basis vectors recovered from g = B/|B|^2)
@@ -627,6 +718,7 @@ struct RasterState {
     RBuf<SplatRecord> records;
     RBuf<ushort4> rects;
     RBuf<uint32_t> block_sums; // coarse instances per chunk of draw ranks
+    RBuf<uint32_t> warp_sums;  // ... and per warp (256 draw ranks) inside the chunk
     RBuf<uint16_t> ikeys[2];   // instance keys ping/pong (coarse tile ids)
     RBuf<unsigned long long> ivals[2];   // instance values ping/pong: {fine-tile mask, splat id}
     RBuf<unsigned long long> list;       // final per-coarse-tile lists
@@ -638,6 +730,11 @@ struct RasterState {
     RBuf<ProjParams> projp;     // per-frame projection parameters (device copy read by k_project)
     RBuf<unsigned char> frame;
     RBuf<gs_projected_splat> exported;
+    // fused tile gather over NVLink peer memory (world_size > 1)
+    RBuf<PeerSync> peer_sync_local;      // rank 0 owns the block
+    PeerSync *peer_sync = nullptr;       // rank 0: local block; others: rank 0's block mapped through CUDA IPC
+    void *peer_frame = nullptr;          // others: rank 0's frame buffer mapped through CUDA IPC
+    bool peer_root = false, peer_attached = false;
     unsigned long long instance_capacity = 0;
     uint32_t hist_stride = 0;
     int sm_count = 148;
@@ -666,6 +763,7 @@ static int raster_init(RasterState &rs, const gs_config &c, int sm_count) {
         RCU(rs.records.ensure(n));
         RCU(rs.rects.ensure(n));
         RCU(rs.block_sums.ensure((n + kBinTile - 1) / kBinTile + 1));
+        RCU(rs.warp_sums.ensure(((n + kBinTile - 1) / kBinTile + 1) * (kBinThreads / 32)));
         const char *f = getenv("GS_INSTANCE_FACTOR");
         const double factor = f ? atof(f) : 4.0;
         const size_t tiles = (size_t)((c.max_width + kTile - 1) / kTile) * ((c.max_height + kTile - 1) / kTile);
@@ -682,9 +780,9 @@ static int raster_init(RasterState &rs, const gs_config &c, int sm_count) {
 
 static void raster_release(RasterState &rs) {
     rs.cc.release(); rs.cov.release(); rs.sh.release(); rs.scene_idx.release(); rs.records.release(); rs.rects.release();
-    rs.block_sums.release(); rs.ikeys[0].release(); rs.ikeys[1].release(); rs.ivals[0].release(); rs.ivals[1].release();
+    rs.block_sums.release(); rs.warp_sums.release(); rs.ikeys[0].release(); rs.ikeys[1].release(); rs.ivals[0].release(); rs.ivals[1].release();
     rs.list.release(); rs.ranges.release(); rs.rctl.release(); rs.sctl.release(); rs.lookback.release();
-    rs.dyn.release(); rs.projp.release(); rs.frame.release(); rs.exported.release();
+    rs.dyn.release(); rs.projp.release(); rs.frame.release(); rs.peer_sync_local.release(); rs.exported.release();
 }
 
 static int raster_upload(RasterState &rs, const gs_config &c, const gs_splat_data &d, cudaStream_t st) {
@@ -773,8 +871,7 @@ static int raster_render(RasterState &rs, const gs_config &c, const gs_uniforms 
     if (p.render_count > rs.uploaded) { snprintf(raster_err(), 512, "render_count %u > uploaded splats %u", p.render_count, rs.uploaded); return GS_ERR_CAPACITY; }
     const int tiles_x = (p.width + kTile - 1) / kTile, tiles_y = (p.height + kTile - 1) / kTile;
     const uint32_t world = c.world_size, rank = c.rank;
-    const int local_rows = owned_rows(0, tiles_y - 1, rank, world);
-    const uint32_t local_tiles = (uint32_t)local_rows * (uint32_t)tiles_x;
+    const uint32_t local_tiles = (uint32_t)tiles_x * (uint32_t)tiles_y;
     uint32_t launches = 0;
 
     if (upload_params) { int prc = raster_upload_params(rs, c, u, p, st); if (prc) return prc; }
@@ -797,11 +894,11 @@ static int raster_render(RasterState &rs, const gs_config &c, const gs_uniforms 
     if (!(phases & 2)) { tm.kernel_launches = launches; return GS_OK; }
     if (p.render_count && local_tiles) {
         const uint32_t chunks = (p.render_count + kBinTile - 1) / kBinTile;
-        k_tile_count<<<chunks, kBinThreads, 0, st>>>(d_order, p.render_count, rs.rects.p, rs.block_sums.p, rs.rctl.p);
+        k_tile_count<<<chunks, kBinThreads, 0, st>>>(d_order, p.render_count, rs.rects.p, rs.block_sums.p, rs.warp_sums.p, rs.rctl.p, make_own_mask(rank, world), world > 1 ? 1 : 0);
         ++launches;
         prof.mark("k_tile_count", st);
-        k_tile_emit<<<chunks, kBinThreads, 0, st>>>(d_order, p.render_count, rs.rects.p, rs.block_sums.p, coarse_x, rs.ikeys[0].p, rs.ivals[0].p,
-                                                   rs.instance_capacity, rs.rctl.p);
+        k_tile_emit<<<chunks, kBinThreads, 0, st>>>(d_order, p.render_count, rs.rects.p, rs.block_sums.p, rs.warp_sums.p, coarse_x, rs.ikeys[0].p, rs.ivals[0].p,
+                                                   rs.instance_capacity, rs.rctl.p, make_own_mask(rank, world), world > 1 ? 1 : 0);
         ++launches;
         prof.mark("k_tile_emit", st);
         static const RadixNames names = {{"k_radix_hist[tile,0]", "k_radix_hist[tile,1]", "k_radix_hist[tile,2]", "k_radix_hist[tile,3]"},
@@ -815,16 +912,28 @@ static int raster_render(RasterState &rs, const gs_config &c, const gs_uniforms 
     }
     if (record_events) RCU(cudaEventRecord(ev_bin, st));
     if (local_tiles) {
+        const bool peer_mode = world > 1 && (rs.peer_root || rs.peer_attached);
+        // multi-GPU without the peer path: pixels of other ranks' tiles must be zero so that the frames can be summed (all-reduce)
+        if (world > 1 && !peer_mode) RCU(cudaMemsetAsync(rs.frame.p, 0, (size_t)p.width * p.height * (p.frame_format == GS_FRAME_RGBA8 ? 4 : 16), st));
+        void *target = rs.frame.p;
+        if (peer_mode && rs.peer_root) { k_peer_release<<<1, 1, 0, st>>>(rs.peer_sync, rs.rctl.p); ++launches; }
+        if (peer_mode && rs.peer_attached) {   // fused tile gather: blend straight into rank 0's frame over NVLink
+            k_peer_wait_release<<<1, 1, 0, st>>>(rs.peer_sync, rs.rctl.p);
+            ++launches;
+            target = rs.peer_frame;
+        }
         const uint32_t grid = ncoarse * kFinePerCoarse;
         if (p.frame_format == GS_FRAME_RGBA8)
-            k_blend<GS_FRAME_RGBA8><<<grid, kBlendThreads, 0, st>>>(rs.ranges.p, rs.list.p, rs.records.p, tiles_x, tiles_y, coarse_x, rank, world, (int)p.width, (int)p.height, p.flip_y, rs.frame.p);
+            k_blend<GS_FRAME_RGBA8><<<grid, kBlendThreads, 0, st>>>(rs.ranges.p, rs.list.p, rs.records.p, tiles_x, tiles_y, coarse_x, rank, world, (int)p.width, (int)p.height, p.flip_y, target);
         else
-            k_blend<GS_FRAME_RGBA32F><<<grid, kBlendThreads, 0, st>>>(rs.ranges.p, rs.list.p, rs.records.p, tiles_x, tiles_y, coarse_x, rank, world, (int)p.width, (int)p.height, p.flip_y, rs.frame.p);
+            k_blend<GS_FRAME_RGBA32F><<<grid, kBlendThreads, 0, st>>>(rs.ranges.p, rs.list.p, rs.records.p, tiles_x, tiles_y, coarse_x, rank, world, (int)p.width, (int)p.height, p.flip_y, target);
         ++launches;
         prof.mark("k_blend", st);
+        if (peer_mode && rs.peer_attached) { k_peer_signal<<<1, 1, 0, st>>>(rs.peer_sync); ++launches; }
+        if (peer_mode && rs.peer_root) { k_peer_wait_arrived<<<1, 1, 0, st>>>(rs.peer_sync, rs.rctl.p, world - 1); ++launches; prof.mark("k_peer_wait_arrived", st); }
     }
     rs.last_format = p.frame_format;
-    const size_t rows = world == 1 ? p.height : (size_t)local_rows * kTile;
+    const size_t rows = p.height;
     rs.last_frame_bytes = rows * p.width * (p.frame_format == GS_FRAME_RGBA8 ? 4 : 16);
     tm.kernel_launches = launches;
     return GS_OK;

@@ -239,11 +239,7 @@ class Engine:
         return p, keep
 
     def _frame_shape(self, width, height, fmt):
-        rows = height
-        if self.world_size > 1:
-            tiles_y = (height + 15) // 16
-            rows = len(range(self.rank, tiles_y, self.world_size)) * 16
-        return (rows, width, 4), (np.uint8 if fmt == N.GS_FRAME_RGBA8 else np.float32)
+        return (height, width, 4), (np.uint8 if fmt == N.GS_FRAME_RGBA8 else np.float32)
 
     def render(self, uniforms: Uniforms, width: int, height: int, render_count: int, sorted_indexes=None, *,
                frame_format: int = N.GS_FRAME_RGBA32F, flip_y: bool = False, out: np.ndarray | None = None, download: bool = True):
@@ -288,6 +284,16 @@ class Engine:
         """gs_frame with pre-marshalled arguments (host buffers: frame_out / sorted_out may be pinned arrays)."""
         sp, u, rp = prepared
         N.check(self._lib.gs_frame(self._h, C.byref(sp), C.byref(u), C.byref(rp), N.ptr(sorted_out), N.ptr(frame_out)), "gs_frame")
+
+    def peer_export(self) -> tuple[bytes, bytes]:
+        """Rank 0: CUDA-IPC handles (frame buffer, handshake block) for the fused tile gather."""
+        a, b = C.create_string_buffer(64), C.create_string_buffer(64)
+        N.check(self._lib.gs_peer_export(self._h, a, b), "gs_peer_export")
+        return a.raw, b.raw
+
+    def peer_attach(self, frame_handle: bytes, sync_handle: bytes) -> None:
+        """Ranks > 0: blend straight into rank 0's frame over NVLink from now on."""
+        N.check(self._lib.gs_peer_attach(self._h, C.create_string_buffer(frame_handle, 64), C.create_string_buffer(sync_handle, 64)), "gs_peer_attach")
 
     def set_graph_enabled(self, on: bool) -> None:
         N.check(self._lib.gs_set_graph_enabled(self._h, 1 if on else 0), "gs_set_graph_enabled")

@@ -77,8 +77,9 @@ typedef struct gs_config {
     uint8_t dynamic_mode;           /* Viewer option dynamicScene                SortWorker.js:120               */
     uint8_t reserved0[2];
     uint32_t max_width, max_height; /* largest framebuffer gs_render will be asked for (0,0: sort only)          */
-    /* multi-GPU sharding (one engine per process per GPU).  tile rows [tile_row_begin, tile_row_end) of the
-     * 16x16-pixel tile grid are rendered by this engine; 0,0 = all rows.                                        */
+    /* multi-GPU sharding (one engine per process per GPU): this engine rasterises the 128x64-pixel coarse tiles
+     * (cx, cy) with (cx + cy) % world_size == rank and leaves every other pixel of its frame zero, so the ranks'
+     * frames SUM to the picture (one NCCL all-reduce).  world_size 0 or 1 = everything.                         */
     uint32_t rank, world_size;
 } gs_config;
 
@@ -235,6 +236,14 @@ GS_API int gs_buffer_dev(gs_engine *e, int buffer_id, void **ptr_dev, size_t *by
 GS_API int gs_read_buffer(gs_engine *e, int buffer_id, void *out, size_t offset, size_t bytes); /* D2H copy, for tests / tools */
 GS_API int gs_stream(gs_engine *e, void **cuda_stream); /* cudaStream_t of the engine */
 GS_API int gs_synchronize(gs_engine *e);
+
+/* Fused tile gather (multi-GPU, one process per GPU).  Rank 0 exports CUDA-IPC handles of its frame buffer and of a small handshake
+ * block; every other rank attaches, after which its blend kernel stores finished pixels STRAIGHT INTO RANK 0'S FRAME over NVLink
+ * and rank 0's frame is complete when gs_frame / gs_synchronize returns -- no NCCL call, no staging copy.  All ranks must render
+ * the same sequence of frames.  (Without these calls the ranks' frames are zero outside their own tiles and can be summed.)        */
+#define GS_IPC_HANDLE_BYTES 64
+GS_API int gs_peer_export(gs_engine *e, void *frame_handle /*64 B out*/, void *sync_handle /*64 B out*/);      /* rank 0     */
+GS_API int gs_peer_attach(gs_engine *e, const void *frame_handle, const void *sync_handle);                    /* ranks > 0  */
 
 /* Page-locked host memory for callers: the counterpart of the SharedArrayBuffer views a shared-memory sort worker
  * hands to the main thread (SortWorker.js:180-191).  Buffers passed to gs_sort / gs_render from such memory are

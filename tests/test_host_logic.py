@@ -53,15 +53,6 @@ def test_packing_matches_reference_layout(oracle_mod):
     assert np.array_equal(integer_centers(raw.centers), oracle_mod.integer_centers(raw.centers))
 
 
-def test_owned_rows_partition():
-    """row-interleaved tile ownership used for multi-GPU: every tile row is owned exactly once."""
-    from gaussiansplats3d_b200.parallel import owned_tile_rows
-    for tiles_y in (1, 7, 68, 135):
-        for world in (1, 2, 4, 8):
-            rows = sorted(r for rank in range(world) for r in owned_tile_rows(tiles_y, rank, world))
-            assert rows == list(range(tiles_y))
-
-
 def test_raster_oracle_single_splat_analytic(oracle_mod):
     """One isotropic splat at the optical axis: the oracle's alpha profile must be exp(-r^2 / (2 sigma_px^2)) * a."""
     from gaussiansplats3d_b200.engine import Uniforms

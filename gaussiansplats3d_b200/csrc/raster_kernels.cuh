@@ -16,7 +16,7 @@ namespace gs {
 
 constexpr int kTile = 16;              // tile edge in pixels
 constexpr int kTileShift = 4;
-constexpr float kTransmittanceCutoff = 1.0f / 4096.0f; // stop compositing a pixel below this (stated deviation)
+constexpr float kTransmittanceCutoff = 1.0f / 512.0f;  // stop compositing below this: what is left adds < 0.5/255 (half an RGBA8 step); stated deviation
 
 struct __align__(16) SplatRecord {     // 48 bytes, read as 3 x 16 B
     float cx, cy;                      // quad centre in pixels, GL window coordinates (y up)
@@ -161,6 +161,8 @@ k_project(const uint4 *__restrict__ cc, const void *__restrict__ cov, const void
     }
     __syncthreads();
     const ProjParams &P = s_P;
+    __shared__ float4 s_out[kProjThreads / 32][96];
+    const uint32_t lane = threadIdx.x & 31;
     const uint32_t s = blockIdx.x * kProjThreads + threadIdx.x;
     uint32_t visible = 0;
     if (s < count) {
@@ -169,7 +171,29 @@ k_project(const uint4 *__restrict__ cc, const void *__restrict__ cov, const void
         o.ndc_z = 2.0f;
         o.hxhy = 0;
         ushort4 rect = make_ushort4(1, 1, 0, 0); // empty
+        // all of the splat's loads are issued up front (also for splats that turn out to be culled): the kernel is bound by load
+        // latency, so memory-level parallelism matters more than the ~30% of bytes that culled splats would not have needed
         const int4 c4 = ld_nc_v4(cc + s);
+        float V[6];
+        if (COVF16) {
+            const uint32_t *h32 = (const uint32_t *)cov + (size_t)s * 3;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const uint32_t w = ld_nc_u32(h32 + k);
+                const __half2 hh = *reinterpret_cast<const __half2 *>(&w);
+                V[2 * k] = __low2float(hh); V[2 * k + 1] = __high2float(hh);
+            }
+        } else {
+            const float2 *f2 = (const float2 *)cov + (size_t)s * 3;
+            const float2 a0 = __ldg(f2), a1 = __ldg(f2 + 1), a2 = __ldg(f2 + 2);
+            V[0] = a0.x; V[1] = a0.y; V[2] = a1.x; V[3] = a1.y; V[4] = a2.x; V[5] = a2.y;
+        }
+        int4 shq[3];
+        if (SHFMT == GS_SH_F16 && sh_data_degree >= 2 && P.sh_degree >= 1) {
+            const uint4 *h4 = (const uint4 *)((const __half *)sh + (size_t)s * 24);
+#pragma unroll
+            for (int q = 0; q < 3; ++q) shq[q] = ld_nc_v4(h4 + q);
+        }
         const float cx = __int_as_float(c4.y), cy = __int_as_float(c4.z), cz = __int_as_float(c4.w);
         uint32_t scene = 0;
         if (P.scene_count > 1 && scene_idx) scene = scene_idx[s] & (GS_MAX_SCENES_DEV - 1);
@@ -201,10 +225,9 @@ k_project(const uint4 *__restrict__ cc, const void *__restrict__ cov, const void
                 if (SHFMT == GS_SH_F16) {
                     const __half *h = (const __half *)sh + (size_t)s * ncomp;
                     if (ncomp == 24) {
-                        const uint4 *h4 = (const uint4 *)h;
 #pragma unroll
                         for (int q = 0; q < 3; ++q) {
-                            const int4 v = ld_nc_v4(h4 + q);
+                            const int4 v = shq[q];
                             const uint32_t w[4] = {(uint32_t)v.x, (uint32_t)v.y, (uint32_t)v.z, (uint32_t)v.w};
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
@@ -252,16 +275,6 @@ k_project(const uint4 *__restrict__ cc, const void *__restrict__ cov, const void
                 for (int ch = 0; ch < 3; ++ch) col[ch] = __saturatef(col[ch]);
             }
 
-            float V[6];
-            if (COVF16) {
-                const __half *h = (const __half *)cov + (size_t)s * 6;
-#pragma unroll
-                for (int k = 0; k < 6; ++k) V[k] = __half2float(h[k]);
-            } else {
-                const float2 *f2 = (const float2 *)cov + (size_t)s * 3;
-                const float2 a0 = f2[0], a1 = f2[1], a2 = f2[2];
-                V[0] = a0.x; V[1] = a0.y; V[2] = a1.x; V[3] = a1.y; V[4] = a2.x; V[5] = a2.y;
-            }
             float j00, j02, j11, j12;
             if (P.orthographic == 1) { j00 = P.ortho_zoom; j11 = P.ortho_zoom; j02 = 0.f; j12 = 0.f; }
             else {
@@ -342,11 +355,26 @@ k_project(const uint4 *__restrict__ cc, const void *__restrict__ cov, const void
                 }
             }
         }
-        float4 *dst = reinterpret_cast<float4 *>(rec + s);
-        dst[0] = make_float4(o.cx, o.cy, o.g1x, o.g1y);
-        dst[1] = make_float4(o.g2x, o.g2y, __uint_as_float(o.hxhy), o.a);
-        dst[2] = make_float4(o.r, o.g, o.b, o.ndc_z);
+        // stage the 48-byte record so that the warp stores its 1536 contiguous bytes with three fully coalesced 16-byte stores
+        float4 *stage = s_out[threadIdx.x >> 5];
+        stage[lane * 3 + 0] = make_float4(o.cx, o.cy, o.g1x, o.g1y);
+        stage[lane * 3 + 1] = make_float4(o.g2x, o.g2y, __uint_as_float(o.hxhy), o.a);
+        stage[lane * 3 + 2] = make_float4(o.r, o.g, o.b, o.ndc_z);
         rects[s] = rect;
+    }
+    __syncwarp();
+    {
+        const uint32_t warp_first = blockIdx.x * kProjThreads + (threadIdx.x & ~31u);
+        if (warp_first < count) {
+            const uint32_t nrec = min(32u, count - warp_first);
+            float4 *gdst = reinterpret_cast<float4 *>(rec + warp_first);
+            const float4 *stage = s_out[threadIdx.x >> 5];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const uint32_t idx = (uint32_t)k * 32 + lane;
+                if (idx < nrec * 3) gdst[idx] = stage[idx];
+            }
+        }
     }
     const uint32_t nvis = __popc(__ballot_sync(0xffffffffu, visible));
     if ((threadIdx.x & 31) == 0 && nvis) atomicAdd(&rctl->visible, nvis);

@@ -271,7 +271,8 @@ def run_ours(args):
     e.set_profiling(True)
     acc: dict[str, list[float]] = {}
     for i in range(K):
-        e.flush_l2()
+        for _ in range(10):          # ~0.3 ms of queued GPU work: the host enqueues the whole frame (launches + event records) meanwhile,
+            e.flush_l2()             # so the intervals between events are kernel time, not host launch latency; the last one flushes L2
         step_async()
         e.synchronize()
         for name, ms in e.kernel_timings():

@@ -109,6 +109,8 @@ struct gs_engine {
     DevBuf<DepthParams> depthp;      // per-frame depth parameters (device copy read by k_depth)
     DevBuf<uint32_t> lookback;       // radix tile histograms / offsets [pass][digit][tile]
     DevBuf<uint32_t> freq;           // scratch reproduction for gs_sort_indexes
+    DevBuf<uint32_t> sub_idx;        // sharded frames: this rank's subset of the sort input (index, distance)
+    DevBuf<int32_t> sub_dist;
     uint32_t uploaded_splats = 0;    // 'uploadedSplatCount' SortWorker.js:97
     uint32_t last_render_count = 0;
     bool have_sorted = false;
@@ -130,6 +132,7 @@ struct gs_engine {
     unsigned long long graph_key[8] = {0};
     bool graph_enabled = true;
     bool last_frame_was_graph = false;
+    bool no_subset = false;          // gs_frame with sorted_out on a sharded engine needs the full order: replicated sort
     uint32_t graph_launches = 0;
     bool have_prof_begin = false;    // true while a frame's sort already opened the timeline
     bool pending_async = false;
@@ -199,7 +202,7 @@ extern "C" void gs_destroy(gs_engine *e) {
     if (e->stream) cudaStreamSynchronize(e->stream);
     e->centers.release(); e->scene_idx.release(); e->indexes.release(); e->precomputed.release(); e->dist.release();
     e->keys[0].release(); e->keys[1].release(); e->vals[0].release(); e->vals[1].release(); e->sorted.release();
-    e->transforms.release(); e->ctl.release(); e->depthp.release(); e->lookback.release(); e->freq.release();
+    e->transforms.release(); e->ctl.release(); e->depthp.release(); e->lookback.release(); e->freq.release(); e->sub_idx.release(); e->sub_dist.release();
     e->h_indexes.release(); e->h_sorted.release(); e->h_ctl.release(); e->h_frame.release(); e->flush.release(); e->prof.release();
     if (e->rs.peer_attached) { if (e->rs.peer_frame) cudaIpcCloseMemHandle(e->rs.peer_frame); if (e->rs.peer_sync) cudaIpcCloseMemHandle(e->rs.peer_sync); }
     raster_release(e->rs);
@@ -234,7 +237,7 @@ static void launch_depth(bool identity, int blocks, cudaStream_t st, const uint3
 
 // The sort proper, everything already on the device.  d_indexes == nullptr: identity.
 static int sort_on_device(gs_engine *e, const uint32_t *d_indexes, const float *mvp, uint32_t sort_count, uint32_t render_count,
-                          bool use_pre, bool write_buckets, bool capturing = false) {
+                          bool use_pre, bool write_buckets, bool capturing = false, bool subset = false, cudaEvent_t wait_for_rects = nullptr) {
     if (sort_count > render_count) return fail(GS_ERR_BAD_ARG, "sortCount %u > renderCount %u", sort_count, render_count);
     if (render_count > e->cfg.max_splat_count) return fail(GS_ERR_CAPACITY, "renderCount %u > max_splat_count %u", render_count, e->cfg.max_splat_count);
     cudaStream_t st = e->stream;
@@ -245,7 +248,7 @@ static int sort_on_device(gs_engine *e, const uint32_t *d_indexes, const float *
     int rc = e->lookback.ensure(radix_tile_hist_words(std::max(n, 1u), pl.npasses, &stride));
     if (rc) return rc;
     if (!capturing) CU(cudaEventRecord(e->ev[EV_SORT0], st));
-    e->prof.begin(st);
+    if (!e->have_prof_begin) e->prof.begin(st);
     k_sort_init<<<1, 256, 0, st>>>(e->ctl.p);
     ++launches;
     e->prof.mark("k_sort_init", st);
@@ -279,24 +282,34 @@ static int sort_on_device(gs_engine *e, const uint32_t *d_indexes, const float *
         const uint32_t tiles = (n + kRadixTile - 1) / kRadixTile;
         const uint32_t R = e->cfg.distance_map_range;
         const uint32_t *vsrc = identity ? nullptr : d_indexes + s0;
-        const int vmode = identity ? kValIotaReversed : kValArrayReversed;
+        int vmode = identity ? kValIotaReversed : kValArrayReversed;
+        int32_t *dist_sorted = e->dist.p + s0;
+        const unsigned long long *n_dev = nullptr;
+        if (subset) {   // this rank sorts only the splats that reach its tiles; bucketed with the GLOBAL min/max found by k_depth above
+            if (wait_for_rects) CU(cudaStreamWaitEvent(st, wait_for_rects, 0));
+            int rcs = raster_subset(e->rs, e->cfg, d_indexes, render_count, e->dist.p, e->sub_idx.p, e->sub_dist.p, st, e->prof, launches);
+            if (rcs) return rcs;
+            vsrc = e->sub_idx.p; vmode = kValArrayReversed;
+            dist_sorted = e->sub_dist.p;
+            n_dev = &e->rs.rctl.p->subset_count;
+        }
         static const RadixNames names = {{"k_radix_hist[depth,0]", "k_radix_hist[depth,1]", "k_radix_hist[depth,2]", "k_radix_hist[depth,3]"},
                                          {"k_radix_scan[depth,0]", "k_radix_scan[depth,1]", "k_radix_scan[depth,2]", "k_radix_scan[depth,3]"},
                                          {"k_radix_scatter[depth,0]", "k_radix_scatter[depth,1]", "k_radix_scatter[depth,2]", "k_radix_scatter[depth,3]"}};
         if (e->key_bits <= 16) {
-            k_bucket<uint16_t><<<tiles, kRadixThreads, 0, st>>>(e->dist.p, (uint16_t *)e->keys[0].p, s0, render_count, R, pl, write_buckets ? 1 : 0, e->ctl.p, e->lookback.p, stride);
+            k_bucket<uint16_t><<<tiles, kRadixThreads, 0, st>>>(dist_sorted, (uint16_t *)e->keys[0].p, n, n_dev, R, pl, write_buckets ? 1 : 0, e->ctl.p, e->lookback.p, stride);
             ++launches;
             e->prof.mark("k_bucket", st);
             if (!capturing) CU(cudaEventRecord(e->ev[EV_BUCKET], st));
             radix_sort_pairs<uint16_t, uint32_t>((uint16_t *)e->keys[0].p, (uint16_t *)e->keys[1].p, vsrc, render_count - 1u, vmode, e->vals[0].p, e->vals[1].p,
-                                       e->sorted.p + s0, n, nullptr, 0ull, pl, e->ctl.p, e->lookback.p, stride, true, nullptr, st, launches, &e->prof, names);
+                                       e->sorted.p + s0, n, n_dev, (unsigned long long)n, pl, e->ctl.p, e->lookback.p, stride, true, nullptr, st, launches, &e->prof, names);
         } else {
-            k_bucket<uint32_t><<<tiles, kRadixThreads, 0, st>>>(e->dist.p, e->keys[0].p, s0, render_count, R, pl, write_buckets ? 1 : 0, e->ctl.p, e->lookback.p, stride);
+            k_bucket<uint32_t><<<tiles, kRadixThreads, 0, st>>>(dist_sorted, e->keys[0].p, n, n_dev, R, pl, write_buckets ? 1 : 0, e->ctl.p, e->lookback.p, stride);
             ++launches;
             e->prof.mark("k_bucket", st);
             if (!capturing) CU(cudaEventRecord(e->ev[EV_BUCKET], st));
             radix_sort_pairs<uint32_t, uint32_t>(e->keys[0].p, e->keys[1].p, vsrc, render_count - 1u, vmode, e->vals[0].p, e->vals[1].p, e->sorted.p + s0, n,
-                                       nullptr, 0ull, pl, e->ctl.p, e->lookback.p, stride, true, nullptr, st, launches, &e->prof, names);
+                                       n_dev, (unsigned long long)n, pl, e->ctl.p, e->lookback.p, stride, true, nullptr, st, launches, &e->prof, names);
         }
     } else if (!capturing) {
         CU(cudaEventRecord(e->ev[EV_DEPTH], st));
@@ -500,13 +513,14 @@ extern "C" int gs_upload_splat_data(gs_engine *e, const gs_splat_data *d) {
     return GS_OK;
 }
 
-static int render_on_device(gs_engine *e, const gs_uniforms *u, const gs_render_params *p, const uint32_t *d_order, bool capturing = false, int phases = 3) {
+static int render_on_device(gs_engine *e, const gs_uniforms *u, const gs_render_params *p, const uint32_t *d_order, bool capturing = false, int phases = 3,
+                            const unsigned long long *order_count_dev = nullptr) {
     cudaStream_t st = e->stream;
-    if (!capturing) CU(cudaEventRecord(e->ev[EV_R0], st));
+    if (!capturing && (phases & 1)) CU(cudaEventRecord(e->ev[EV_R0], st));
     if (!e->have_prof_begin) e->prof.begin(st);
-    int rc = raster_render(e->rs, e->cfg, *u, *p, d_order, st, e->ev[EV_PROJECT], e->ev[EV_BIN], e->tm, e->prof, !capturing, !capturing, phases);
+    int rc = raster_render(e->rs, e->cfg, *u, *p, d_order, st, e->ev[EV_PROJECT], e->ev[EV_BIN], e->tm, e->prof, !capturing, !capturing, phases, order_count_dev);
     if (rc) return rc;
-    if (!capturing) CU(cudaEventRecord(e->ev[EV_R1], st));
+    if (!capturing && (phases & 2)) CU(cudaEventRecord(e->ev[EV_R1], st));
     CU(cudaGetLastError());
     return GS_OK;
 }
@@ -594,12 +608,21 @@ static int enqueue_frame(gs_engine *e, const gs_sort_params *s, const gs_uniform
     rp.render_count = std::min(rp.render_count, q.render_count);
     cudaStream_t st = e->stream;
     e->last_frame_was_graph = false;
+    // sharded frame: sort only this rank's subset (full sorts only; a partial sort keeps the replicated path)
+    // The subset path adds two compaction kernels (~35 us at 1M splats) and only shrinks kernels that are already at their latency
+    // floor there; it pays off from a few million splats (measured: 1.2M slower, 16M faster).  GS_SUBSET_MIN overrides the threshold.
+    const uint32_t subset_min = getenv("GS_SUBSET_MIN") ? (uint32_t)atoll(getenv("GS_SUBSET_MIN")) : 3000000u;
+    const bool subset = e->cfg.world_size > 1 && q.sort_count == q.render_count && q.render_count >= subset_min && q.render_count > 0 && !e->no_subset;
+    if (subset) {
+        if ((rc = e->sub_idx.ensure(e->cfg.max_splat_count)) || (rc = e->sub_dist.ensure(e->cfg.max_splat_count))) return rc;
+    }
+    const unsigned long long *order_count = subset ? &e->rs.rctl.p->subset_count : nullptr;
     const bool use_graph = e->graph_enabled && !e->prof.on && q.sort_count <= q.render_count && q.render_count <= e->cfg.max_splat_count && e->rs.uploaded;
     if (use_graph) {
         const unsigned long long key[8] = {q.render_count, q.sort_count, ((unsigned long long)rp.width << 32) | rp.height,
                                            ((unsigned long long)rp.frame_format << 8) | (unsigned long long)(rp.flip_y ? 1 : 0) | ((unsigned long long)q.use_precomputed_distances << 4),
                                            (unsigned long long)(uintptr_t)d_idx, ((unsigned long long)e->rs.cov_format << 16) | ((unsigned long long)e->rs.sh_format << 8) | e->rs.sh_degree,
-                                           e->rs.uploaded, rp.render_count};
+                                           e->rs.uploaded, ((unsigned long long)rp.render_count << 1) | (subset ? 1ull : 0ull)};
         if ((rc = upload_frame_params(e, q.model_view_proj, *u, rp))) return rc;
         if (!e->graph_exec || memcmp(key, e->graph_key, sizeof(key)) != 0) {
             if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
@@ -621,10 +644,10 @@ static int enqueue_frame(gs_engine *e, const gs_sort_params *s, const gs_uniform
                 e->stream = keep;
             }
             CU(cudaEventRecord(e->ev_join, e->stream2));
-            rc = sort_on_device(e, d_idx, q.model_view_proj, q.sort_count, q.render_count, q.use_precomputed_distances != 0, false, true);
+            rc = sort_on_device(e, d_idx, q.model_view_proj, q.sort_count, q.render_count, q.use_precomputed_distances != 0, false, true, subset, e->ev_join);
             const uint32_t sort_launches = e->tm.kernel_launches;
             CU(cudaStreamWaitEvent(st, e->ev_join, 0));
-            if (!rc2) rc2 = rc ? rc : render_on_device(e, u, &rp, e->sorted.p, true, 2);
+            if (!rc2) rc2 = rc ? rc : render_on_device(e, u, &rp, e->sorted.p, true, 2, order_count);
             e->graph_launches = e->tm.kernel_launches + sort_launches + proj_launches;
             cudaGraph_t g = nullptr;
             cudaError_t ce = cudaStreamEndCapture(st, &g);
@@ -640,8 +663,22 @@ static int enqueue_frame(gs_engine *e, const gs_sort_params *s, const gs_uniform
         CU(cudaEventRecord(e->ev[EV_R1], st));
         e->tm.kernel_launches = e->graph_launches;
         e->last_render_count = q.render_count;
-        e->have_sorted = true;
+        e->have_sorted = !subset;   // a subset order is not a draw order for gs_render
         e->last_frame_was_graph = true;
+        return GS_OK;
+    }
+    if (subset) {   // one stream: projection first (its rects select the subset), then depth + subset sort, then binning + blend
+        e->prof.begin(st);
+        e->have_prof_begin = true;
+        if ((rc = render_on_device(e, u, &rp, e->sorted.p, false, 1))) { e->have_prof_begin = false; return rc; }
+        const uint32_t proj_launches = e->tm.kernel_launches;
+        if ((rc = sort_on_device(e, d_idx, q.model_view_proj, q.sort_count, q.render_count, q.use_precomputed_distances != 0, false, false, true, nullptr))) { e->have_prof_begin = false; return rc; }
+        const uint32_t sort_launches = e->tm.kernel_launches;
+        rc = render_on_device(e, u, &rp, e->sorted.p, false, 2, order_count);
+        e->have_prof_begin = false;
+        if (rc) return rc;
+        e->tm.kernel_launches += sort_launches + proj_launches;
+        e->have_sorted = false;
         return GS_OK;
     }
     if ((rc = sort_on_device(e, d_idx, q.model_view_proj, q.sort_count, q.render_count, q.use_precomputed_distances != 0, false))) return rc;
@@ -659,7 +696,10 @@ extern "C" int gs_frame(gs_engine *e, const gs_sort_params *s, const gs_uniforms
     if (rc) return rc;
     if (!s || !u || !p) return fail(GS_ERR_BAD_ARG, "gs_frame: null argument");
     gs_sort_params q; gs_render_params rp;
-    if ((rc = enqueue_frame(e, s, u, p, q, rp))) return rc;
+    e->no_subset = (sorted_out != nullptr);
+    rc = enqueue_frame(e, s, u, p, q, rp);
+    e->no_subset = false;
+    if (rc) return rc;
     if (sorted_out && q.render_count) CU(cudaMemcpyAsync(sorted_out, e->sorted.p, (size_t)q.render_count * 4, cudaMemcpyDeviceToHost, e->stream));
     int rc2 = finish_render(e, &rp, frame_out);
     rc = finish_sort(e, nullptr);

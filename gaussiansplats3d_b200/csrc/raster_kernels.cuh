@@ -36,6 +36,7 @@ struct RasterControl {
     uint32_t frame_seq;      // frames rendered so far (never reset): the peer-gather handshake counts in frames
     uint32_t peer_timeout;   // a peer handshake gave up waiting
     uint32_t pad[1];
+    unsigned long long subset_count;   // sharded frames: splats whose rect touches one of this rank's coarse tiles
 };
 
 // Block in rank 0's memory that the other ranks map through CUDA IPC: the fused tile gather's handshake.
@@ -395,6 +396,20 @@ struct OwnMask { unsigned long long lo, hi; };
 __host__ __device__ __forceinline__ bool own_diag(const OwnMask &m, int diag) {
     return ((diag < 64 ? m.lo >> diag : m.hi >> (diag - 64)) & 1ull) != 0ull;
 }
+__device__ __forceinline__ uint32_t own_count_range(const OwnMask &m, int d0, int d1) {   // 0 <= d0 <= d1 < 128
+    uint32_t n = 0;
+    if (d0 < 64) {
+        const int hi = min(d1, 63);
+        const unsigned long long w = (m.lo >> d0) & (hi - d0 == 63 ? ~0ull : ((1ull << (hi - d0 + 1)) - 1ull));
+        n += __popcll(w);
+    }
+    if (d1 >= 64) {
+        const int lo = max(d0, 64) - 64, hi = d1 - 64;
+        const unsigned long long w = (m.hi >> lo) & (hi - lo == 63 ? ~0ull : ((1ull << (hi - lo + 1)) - 1ull));
+        n += __popcll(w);
+    }
+    return n;
+}
 static inline OwnMask make_own_mask(uint32_t rank, uint32_t world) {
     OwnMask m{~0ull, ~0ull};
     if (world > 1) {
@@ -410,21 +425,22 @@ __device__ __forceinline__ uint32_t coarse_instances(ushort4 r, const OwnMask &o
     const int cx0 = r.x >> kCoarseShiftX, cx1 = r.z >> kCoarseShiftX, cy0 = r.y >> kCoarseShiftY, cy1 = r.w >> kCoarseShiftY;
     if (!sharded) return (uint32_t)(cx1 - cx0 + 1) * (uint32_t)(cy1 - cy0 + 1);
     if (cx0 == cx1 && cy0 == cy1) return own_diag(own, cx0 + cy0) ? 1u : 0u;
-    uint32_t n = 0;
-    for (int cy = cy0; cy <= cy1; ++cy)
-        for (int cx = cx0; cx <= cx1; ++cx) n += own_diag(own, cx + cy) ? 1u : 0u;
+    uint32_t n = 0;   // per coarse row: owned diagonals in [cx0 + cy, cx1 + cy] = population count of a window of the 128-bit mask
+    for (int cy = cy0; cy <= cy1; ++cy) n += own_count_range(own, cx0 + cy, cx1 + cy);
     return n;
 }
 
 constexpr int kBinThreads = 256;
-constexpr int kBinItems = 8;
+constexpr int kBinItems = 2;
 constexpr int kBinTile = kBinThreads * kBinItems;   // draw ranks per CTA
 
 // pass 1: instances per warp (256 consecutive draw ranks) and per CTA chunk (rank p = 0 is the NEAREST splat = last in the
 // reference's draw order).  Warp-striped like pass 2: warp w of a CTA owns ranks [chunk + 256 w, +256), item k of lane l = +32k + l.
 __global__ void __launch_bounds__(kBinThreads)
-k_tile_count(const uint32_t *__restrict__ order, uint32_t render_count, const ushort4 *__restrict__ rects,
-             uint32_t *__restrict__ block_sums, uint32_t *__restrict__ warp_sums, RasterControl *rctl, OwnMask own, int sharded) {
+k_tile_count(const uint32_t *__restrict__ order, uint32_t render_count_host, const unsigned long long *__restrict__ n_dev,
+             const ushort4 *__restrict__ rects, uint32_t *__restrict__ block_sums, uint32_t *__restrict__ warp_sums, RasterControl *rctl,
+             OwnMask own, int sharded) {
+    const uint32_t render_count = n_dev ? (uint32_t)*n_dev : render_count_host;
     __shared__ uint32_t s_w[kBinThreads / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t run = blockIdx.x * kBinTile + (uint32_t)warp * (32 * kBinItems) + lane;
@@ -450,9 +466,11 @@ k_tile_count(const uint32_t *__restrict__ order, uint32_t render_count, const us
 // pass 2: write (coarse tile id, {fine mask, splat id}) for every instance, in draw order.  One item at a time (rolled loop, no
 // per-thread arrays): the warp's base offset comes from pass 1's sums, the offsets inside an item from a warp scan.
 __global__ void __launch_bounds__(kBinThreads)
-k_tile_emit(const uint32_t *__restrict__ order, uint32_t render_count, const ushort4 *__restrict__ rects,
-            const uint32_t *__restrict__ block_sums, const uint32_t *__restrict__ warp_sums, int coarse_x, uint16_t *__restrict__ keys,
-            unsigned long long *__restrict__ vals, unsigned long long capacity, RasterControl *rctl, OwnMask own, int sharded) {
+k_tile_emit(const uint32_t *__restrict__ order, uint32_t render_count_host, const unsigned long long *__restrict__ n_dev,
+            const ushort4 *__restrict__ rects, const uint32_t *__restrict__ block_sums, const uint32_t *__restrict__ warp_sums, int coarse_x,
+            uint16_t *__restrict__ keys, unsigned long long *__restrict__ vals, unsigned long long capacity, RasterControl *rctl, OwnMask own,
+            int sharded) {
+    const uint32_t render_count = n_dev ? (uint32_t)*n_dev : render_count_host;
     __shared__ unsigned long long s_prefix;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // instances of all earlier chunks
@@ -494,7 +512,8 @@ k_tile_emit(const uint32_t *__restrict__ order, uint32_t render_count, const ush
         }
         // splats spanning MANY coarse tiles (a few huge ones cover the whole screen): the WARP walks each one's rect together,
         // 32 coarse tiles per step.  Instances of one splat land in different lists, so their mutual order is free.
-        if (cnt && !single && cnt <= 32u) {   // a handful of coarse tiles: each lane walks its own rect
+        const uint32_t area = (uint32_t)(cx1 - cx0 + 1) * (uint32_t)(cy1 - cy0 + 1);
+        if (cnt && !single && area <= 32u) {   // a handful of coarse tiles: each lane walks its own rect
 #pragma unroll 1
             for (int cy = cy0; cy <= cy1; ++cy) {
                 const int fy0 = max((int)r.y, cy * kCoarseH) - cy * kCoarseH, fy1 = min((int)r.w, cy * kCoarseH + kCoarseH - 1) - cy * kCoarseH;
@@ -512,7 +531,7 @@ k_tile_emit(const uint32_t *__restrict__ order, uint32_t render_count, const ush
                 }
             }
         }
-        uint32_t multi = __ballot_sync(0xffffffffu, cnt > 32u);
+        uint32_t multi = __ballot_sync(0xffffffffu, cnt != 0u && area > 32u);
         while (multi) {
             const int src = __ffs(multi) - 1;
             multi &= multi - 1;
@@ -550,11 +569,76 @@ k_tile_emit(const uint32_t *__restrict__ order, uint32_t render_count, const ush
     if (overflow) rctl->overflow = 1;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Sharded frames (world_size > 1): the depth sort of a rank covers only the splats whose screen rect touches one of ITS coarse tiles.
+// Any subset, bucketed with the GLOBAL min/max and kept in input order, sorts into exactly the global order restricted to that subset
+// (ties are broken by input position) -- SURVEY.md 8(e) -- so no keys or splats are exchanged between GPUs.
+// pass 1: survivors per warp / chunk of input positions;  pass 2: order-preserving compaction of (index, distance).
+__global__ void __launch_bounds__(kBinThreads)
+k_subset_count(const uint32_t *__restrict__ indexes, uint32_t count, const ushort4 *__restrict__ rects, OwnMask own,
+               uint32_t *__restrict__ block_sums, uint32_t *__restrict__ warp_sums, RasterControl *rctl) {
+    __shared__ uint32_t s_w[kBinThreads / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t run = blockIdx.x * kBinTile + (uint32_t)warp * (32 * kBinItems) + lane;
+    uint32_t mine = 0;
+#pragma unroll
+    for (int k = 0; k < kBinItems; ++k) {
+        const uint32_t i = run + (uint32_t)k * 32;
+        if (i < count) mine += coarse_instances(rects[indexes ? ld_nc_u32(indexes + i) : i], own, true) ? 1u : 0u;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+    if (lane == 0) { s_w[warp] = mine; warp_sums[blockIdx.x * (kBinThreads / 32) + warp] = mine; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t total = 0;
+#pragma unroll
+        for (int w = 0; w < kBinThreads / 32; ++w) total += s_w[w];
+        block_sums[blockIdx.x] = total;
+        atomicAdd(&rctl->subset_count, (unsigned long long)total);
+    }
+}
+__global__ void __launch_bounds__(kBinThreads)
+k_subset_emit(const uint32_t *__restrict__ indexes, uint32_t count, const ushort4 *__restrict__ rects, OwnMask own,
+              const uint32_t *__restrict__ block_sums, const uint32_t *__restrict__ warp_sums, const int32_t *__restrict__ dist,
+              uint32_t *__restrict__ sub_idx, int32_t *__restrict__ sub_dist) {
+    __shared__ uint32_t s_prefix;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t before = 0;
+    for (uint32_t b = threadIdx.x; b < blockIdx.x; b += kBinThreads) before += block_sums[b];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(0xffffffffu, before, o);
+    if (threadIdx.x == 0) s_prefix = 0;
+    __syncthreads();
+    if (lane == 0 && before) atomicAdd(&s_prefix, before);
+    __syncthreads();
+    uint32_t w0 = s_prefix;
+    for (int w = 0; w < warp; ++w) w0 += warp_sums[blockIdx.x * (kBinThreads / 32) + w];
+    const uint32_t run = blockIdx.x * kBinTile + (uint32_t)warp * (32 * kBinItems) + lane;
+#pragma unroll 2
+    for (int k = 0; k < kBinItems; ++k) {
+        const uint32_t i = run + (uint32_t)k * 32;
+        uint32_t g = 0;
+        bool keep = false;
+        if (i < count) {
+            g = indexes ? ld_nc_u32(indexes + i) : i;
+            keep = coarse_instances(rects[g], own, true) != 0u;
+        }
+        const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+        if (keep) {
+            const uint32_t at = w0 + __popc(bal & lanemask_lt());
+            sub_idx[at] = g;
+            sub_dist[at] = dist[i];
+        }
+        w0 += __popc(bal);
+    }
+}
+
 __global__ void k_raster_init(RasterControl *rctl, SortControl *ctl, uint2 *ranges, uint32_t ntiles) {
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     if (tid == 0) {
-        rctl->total_instances = 0; rctl->overflow = 0; rctl->visible = 0; rctl->scan_ticket = 0;
+        rctl->total_instances = 0; rctl->overflow = 0; rctl->visible = 0; rctl->scan_ticket = 0; rctl->subset_count = 0;
         rctl->frame_seq += 1;
         ctl->error = 0;
         for (int i = 0; i < 4; ++i) ctl->ticket[i] = 0;
@@ -891,7 +975,7 @@ static int raster_upload_params(RasterState &rs, const gs_config &c, const gs_un
 
 static int raster_render(RasterState &rs, const gs_config &c, const gs_uniforms &u, const gs_render_params &p, const uint32_t *d_order,
                          cudaStream_t st, cudaEvent_t ev_project, cudaEvent_t ev_bin, gs_timings &tm, Profiler &prof, bool upload_params, bool record_events,
-                         int phases = 3) {
+                         int phases = 3, const unsigned long long *order_count_dev = nullptr) {
     if (!rs.uploaded) { snprintf(raster_err(), 512, "gs_render before gs_upload_splat_data"); return GS_ERR_NOT_READY; }
     if (p.width == 0 || p.height == 0 || p.width > c.max_width || p.height > c.max_height) {
         snprintf(raster_err(), 512, "frame %ux%u outside the engine's %ux%u", p.width, p.height, c.max_width, c.max_height); return GS_ERR_BAD_ARG;
@@ -922,10 +1006,10 @@ static int raster_render(RasterState &rs, const gs_config &c, const gs_uniforms 
     if (!(phases & 2)) { tm.kernel_launches = launches; return GS_OK; }
     if (p.render_count && local_tiles) {
         const uint32_t chunks = (p.render_count + kBinTile - 1) / kBinTile;
-        k_tile_count<<<chunks, kBinThreads, 0, st>>>(d_order, p.render_count, rs.rects.p, rs.block_sums.p, rs.warp_sums.p, rs.rctl.p, make_own_mask(rank, world), world > 1 ? 1 : 0);
+        k_tile_count<<<chunks, kBinThreads, 0, st>>>(d_order, p.render_count, order_count_dev, rs.rects.p, rs.block_sums.p, rs.warp_sums.p, rs.rctl.p, make_own_mask(rank, world), world > 1 ? 1 : 0);
         ++launches;
         prof.mark("k_tile_count", st);
-        k_tile_emit<<<chunks, kBinThreads, 0, st>>>(d_order, p.render_count, rs.rects.p, rs.block_sums.p, rs.warp_sums.p, coarse_x, rs.ikeys[0].p, rs.ivals[0].p,
+        k_tile_emit<<<chunks, kBinThreads, 0, st>>>(d_order, p.render_count, order_count_dev, rs.rects.p, rs.block_sums.p, rs.warp_sums.p, coarse_x, rs.ikeys[0].p, rs.ivals[0].p,
                                                    rs.instance_capacity, rs.rctl.p, make_own_mask(rank, world), world > 1 ? 1 : 0);
         ++launches;
         prof.mark("k_tile_emit", st);
@@ -964,6 +1048,20 @@ static int raster_render(RasterState &rs, const gs_config &c, const gs_uniforms 
     const size_t rows = p.height;
     rs.last_frame_bytes = rows * p.width * (p.frame_format == GS_FRAME_RGBA8 ? 4 : 16);
     tm.kernel_launches = launches;
+    return GS_OK;
+}
+
+// order-preserving compaction of the sort input to this rank's splats (needs k_project's rects of THIS frame)
+static int raster_subset(RasterState &rs, const gs_config &c, const uint32_t *d_indexes, uint32_t count, const int32_t *dist, uint32_t *sub_idx,
+                         int32_t *sub_dist, cudaStream_t st, Profiler &prof, uint32_t &launches) {
+    const uint32_t chunks = (count + kBinTile - 1) / kBinTile;
+    const OwnMask own = make_own_mask(c.rank, c.world_size);
+    k_subset_count<<<chunks, kBinThreads, 0, st>>>(d_indexes, count, rs.rects.p, own, rs.block_sums.p, rs.warp_sums.p, rs.rctl.p);
+    ++launches;
+    prof.mark("k_subset_count", st);
+    k_subset_emit<<<chunks, kBinThreads, 0, st>>>(d_indexes, count, rs.rects.p, own, rs.block_sums.p, rs.warp_sums.p, dist, sub_idx, sub_dist);
+    ++launches;
+    prof.mark("k_subset_emit", st);
     return GS_OK;
 }
 

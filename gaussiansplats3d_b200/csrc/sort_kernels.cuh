@@ -189,8 +189,9 @@ __device__ __forceinline__ uint32_t warp_peers9(uint32_t d) {
 // Optionally leaves the bucket in dist[i] (the reference's mappedDistances).
 template <typename KeyT>
 __global__ void __launch_bounds__(kRadixThreads)
-k_bucket(int32_t *__restrict__ dist, KeyT *__restrict__ keys, uint32_t s0, uint32_t rc, uint32_t R, PassPlan plan,
-         int write_buckets, SortControl *ctl, uint32_t *__restrict__ tile_hist, uint32_t stride) {
+k_bucket(int32_t *__restrict__ dist /* distances of the n sorted positions (dist + sortStart) */, KeyT *__restrict__ keys, uint32_t n_host,
+         const unsigned long long *__restrict__ n_dev, uint32_t R, PassPlan plan, int write_buckets, SortControl *ctl,
+         uint32_t *__restrict__ tile_hist, uint32_t stride) {
     __shared__ uint32_t s_hist[kRadix];
     if (threadIdx.x < kRadix) s_hist[threadIdx.x] = 0;
     __syncthreads();
@@ -199,13 +200,13 @@ k_bucket(int32_t *__restrict__ dist, KeyT *__restrict__ keys, uint32_t s0, uint3
     const float range_map = __fdiv_rn(__uint2float_rn(R - 1u), span);          // sorter.cpp:143
     const bool degenerate = (dmax == dmin);
     uint32_t err = 0;
-    const uint32_t n = rc - s0;
+    const uint32_t n = n_dev ? (uint32_t)*n_dev : n_host;   // device-side count: the per-GPU subset of a sharded frame
     const uint64_t jbase = (uint64_t)blockIdx.x * kRadixTile;
     int32_t d[kRadixItems];
 #pragma unroll
     for (int k = 0; k < kRadixItems; ++k) {
         const uint64_t j = jbase + (uint64_t)k * kRadixThreads + threadIdx.x;
-        d[k] = (j < n) ? dist[(uint64_t)rc - 1u - j] : 0;
+        d[k] = (j < n) ? dist[(uint64_t)n - 1u - j] : 0;
     }
 #pragma unroll
     for (int k = 0; k < kRadixItems; ++k) {
@@ -218,7 +219,7 @@ k_bucket(int32_t *__restrict__ dist, KeyT *__restrict__ keys, uint32_t s0, uint3
             // frequencies[R], outside its prefix sum): clamp.  A negative (d - min) means int32 wrap-around: report.
             if (rel < 0 || b < 0) { err |= kErrBucketRange; b = 0; }
             else if ((uint32_t)b >= R) b = (int32_t)(R - 1u);
-            if (write_buckets) dist[(uint64_t)rc - 1u - j] = b;
+            if (write_buckets) dist[(uint64_t)n - 1u - j] = b;
             const uint32_t key = (R - 1u) - (uint32_t)b;
             keys[j] = (KeyT)key;
             // shared-memory atomics: measured faster here than grouping equal digits with MATCH.ANY (2x slower) or ballots (1.4x)

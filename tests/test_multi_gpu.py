@@ -63,8 +63,11 @@ def test_ownership_map_is_a_partition():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("subset_sort", [False, True])
 @pytest.mark.parametrize("world", [2, 3, 8])
-def test_sharded_frames_sum_to_single_engine_frame(gs, world):
+def test_sharded_frames_sum_to_single_engine_frame(gs, world, subset_sort, monkeypatch):
+    # both sort strategies of a sharded frame: replicated full sort (small scenes) and per-rank subset sort (default from 3M splats)
+    monkeypatch.setenv("GS_SUBSET_MIN", "1" if subset_sort else "4000000000")
     from gaussiansplats3d_b200.parallel import combine_frames, ownership_map
     from gaussiansplats3d_b200.scenes import CAMERAS, synthetic_scene
     from gaussiansplats3d_b200.viewer import Viewer

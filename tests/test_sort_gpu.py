@@ -145,3 +145,21 @@ def test_float_24bit_precision_overshoot_is_clamped(gs, oracle_mod):
         assert np.array_equal(np.sort(got), np.sort(c["indexes"]))
         hit += int(buckets.max() == R - 1)
     assert hit > 0
+
+
+def test_engine_argument_errors_and_empty_work(gs):
+    """Error behaviour of the boundary: bad arguments are reported with a status, nothing is executed, nothing crashes."""
+    c = cases.sort_case(seed=4, n=1000)
+    with gs.Engine(1000) as e:
+        with pytest.raises(gs.GsError):                       # more centres than the engine was created for
+            e.upload_centers(np.zeros((2000, 4), np.int32))
+        e.upload_centers(c["centers"][:400])
+        out, _ = e.sort(c["mvp"], 1000, 1000, None)           # counts clamp to what has been uploaded (SortWorker.js:99-100)
+        assert out.shape[0] == 1000 and np.array_equal(np.sort(out[:400]), np.arange(400, dtype=np.uint32))
+        out0, _ = e.sort(c["mvp"], 0, 0, None)                 # nothing to sort
+        assert out0.shape[0] == 0
+        with pytest.raises(gs.GsError):                       # no framebuffer was requested at create time
+            from gaussiansplats3d_b200.engine import Uniforms
+            e.render(Uniforms(np.eye(4), np.eye(4), np.zeros(3), (1, 1), (8, 8)), 8, 8, 10)
+    with pytest.raises(gs.GsError):
+        gs.Engine(10, distance_map_range=1)                   # range < 2

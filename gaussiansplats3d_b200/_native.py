@@ -122,6 +122,7 @@ EXPORTED_SYMBOLS = [
     "gs_render", "gs_frame", "gs_buffer_dev", "gs_stream", "gs_synchronize", "gs_host_alloc", "gs_host_free",
     "gs_read_projected", "gs_last_timings", "gs_frame_async", "gs_flush_l2", "gs_event_create", "gs_event_record",
     "gs_event_elapsed_ms", "gs_event_destroy", "gs_set_profiling", "gs_kernel_timings", "gs_set_graph_enabled", "gs_upload_ksplat", "gs_read_buffer", "gs_peer_export", "gs_peer_attach",
+    "gs_shard_export", "gs_shard_attach", "gs_shard_attach_local", "gs_sort_sharded", "gs_sort_sharded_async", "gs_sort_sharded_finish",
 ]
 
 _lib = None
@@ -202,6 +203,18 @@ def load() -> C.CDLL:
     lib.gs_peer_export.argtypes = [vp, vp, vp]
     lib.gs_peer_attach.restype = C.c_int
     lib.gs_peer_attach.argtypes = [vp, vp, vp]
+    lib.gs_shard_export.restype = C.c_int
+    lib.gs_shard_export.argtypes = [vp, vp, vp]
+    lib.gs_shard_attach.restype = C.c_int
+    lib.gs_shard_attach.argtypes = [vp, u32, vp, vp]
+    lib.gs_shard_attach_local.restype = C.c_int
+    lib.gs_shard_attach_local.argtypes = [vp, u32, C.POINTER(vp)]
+    lib.gs_sort_sharded.restype = C.c_int
+    lib.gs_sort_sharded.argtypes = [vp, C.POINTER(gs_sort_params), vp, C.POINTER(C.c_float)]
+    lib.gs_sort_sharded_async.restype = C.c_int
+    lib.gs_sort_sharded_async.argtypes = [vp, C.POINTER(gs_sort_params)]
+    lib.gs_sort_sharded_finish.restype = C.c_int
+    lib.gs_sort_sharded_finish.argtypes = [vp, vp, C.POINTER(C.c_float)]
     lib.gs_set_graph_enabled.restype = C.c_int
     lib.gs_set_graph_enabled.argtypes = [vp, C.c_int]
     lib.gs_kernel_timings.restype = C.c_int

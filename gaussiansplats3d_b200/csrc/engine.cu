@@ -7,6 +7,7 @@
 #include "common.cuh"
 #include "sort_kernels.cuh"
 #include "raster_kernels.cuh"
+#include "shard_kernels.cuh"
 #include "ksplat_kernels.cuh"
 
 #include <algorithm>
@@ -114,6 +115,7 @@ struct gs_engine {
     uint32_t uploaded_splats = 0;    // 'uploadedSplatCount' SortWorker.js:97
     uint32_t last_render_count = 0;
     bool have_sorted = false;
+    bool ctl_dirty = true;           // SortControl needs k_sort_init (first sort / after a failed one); otherwise the sort leaves it clean
 
     // pinned staging (the shared-memory views of SortWorker.js:180-191)
     PinBuf<uint32_t> h_indexes, h_sorted;
@@ -138,6 +140,18 @@ struct gs_engine {
     bool pending_async = false;
     gs_render_params pending_rp{};
     DevBuf<uint32_t> flush;          // L2 flush scratch (bench hygiene)
+
+    // --- sort-only sharding by input position (shard_kernels.cuh) ---
+    struct Shard {
+        DevBuf<unsigned char> block;                 // ShardHeader + runs[R] (exported through CUDA IPC)
+        DevBuf<uint32_t> total, ahead, block_total, delta, local_sorted;
+        ShardPeers peers{};
+        uint32_t *root_out = nullptr;                // rank 0's sortedIndexes as mapped here
+        void *opened[kMaxShardRanks + 1] = {nullptr};// IPC mappings to close
+        uint32_t world = 0, seq = 0;
+        uint32_t pending_render_count = 0;
+        bool attached = false, pending = false;
+    } shard;
 };
 
 static int check_engine(gs_engine *e) {
@@ -204,6 +218,8 @@ extern "C" void gs_destroy(gs_engine *e) {
     e->keys[0].release(); e->keys[1].release(); e->vals[0].release(); e->vals[1].release(); e->sorted.release();
     e->transforms.release(); e->ctl.release(); e->depthp.release(); e->lookback.release(); e->freq.release(); e->sub_idx.release(); e->sub_dist.release();
     e->h_indexes.release(); e->h_sorted.release(); e->h_ctl.release(); e->h_frame.release(); e->flush.release(); e->prof.release();
+    e->shard.block.release(); e->shard.total.release(); e->shard.ahead.release(); e->shard.block_total.release(); e->shard.delta.release(); e->shard.local_sorted.release();
+    for (void *m : e->shard.opened) if (m) cudaIpcCloseMemHandle(m);
     if (e->rs.peer_attached) { if (e->rs.peer_frame) cudaIpcCloseMemHandle(e->rs.peer_frame); if (e->rs.peer_sync) cudaIpcCloseMemHandle(e->rs.peer_sync); }
     raster_release(e->rs);
     for (int i = 0; i < EV_COUNT; ++i) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
@@ -235,6 +251,35 @@ static void launch_depth(bool identity, int blocks, cudaStream_t st, const uint3
     else k_depth<MODE, false><<<blocks, kDepthThreads, 0, st>>>(idx, centers, pre, scene, tr, P, s0, rc, dist, ctl);
 }
 
+// Distance pass (sorter.cpp:29-140) over positions [lo, hi) of the index list: dist[i] and the running min/max in the control block.
+static int enqueue_depth(gs_engine *e, const uint32_t *d_indexes, const float *mvp, bool use_pre, uint32_t lo, uint32_t hi, bool capturing) {
+    cudaStream_t st = e->stream;
+    const uint32_t n = hi - lo;
+    DepthParams P{};
+    memcpy(P.mvp, mvp, 64);
+    P.irow[0] = (int32_t)((double)mvp[2] * 1000.0);   // sorter.cpp:64 -- f64 product, truncation toward zero
+    P.irow[1] = (int32_t)((double)mvp[6] * 1000.0);
+    P.irow[2] = (int32_t)((double)mvp[10] * 1000.0);
+    P.irow[3] = 1;
+    P.frow[0] = mvp[2]; P.frow[1] = mvp[6]; P.frow[2] = mvp[10]; P.frow[3] = 0.f;
+    if (!capturing) CU(cudaMemcpyAsync(e->depthp.p, &P, sizeof(P), cudaMemcpyHostToDevice, st)); // pageable source: staged before return
+    const bool integer = e->cfg.integer_based_sort, dyn = e->cfg.dynamic_mode;
+    const int mode = use_pre ? (integer ? kIntPrecomputed : kFloatPrecomputed)
+                             : (integer ? (dyn ? kIntDynamic : kIntStatic) : (dyn ? kFloatDynamic : kFloatStatic));
+    const int dblocks = (int)std::max<uint64_t>(1, std::min<uint64_t>(((uint64_t)n + kDepthThreads * kDepthItems - 1) / (kDepthThreads * kDepthItems), (uint64_t)e->sm_count * 8));
+    const bool identity = (d_indexes == nullptr);
+    const void *pre = e->precomputed.p;
+    switch (mode) {
+        case kIntStatic: launch_depth<kIntStatic>(identity, dblocks, st, d_indexes, e->centers.p, pre, e->scene_idx.p, e->transforms.p, e->depthp.p, lo, hi, e->dist.p, e->ctl.p); break;
+        case kIntDynamic: launch_depth<kIntDynamic>(identity, dblocks, st, d_indexes, e->centers.p, pre, e->scene_idx.p, e->transforms.p, e->depthp.p, lo, hi, e->dist.p, e->ctl.p); break;
+        case kIntPrecomputed: launch_depth<kIntPrecomputed>(identity, dblocks, st, d_indexes, e->centers.p, pre, e->scene_idx.p, e->transforms.p, e->depthp.p, lo, hi, e->dist.p, e->ctl.p); break;
+        case kFloatStatic: launch_depth<kFloatStatic>(identity, dblocks, st, d_indexes, e->centers.p, pre, e->scene_idx.p, e->transforms.p, e->depthp.p, lo, hi, e->dist.p, e->ctl.p); break;
+        case kFloatDynamic: launch_depth<kFloatDynamic>(identity, dblocks, st, d_indexes, e->centers.p, pre, e->scene_idx.p, e->transforms.p, e->depthp.p, lo, hi, e->dist.p, e->ctl.p); break;
+        default: launch_depth<kFloatPrecomputed>(identity, dblocks, st, d_indexes, e->centers.p, pre, e->scene_idx.p, e->transforms.p, e->depthp.p, lo, hi, e->dist.p, e->ctl.p); break;
+    }
+    return GS_OK;
+}
+
 // The sort proper, everything already on the device.  d_indexes == nullptr: identity.
 static int sort_on_device(gs_engine *e, const uint32_t *d_indexes, const float *mvp, uint32_t sort_count, uint32_t render_count,
                           bool use_pre, bool write_buckets, bool capturing = false, bool subset = false, cudaEvent_t wait_for_rects = nullptr) {
@@ -249,33 +294,15 @@ static int sort_on_device(gs_engine *e, const uint32_t *d_indexes, const float *
     if (rc) return rc;
     if (!capturing) CU(cudaEventRecord(e->ev[EV_SORT0], st));
     if (!e->have_prof_begin) e->prof.begin(st);
-    k_sort_init<<<1, 256, 0, st>>>(e->ctl.p);
-    ++launches;
-    e->prof.mark("k_sort_init", st);
+    if (e->ctl_dirty && !capturing) {   // first sort, or the previous one failed part-way; a completed sort leaves the block clean
+        k_sort_init<<<1, 256, 0, st>>>(e->ctl.p);
+        ++launches;
+    }
+    if (!capturing) e->ctl_dirty = true;
     if (s0 > 0) { k_copy_head<<<std::min<uint32_t>((s0 + 255) / 256, e->sm_count * 8), 256, 0, st>>>(d_indexes, e->sorted.p, s0); ++launches; e->prof.mark("k_copy_head", st); }
     if (n > 0) {
-        DepthParams P{};
-        memcpy(P.mvp, mvp, 64);
-        P.irow[0] = (int32_t)((double)mvp[2] * 1000.0);   // sorter.cpp:64 -- f64 product, truncation toward zero
-        P.irow[1] = (int32_t)((double)mvp[6] * 1000.0);
-        P.irow[2] = (int32_t)((double)mvp[10] * 1000.0);
-        P.irow[3] = 1;
-        P.frow[0] = mvp[2]; P.frow[1] = mvp[6]; P.frow[2] = mvp[10]; P.frow[3] = 0.f;
-        if (!capturing) CU(cudaMemcpyAsync(e->depthp.p, &P, sizeof(P), cudaMemcpyHostToDevice, st)); // pageable source: staged before return
-        const bool integer = e->cfg.integer_based_sort, dyn = e->cfg.dynamic_mode;
-        const int mode = use_pre ? (integer ? kIntPrecomputed : kFloatPrecomputed)
-                                 : (integer ? (dyn ? kIntDynamic : kIntStatic) : (dyn ? kFloatDynamic : kFloatStatic));
-        const int dblocks = (int)std::min<uint64_t>(((uint64_t)n + kDepthThreads * kDepthItems - 1) / (kDepthThreads * kDepthItems), (uint64_t)e->sm_count * 8);
+        if ((rc = enqueue_depth(e, d_indexes, mvp, use_pre, s0, render_count, capturing))) return rc;
         const bool identity = (d_indexes == nullptr);
-        const void *pre = e->precomputed.p;
-        switch (mode) {
-            case kIntStatic: launch_depth<kIntStatic>(identity, dblocks, st, d_indexes, e->centers.p, pre, e->scene_idx.p, e->transforms.p, e->depthp.p, s0, render_count, e->dist.p, e->ctl.p); break;
-            case kIntDynamic: launch_depth<kIntDynamic>(identity, dblocks, st, d_indexes, e->centers.p, pre, e->scene_idx.p, e->transforms.p, e->depthp.p, s0, render_count, e->dist.p, e->ctl.p); break;
-            case kIntPrecomputed: launch_depth<kIntPrecomputed>(identity, dblocks, st, d_indexes, e->centers.p, pre, e->scene_idx.p, e->transforms.p, e->depthp.p, s0, render_count, e->dist.p, e->ctl.p); break;
-            case kFloatStatic: launch_depth<kFloatStatic>(identity, dblocks, st, d_indexes, e->centers.p, pre, e->scene_idx.p, e->transforms.p, e->depthp.p, s0, render_count, e->dist.p, e->ctl.p); break;
-            case kFloatDynamic: launch_depth<kFloatDynamic>(identity, dblocks, st, d_indexes, e->centers.p, pre, e->scene_idx.p, e->transforms.p, e->depthp.p, s0, render_count, e->dist.p, e->ctl.p); break;
-            default: launch_depth<kFloatPrecomputed>(identity, dblocks, st, d_indexes, e->centers.p, pre, e->scene_idx.p, e->transforms.p, e->depthp.p, s0, render_count, e->dist.p, e->ctl.p); break;
-        }
         ++launches;
         e->prof.mark("k_depth", st);
         if (!capturing) CU(cudaEventRecord(e->ev[EV_DEPTH], st));
@@ -302,14 +329,14 @@ static int sort_on_device(gs_engine *e, const uint32_t *d_indexes, const float *
             e->prof.mark("k_bucket", st);
             if (!capturing) CU(cudaEventRecord(e->ev[EV_BUCKET], st));
             radix_sort_pairs<uint16_t, uint32_t>((uint16_t *)e->keys[0].p, (uint16_t *)e->keys[1].p, vsrc, render_count - 1u, vmode, e->vals[0].p, e->vals[1].p,
-                                       e->sorted.p + s0, n, n_dev, (unsigned long long)n, pl, e->ctl.p, e->lookback.p, stride, true, nullptr, st, launches, &e->prof, names);
+                                       e->sorted.p + s0, n, n_dev, (unsigned long long)n, pl, e->ctl.p, e->lookback.p, stride, true, nullptr, st, launches, &e->prof, names, true);
         } else {
             k_bucket<uint32_t><<<tiles, kRadixThreads, 0, st>>>(dist_sorted, e->keys[0].p, n, n_dev, R, pl, write_buckets ? 1 : 0, e->ctl.p, e->lookback.p, stride);
             ++launches;
             e->prof.mark("k_bucket", st);
             if (!capturing) CU(cudaEventRecord(e->ev[EV_BUCKET], st));
             radix_sort_pairs<uint32_t, uint32_t>(e->keys[0].p, e->keys[1].p, vsrc, render_count - 1u, vmode, e->vals[0].p, e->vals[1].p, e->sorted.p + s0, n,
-                                       n_dev, (unsigned long long)n, pl, e->ctl.p, e->lookback.p, stride, true, nullptr, st, launches, &e->prof, names);
+                                       n_dev, (unsigned long long)n, pl, e->ctl.p, e->lookback.p, stride, true, nullptr, st, launches, &e->prof, names, true);
         }
     } else if (!capturing) {
         CU(cudaEventRecord(e->ev[EV_DEPTH], st));
@@ -320,6 +347,7 @@ static int sort_on_device(gs_engine *e, const uint32_t *d_indexes, const float *
     e->tm.kernel_launches = launches;
     e->last_render_count = render_count;
     e->have_sorted = true;
+    if (!capturing) e->ctl_dirty = false;
     return GS_OK;
 }
 
@@ -384,6 +412,253 @@ extern "C" int gs_sort(gs_engine *e, const gs_sort_params *p, uint32_t *sorted_o
     cudaEventElapsedTime(&e->tm.h2d_ms, e->ev[EV_H2D0], e->ev[EV_H2D1]);
     cudaEventElapsedTime(&e->tm.d2h_ms, e->ev[EV_D2H0], e->ev[EV_D2H1]);
     return rc;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// Sort-only on N GPUs (SURVEY.md 8(e) "depth + sort"): rank g sorts the input positions [lo_g, hi_g) of the sort window and the
+// ranks assemble the reference's global order in rank 0's sortedIndexes over peer memory.  See shard_kernels.cuh.
+static int shard_prepare(gs_engine *e) {
+    const uint32_t R = e->cfg.distance_map_range;
+    int rc;
+    const size_t bytes = sizeof(ShardHeader) + (size_t)R * sizeof(uint2);
+    if (e->shard.block.n < bytes) {
+        if ((rc = e->shard.block.ensure(bytes))) return rc;
+        CU(cudaMemset(e->shard.block.p, 0, bytes));
+    }
+    const size_t blocks = ((size_t)R + kShardScanThreads - 1) / kShardScanThreads;
+    if ((rc = e->shard.total.ensure(R)) || (rc = e->shard.ahead.ensure(R)) || (rc = e->shard.delta.ensure(R)) || (rc = e->shard.block_total.ensure(blocks)) ||
+        (rc = e->shard.local_sorted.ensure(e->cfg.max_splat_count)))
+        return rc;
+    // everything the per-sort path could otherwise grow (cudaFree synchronises the device: not while a peer's wait kernel may be spinning)
+    const PassPlan pl = make_plan_bits(e->key_bits);
+    if ((rc = e->lookback.ensure(radix_tile_hist_words(std::max(e->cfg.max_splat_count, 1u), pl.npasses, nullptr))) || (rc = e->precomputed.ensure(e->cfg.max_splat_count))) return rc;
+    return GS_OK;
+}
+// CUDA loads a kernel's code on its first launch (lazy module loading) and that load can wait for running kernels to finish.  The
+// sharded sort keeps bounded spin-wait kernels in flight while the host enqueues the rest of the chain, so every kernel of the chain
+// is loaded up front (cudaFuncGetAttributes forces the load); otherwise a first sort could stall on its own wait kernel.
+template <typename F> static inline void preload_kernel(F f) { cudaFuncAttributes a; (void)cudaFuncGetAttributes(&a, f); }
+template <typename KeyT> static void shard_preload_keyed() {
+    preload_kernel(k_bucket<KeyT>);
+    preload_kernel(k_radix_hist<KeyT>);
+    preload_kernel(k_shard_place<KeyT>);
+    preload_kernel(k_radix_scatter<KeyT, uint32_t, kValArray, true, false>);
+    preload_kernel(k_radix_scatter<KeyT, uint32_t, kValArrayReversed, true, false>);
+    preload_kernel(k_radix_scatter<KeyT, uint32_t, kValIotaReversed, true, false>);
+    preload_kernel(k_radix_scatter<KeyT, uint32_t, kValArray, true, true>);
+    preload_kernel(k_radix_scatter<KeyT, uint32_t, kValArrayReversed, true, true>);
+    preload_kernel(k_radix_scatter<KeyT, uint32_t, kValIotaReversed, true, true>);
+}
+template <int MODE> static void shard_preload_depth() { preload_kernel(k_depth<MODE, true>); preload_kernel(k_depth<MODE, false>); }
+static void shard_preload(gs_engine *e) {
+    preload_kernel(k_sort_init); preload_kernel(k_copy_head); preload_kernel(k_radix_scan);
+    preload_kernel(k_shard_push_minmax); preload_kernel(k_shard_wait_minmax); preload_kernel(k_shard_runs_init); preload_kernel(k_shard_publish_runs);
+    preload_kernel(k_shard_wait_runs); preload_kernel(k_shard_totals); preload_kernel(k_shard_delta); preload_kernel(k_shard_done); preload_kernel(k_shard_wait_done);
+    shard_preload_depth<kIntStatic>(); shard_preload_depth<kIntDynamic>(); shard_preload_depth<kIntPrecomputed>();
+    shard_preload_depth<kFloatStatic>(); shard_preload_depth<kFloatDynamic>(); shard_preload_depth<kFloatPrecomputed>();
+    if (e->key_bits <= 16) shard_preload_keyed<uint16_t>(); else shard_preload_keyed<uint32_t>();
+    (void)cudaGetLastError();
+}
+static inline ShardHeader *shard_hdr(void *block) { return (ShardHeader *)block; }
+static inline const uint2 *shard_runs(void *block) { return (const uint2 *)((unsigned char *)block + sizeof(ShardHeader)); }
+
+extern "C" int gs_shard_export(gs_engine *e, void *block_handle, void *sorted_handle) {
+    int rc = check_engine(e);
+    if (rc) return rc;
+    if (!block_handle || !sorted_handle) return fail(GS_ERR_BAD_ARG, "gs_shard_export: null");
+    if ((rc = shard_prepare(e))) return rc;
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, e->shard.block.p));
+    memcpy(block_handle, &h, sizeof(h));
+    CU(cudaIpcGetMemHandle(&h, e->sorted.p));
+    memcpy(sorted_handle, &h, sizeof(h));
+    return GS_OK;
+}
+static int shard_bind(gs_engine *e, uint32_t world, void *const *blocks, uint32_t *root_out) {
+    for (uint32_t g = 0; g < world; ++g) {
+        e->shard.peers.hdr[g] = shard_hdr(blocks[g]);
+        e->shard.peers.runs[g] = shard_runs(blocks[g]);
+    }
+    shard_preload(e);
+    e->shard.root_out = root_out;
+    e->shard.world = world;
+    e->shard.seq = 0;
+    e->shard.attached = true;
+    return GS_OK;
+}
+static int shard_check_group(gs_engine *e, uint32_t world, const char *who) {
+    if (world < 1 || world > (uint32_t)kMaxShardRanks) return fail(GS_ERR_BAD_ARG, "%s: world %u outside [1, %d]", who, world, kMaxShardRanks);
+    if (e->cfg.world_size != world || e->cfg.rank >= world) return fail(GS_ERR_BAD_ARG, "%s: engine was created as rank %u of %u, not of %u", who, e->cfg.rank, e->cfg.world_size, world);
+    return GS_OK;
+}
+extern "C" int gs_shard_attach(gs_engine *e, uint32_t world, const void *block_handles, const void *root_sorted_handle) {
+    int rc = check_engine(e);
+    if (rc) return rc;
+    if (!block_handles || !root_sorted_handle) return fail(GS_ERR_BAD_ARG, "gs_shard_attach: null");
+    if ((rc = shard_check_group(e, world, "gs_shard_attach")) || (rc = shard_prepare(e))) return rc;
+    void *blocks[kMaxShardRanks] = {nullptr};
+    for (uint32_t g = 0; g < world; ++g) {
+        if (g == e->cfg.rank) { blocks[g] = e->shard.block.p; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const unsigned char *)block_handles + (size_t)g * GS_IPC_HANDLE_BYTES, sizeof(h));
+        CU(cudaIpcOpenMemHandle(&blocks[g], h, cudaIpcMemLazyEnablePeerAccess));
+        e->shard.opened[g] = blocks[g];
+    }
+    uint32_t *root_out = e->sorted.p;
+    if (e->cfg.rank != 0) {
+        cudaIpcMemHandle_t h;
+        void *m = nullptr;
+        memcpy(&h, root_sorted_handle, sizeof(h));
+        CU(cudaIpcOpenMemHandle(&m, h, cudaIpcMemLazyEnablePeerAccess));
+        e->shard.opened[kMaxShardRanks] = m;
+        root_out = (uint32_t *)m;
+    }
+    return shard_bind(e, world, blocks, root_out);
+}
+// Same process, same device (several engines sharing one GPU, or a test without a second GPU): plain pointers instead of IPC mappings.
+extern "C" int gs_shard_attach_local(gs_engine *e, uint32_t world, gs_engine *const *engines) {
+    int rc = check_engine(e);
+    if (rc) return rc;
+    if (!engines) return fail(GS_ERR_BAD_ARG, "gs_shard_attach_local: null");
+    if ((rc = shard_check_group(e, world, "gs_shard_attach_local"))) return rc;
+    void *blocks[kMaxShardRanks] = {nullptr};
+    for (uint32_t g = 0; g < world; ++g) {
+        gs_engine *pe = engines[g];
+        if (!pe || pe->cfg.device != e->cfg.device || pe->cfg.rank != g || pe->cfg.world_size != world ||
+            pe->cfg.distance_map_range != e->cfg.distance_map_range)
+            return fail(GS_ERR_BAD_ARG, "gs_shard_attach_local: engines[%u] must be rank %u of %u on device %d with the same distance_map_range", g, g, world, e->cfg.device);
+        if ((rc = shard_prepare(pe))) return rc;
+        blocks[g] = pe->shard.block.p;
+    }
+    return shard_bind(e, world, blocks, engines[0]->sorted.p);
+}
+
+template <typename KeyT>
+static int shard_local_sort(gs_engine *e, const uint32_t *d_indexes, uint32_t s0, uint32_t lo, uint32_t hi, uint32_t &launches) {
+    cudaStream_t st = e->stream;
+    const uint32_t n = hi - lo, R = e->cfg.distance_map_range;
+    const PassPlan pl = make_plan_bits(e->key_bits);
+    uint32_t stride = 0;
+    int rc = e->lookback.ensure(radix_tile_hist_words(std::max(n, 1u), pl.npasses, &stride));
+    if (rc) return rc;
+    const bool identity = (d_indexes == nullptr);
+    static const RadixNames names = {{"k_radix_hist[shard,0]", "k_radix_hist[shard,1]", "k_radix_hist[shard,2]", "k_radix_hist[shard,3]"},
+                                     {"k_radix_scan[shard,0]", "k_radix_scan[shard,1]", "k_radix_scan[shard,2]", "k_radix_scan[shard,3]"},
+                                     {"k_radix_scatter[shard,0]", "k_radix_scatter[shard,1]", "k_radix_scatter[shard,2]", "k_radix_scatter[shard,3]"}};
+    const uint32_t me = e->cfg.rank, world = e->shard.world, seq = e->shard.seq;
+    uint2 *runs = (uint2 *)shard_runs(e->shard.block.p);
+    KeyT *final_keys = nullptr;
+    if (n) {   // slice -> keys with the GLOBAL range map -> local order + per-key runs of that order
+        const uint32_t tiles = (n + kRadixTile - 1) / kRadixTile;
+        k_bucket<KeyT><<<tiles, kRadixThreads, 0, st>>>(e->dist.p + lo, (KeyT *)e->keys[0].p, n, nullptr, R, pl, 0, e->ctl.p, e->lookback.p, stride);
+        ++launches;
+        e->prof.mark("k_bucket", st);
+        radix_sort_pairs<KeyT, uint32_t>((KeyT *)e->keys[0].p, (KeyT *)e->keys[1].p, identity ? nullptr : d_indexes + lo, hi - 1u,
+                                         identity ? kValIotaReversed : kValArrayReversed, e->vals[0].p, e->vals[1].p, e->shard.local_sorted.p, n, nullptr,
+                                         (unsigned long long)n, pl, e->ctl.p, e->lookback.p, stride, true, runs, st, launches, &e->prof, names, true, true, &final_keys);
+    }
+    // C2: publish my runs, wait for everybody's, turn them into the offsets of my runs in the global order
+    k_shard_publish_runs<<<1, 32, 0, st>>>(e->shard.peers, me, world, seq);
+    k_shard_wait_runs<<<1, 32, 0, st>>>(shard_hdr(e->shard.block.p), world, seq);
+    launches += 2;
+    e->prof.mark("k_shard_exchange_runs", st);
+    if (n) {
+        const uint32_t sblocks = (R + kShardScanThreads - 1) / kShardScanThreads;
+        k_shard_totals<<<sblocks, kShardScanThreads, 0, st>>>(e->shard.peers, me, world, R, e->shard.total.p, e->shard.ahead.p, e->shard.block_total.p);
+        k_shard_delta<<<sblocks, kShardScanThreads, 0, st>>>(runs, R, e->shard.total.p, e->shard.ahead.p, e->shard.block_total.p, e->shard.delta.p);
+        e->prof.mark("k_shard_offsets", st);
+        k_shard_place<KeyT><<<std::min<uint32_t>((n + 255) / 256, e->sm_count * 16), 256, 0, st>>>(final_keys, e->shard.local_sorted.p, n, e->shard.delta.p, e->shard.root_out + s0);
+        e->prof.mark("k_shard_place", st);
+        launches += 3;
+    }
+    return GS_OK;
+}
+
+// Position slice of rank g: [sortStart + n*g/G, sortStart + n*(g+1)/G)
+static inline uint32_t shard_bound(uint32_t s0, uint32_t n, uint32_t g, uint32_t world) { return s0 + (uint32_t)(((uint64_t)n * g) / world); }
+
+extern "C" int gs_sort_sharded_async(gs_engine *e, const gs_sort_params *p) {
+    int rc = check_engine(e);
+    if (rc) return rc;
+    if (!p) return fail(GS_ERR_BAD_ARG, "gs_sort_sharded: null params");
+    if (!e->shard.attached) return fail(GS_ERR_NOT_READY, "gs_sort_sharded: call gs_shard_attach (or gs_shard_attach_local) first");
+    if (e->shard.pending) return fail(GS_ERR_NOT_READY, "gs_sort_sharded_async: the previous sharded sort has not been finished");
+    gs_sort_params q = *p;
+    q.render_count = std::min(q.render_count, e->uploaded_splats);   // SortWorker.js:99-100
+    q.sort_count = std::min(q.sort_count, e->uploaded_splats);
+    if (q.sort_count > q.render_count) return fail(GS_ERR_BAD_ARG, "sortCount %u > renderCount %u", q.sort_count, q.render_count);
+    const uint32_t *d_idx = nullptr;
+    e->last_frame_was_graph = false;
+    if ((rc = stage_sort_inputs(e, &q, &d_idx))) return rc;
+    cudaStream_t st = e->stream;
+    const uint32_t me = e->cfg.rank, world = e->shard.world;
+    const uint32_t s0 = q.render_count - q.sort_count;
+    const uint32_t lo = shard_bound(s0, q.sort_count, me, world), hi = shard_bound(s0, q.sort_count, me + 1, world);
+    const uint32_t seq = ++e->shard.seq;
+    uint32_t launches = 0;
+    CU(cudaEventRecord(e->ev[EV_SORT0], st));
+    e->prof.begin(st);
+    if (e->ctl_dirty) { k_sort_init<<<1, 256, 0, st>>>(e->ctl.p); ++launches; }
+    e->ctl_dirty = true;
+    if (me == 0 && s0 > 0) { k_copy_head<<<std::min<uint32_t>((s0 + 255) / 256, e->sm_count * 8), 256, 0, st>>>(d_idx, e->sorted.p, s0); ++launches; e->prof.mark("k_copy_head", st); }
+    if (hi > lo) {
+        if ((rc = enqueue_depth(e, d_idx, q.model_view_proj, q.use_precomputed_distances != 0, lo, hi, false))) return rc;
+        ++launches;
+        e->prof.mark("k_depth", st);
+    }
+    // C1: global min/max over peer memory
+    k_shard_push_minmax<<<1, 32, 0, st>>>(e->shard.peers, e->ctl.p, me, world, seq);
+    k_shard_wait_minmax<<<1, 32, 0, st>>>(shard_hdr(e->shard.block.p), e->ctl.p, world, seq, hi > lo ? 0 : 1);
+    k_shard_runs_init<<<std::min<uint32_t>((e->cfg.distance_map_range + 255) / 256, e->sm_count * 8), 256, 0, st>>>((uint2 *)shard_runs(e->shard.block.p), e->cfg.distance_map_range);
+    launches += 3;
+    e->prof.mark("k_shard_exchange_minmax", st);
+    CU(cudaEventRecord(e->ev[EV_DEPTH], st));
+    CU(cudaEventRecord(e->ev[EV_BUCKET], st));
+    rc = (e->key_bits <= 16) ? shard_local_sort<uint16_t>(e, d_idx, s0, lo, hi, launches) : shard_local_sort<uint32_t>(e, d_idx, s0, lo, hi, launches);
+    if (rc) return rc;
+    k_shard_done<<<1, 1, 0, st>>>(e->shard.peers.hdr[0], me, seq);
+    ++launches;
+    if (me == 0) { k_shard_wait_done<<<1, 32, 0, st>>>(shard_hdr(e->shard.block.p), world, seq); ++launches; }
+    e->prof.mark("k_shard_done", st);
+    CU(cudaEventRecord(e->ev[EV_SORT1], st));
+    CU(cudaGetLastError());
+    e->tm.kernel_launches = launches;
+    e->last_render_count = q.render_count;
+    e->have_sorted = (me == 0);     // the assembled order lives in rank 0's sortedIndexes
+    e->ctl_dirty = !(hi > lo);      // an empty slice ran no final radix pass, which is what re-seeds the control block
+    e->shard.pending = true;
+    e->shard.pending_render_count = q.render_count;
+    return GS_OK;
+}
+
+extern "C" int gs_sort_sharded_finish(gs_engine *e, uint32_t *sorted_out, float *sort_time_ms) {
+    int rc = check_engine(e);
+    if (rc) return rc;
+    if (!e->shard.pending) return fail(GS_ERR_NOT_READY, "gs_sort_sharded_finish: nothing pending");
+    e->shard.pending = false;
+    const uint32_t rcnt = e->shard.pending_render_count;
+    CU(cudaEventRecord(e->ev[EV_D2H0], e->stream));
+    if (sorted_out && rcnt && e->cfg.rank == 0) CU(cudaMemcpyAsync(sorted_out, e->sorted.p, (size_t)rcnt * 4, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaEventRecord(e->ev[EV_D2H1], e->stream));
+    CU(cudaMemcpyAsync(e->h_ctl.p + 32, e->shard.block.p, sizeof(ShardHeader), cudaMemcpyDeviceToHost, e->stream));
+    rc = finish_sort(e, sort_time_ms);
+    cudaEventElapsedTime(&e->tm.h2d_ms, e->ev[EV_H2D0], e->ev[EV_H2D1]);
+    cudaEventElapsedTime(&e->tm.d2h_ms, e->ev[EV_D2H0], e->ev[EV_D2H1]);
+    ShardHeader hd;
+    memcpy(&hd, e->h_ctl.p + 32, sizeof(hd));
+    if (hd.timeout) {
+        cudaMemsetAsync(&shard_hdr(e->shard.block.p)->timeout, 0, 4, e->stream);
+        e->ctl_dirty = true;
+        return fail(GS_ERR_CUDA, "sharded sort: a peer rank did not reach the exchange within the time limit (are all %u ranks calling gs_sort_sharded?)", e->shard.world);
+    }
+    return rc;
+}
+
+extern "C" int gs_sort_sharded(gs_engine *e, const gs_sort_params *p, uint32_t *sorted_out, float *sort_time_ms) {
+    int rc = gs_sort_sharded_async(e, p);
+    if (rc) return rc;
+    return gs_sort_sharded_finish(e, sorted_out, sort_time_ms);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -658,8 +933,11 @@ static int enqueue_frame(gs_engine *e, const gs_sort_params *s, const gs_uniform
             if (ce != cudaSuccess) { e->graph_exec = nullptr; return fail(GS_ERR_CUDA, "cudaGraphInstantiate -> %s", cudaGetErrorString(ce)); }
             memcpy(e->graph_key, key, sizeof(key));
         }
+        if (e->ctl_dirty) k_sort_init<<<1, 256, 0, st>>>(e->ctl.p);   // the captured sort assumes (and leaves) a clean control block
+        e->ctl_dirty = true;
         CU(cudaEventRecord(e->ev[EV_SORT0], st));
         CU(cudaGraphLaunch(e->graph_exec, st));
+        e->ctl_dirty = false;
         CU(cudaEventRecord(e->ev[EV_R1], st));
         e->tm.kernel_launches = e->graph_launches;
         e->last_render_count = q.render_count;

@@ -110,6 +110,7 @@ k_depth(const uint32_t *__restrict__ indexes, const void *__restrict__ centers, 
         }
         __syncthreads();
     }
+    if (blockIdx.x == 0 && threadIdx.x == 0) ctl->error = 0;   // only k_bucket (a later kernel) raises error bits
     int32_t lmin = 2147483640, lmax = -2147483640;
     const uint32_t tile = kDepthThreads * kDepthItems;
     for (uint64_t base = (uint64_t)s0 + (uint64_t)blockIdx.x * tile; base < rc; base += (uint64_t)gridDim.x * tile) {
@@ -403,9 +404,15 @@ __global__ void __launch_bounds__(kRadixThreads, 2)
 k_radix_scatter(const KeyT *__restrict__ keys_in, const ValT *__restrict__ vals_in, uint32_t iota_top,
                 KeyT *__restrict__ keys_out, ValT *__restrict__ vals_out, uint32_t n_host,
                 const unsigned long long *__restrict__ n_dev, unsigned long long n_cap, int shift, int bits,
-                const uint32_t *__restrict__ tile_offsets, uint32_t stride, uint2 *ranges) {
+                const uint32_t *__restrict__ tile_offsets, uint32_t stride, uint2 *ranges, uint32_t *clear_hist, SortControl *reset_ctl) {
     const uint32_t n = n_dev ? (uint32_t)min(*n_dev, n_cap) : n_host;
     const uint32_t tile = blockIdx.x;
+    // self-cleaning control block (no init kernel on the frame's critical path): this pass's digit totals were consumed by the
+    // scan that ran before this kernel; the final pass also re-seeds min/max (sorter.cpp:24-25) for the next sort
+    if (tile == 0) {
+        if (clear_hist && threadIdx.x < kRadix) clear_hist[threadIdx.x] = 0;
+        if (reset_ctl && threadIdx.x == 0) { reset_ctl->dmin = 2147483640; reset_ctl->dmax = -2147483640; }
+    }
     const uint64_t tile_base = (uint64_t)tile * kRadixTile;
     if (tile_base >= n) return; // surplus CTA of a capacity-sized grid (uniform exit)
     // phase A: per-warp digit counters; phase B: reorder buffers (aliased)
@@ -499,10 +506,16 @@ static inline PassPlan make_plan_bits(int key_bits) {
 template <typename KeyT, typename ValT>
 static void launch_radix_scatter(uint32_t grid, bool first, bool write_keys, bool want_ranges, int valmode, const KeyT *kin, const ValT *vin,
                                  uint32_t iota_top, KeyT *kout, ValT *vout, uint32_t n, const unsigned long long *n_dev, unsigned long long n_cap,
-                                 int shift, int bits, const uint32_t *tile_offsets, uint32_t stride, uint2 *ranges, cudaStream_t st) {
-#define GS_PASS(VM, WK, RG) k_radix_scatter<KeyT, ValT, VM, WK, RG><<<grid, kRadixThreads, 0, st>>>(kin, vin, iota_top, kout, vout, n, n_dev, n_cap, shift, bits, tile_offsets, stride, ranges)
+                                 int shift, int bits, const uint32_t *tile_offsets, uint32_t stride, uint2 *ranges, uint32_t *clear_hist, SortControl *reset_ctl,
+                                 cudaStream_t st) {
+#define GS_PASS(VM, WK, RG) k_radix_scatter<KeyT, ValT, VM, WK, RG><<<grid, kRadixThreads, 0, st>>>(kin, vin, iota_top, kout, vout, n, n_dev, n_cap, shift, bits, tile_offsets, stride, ranges, clear_hist, reset_ctl)
     if (!first) valmode = kValArray;
-    if (want_ranges) { GS_PASS(kValArray, false, true); }
+    if (want_ranges && !write_keys) { GS_PASS(kValArray, false, true); }   // tile-instance sort (values always come from an array)
+    else if (want_ranges) {                                                 // sharded depth sort: sorted keys AND per-key runs
+        if (valmode == kValArray) GS_PASS(kValArray, true, true);
+        else if (valmode == kValArrayReversed) GS_PASS(kValArrayReversed, true, true);
+        else GS_PASS(kValIotaReversed, true, true);
+    }
     else if (valmode == kValArray) { if (!write_keys) GS_PASS(kValArray, false, false); else GS_PASS(kValArray, true, false); }
     else if (valmode == kValArrayReversed) { if (!write_keys) GS_PASS(kValArrayReversed, false, false); else GS_PASS(kValArrayReversed, true, false); }
     else { if (!write_keys) GS_PASS(kValIotaReversed, false, false); else GS_PASS(kValIotaReversed, true, false); }
@@ -519,7 +532,9 @@ template <typename KeyT, typename ValT>
 static void radix_sort_pairs(KeyT *keys0, KeyT *keys1, const ValT *vals_src, uint32_t iota_top, int first_valmode, ValT *vtmp0,
                              ValT *vtmp1, ValT *vals_final, uint32_t n, const unsigned long long *n_dev, unsigned long long n_cap,
                              const PassPlan &pl, SortControl *ctl, uint32_t *tile_hist, uint32_t stride, bool hist0_done, uint2 *ranges,
-                             cudaStream_t st, uint32_t &launches, Profiler *prof, const RadixNames &names) {
+                             cudaStream_t st, uint32_t &launches, Profiler *prof, const RadixNames &names, bool self_clean = false,
+                             bool keep_final_keys = false /* sorted keys are left in the buffer the last pass writes (returned) */,
+                             KeyT **final_keys = nullptr) {
     const unsigned long long n_grid = n_dev ? n_cap : n;
     const uint32_t tiles = (uint32_t)((n_grid + kRadixTile - 1) / kRadixTile);
     if (!tiles) return;
@@ -538,8 +553,10 @@ static void radix_sort_pairs(KeyT *keys0, KeyT *keys1, const ValT *vals_src, uin
         k_radix_scan<<<1u << pl.bits[p], kScanColThreads, 0, st>>>(th, stride, n, n_dev, n_cap, &ctl->hist[p][0]);
         ++launches;
         if (prof) prof->mark(names.scan[p], st);
-        launch_radix_scatter<KeyT, ValT>(tiles, p == 0, !last, last && ranges != nullptr, first_valmode, kin, vin, iota_top, kout, vout, n, n_dev, n_cap,
-                                   pl.shift[p], pl.bits[p], th, stride, ranges, st);
+        if (last && final_keys) *final_keys = kout;
+        launch_radix_scatter<KeyT, ValT>(tiles, p == 0, !last || keep_final_keys, last && ranges != nullptr, first_valmode, kin, vin, iota_top, kout, vout, n, n_dev, n_cap,
+                                   pl.shift[p], pl.bits[p], th, stride, ranges, self_clean ? &ctl->hist[p][0] : nullptr,
+                                   (self_clean && last) ? ctl : nullptr, st);
         ++launches;
         if (prof) prof->mark(names.scatter[p], st);
         vin = vout;

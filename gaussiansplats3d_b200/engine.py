@@ -167,6 +167,40 @@ class Engine:
         N.check(self._lib.gs_sort(self._h, C.byref(p), N.ptr(out) if download else None, C.byref(ms)), "gs_sort")
         return (out if download else None), ms.value
 
+    # -- sort-only on N GPUs (include/gsplat_b200.h "Sort-only on N GPUs") --------------------------------------------
+    def shard_export(self) -> tuple[bytes, bytes]:
+        """CUDA-IPC handles of this rank's exchange block and of its sortedIndexes buffer."""
+        a, b = C.create_string_buffer(64), C.create_string_buffer(64)
+        N.check(self._lib.gs_shard_export(self._h, a, b), "gs_shard_export")
+        return a.raw, b.raw
+
+    def shard_attach(self, block_handles: list[bytes], root_sorted_handle: bytes) -> None:
+        """All ranks: map every rank's exchange block (list index = rank) and rank 0's sortedIndexes."""
+        blob = C.create_string_buffer(b"".join(block_handles), 64 * len(block_handles))
+        N.check(self._lib.gs_shard_attach(self._h, len(block_handles), blob, C.create_string_buffer(root_sorted_handle, 64)), "gs_shard_attach")
+
+    def shard_attach_local(self, engines: list["Engine"]) -> None:
+        """Engines of this process on one device (list index = rank): plain pointers instead of IPC mappings."""
+        arr = (C.c_void_p * len(engines))(*[en._h for en in engines])
+        N.check(self._lib.gs_shard_attach_local(self._h, len(engines), arr), "gs_shard_attach_local")
+
+    def sort_sharded_async(self, mvp, sort_count: int, render_count: int, indexes: np.ndarray | None = None, *, transforms=None, precomputed=None) -> None:
+        p = self._sort_params(mvp, sort_count, render_count, indexes, transforms, precomputed)
+        self._shard_keep = p
+        N.check(self._lib.gs_sort_sharded_async(self._h, C.byref(p)), "gs_sort_sharded_async")
+
+    def sort_sharded_finish(self, out: np.ndarray | None = None):
+        """Waits for this rank's part; on rank 0 `out` (render_count u32) receives the assembled order.  Returns (out, ms)."""
+        ms = C.c_float(0)
+        N.check(self._lib.gs_sort_sharded_finish(self._h, N.ptr(out), C.byref(ms)), "gs_sort_sharded_finish")
+        return out, ms.value
+
+    def sort_sharded(self, mvp, sort_count: int, render_count: int, indexes: np.ndarray | None = None, *, transforms=None, precomputed=None,
+                     out: np.ndarray | None = None):
+        """One sortIndexes call spread over the ranks of the group; every rank calls it with the same arguments."""
+        self.sort_sharded_async(mvp, sort_count, render_count, indexes, transforms=transforms, precomputed=precomputed)
+        return self.sort_sharded_finish(out)
+
     def compute_distances(self, mvp64, count: int, scene_transforms64=None) -> np.ndarray:
         m = np.ascontiguousarray(mvp64, dtype=np.float64).reshape(16)
         st = None if scene_transforms64 is None else np.ascontiguousarray(scene_transforms64, dtype=np.float64).reshape(-1)

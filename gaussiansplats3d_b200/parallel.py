@@ -93,3 +93,59 @@ class PeerGather:
         pass
 
     all_reduce = all_gather
+
+
+# ---- sort-only on N GPUs: one sortIndexes call split by input position ("depth + sort") -------------------------
+def shard_bounds(sort_start: int, sort_count: int, world: int) -> list[tuple[int, int]]:
+    """Input-position slice [lo, hi) of every rank (the C side uses the same integer formula)."""
+    return [(sort_start + (sort_count * g) // world, sort_start + (sort_count * (g + 1)) // world) for g in range(world)]
+
+
+def merge_sharded_order(sort_start: int, range_: int, per_rank: list[tuple[np.ndarray, np.ndarray]]) -> np.ndarray:
+    """Host restatement of the exchange the kernels perform, for tests and documentation.
+
+    per_rank[g] = (buckets, values) of rank g's slice in ORIGINAL input order (buckets computed with the GLOBAL min/max).
+    Each rank orders its slice like the reference orders the whole window (bucket descending, later input position first,
+    sorter.cpp:151-167); rank g's run of bucket b then starts after every run of a larger bucket and after the runs of bucket b
+    held by ranks > g (their input positions are higher).  Returns the sorted part of indexesOut (without the head)."""
+    world = len(per_rank)
+    counts = np.zeros((world, range_), np.int64)
+    local = []
+    for g, (b, v) in enumerate(per_rank):
+        b = np.asarray(b, np.int64)
+        key = (range_ - 1) - b[::-1]                      # ascending key over the reversed slice == the reference's order
+        order = np.argsort(key, kind="stable")
+        local.append((key[order], np.asarray(v)[::-1][order]))
+        counts[g] = np.bincount(key, minlength=range_)
+    total = counts.sum(axis=0)
+    before_key = np.concatenate([[0], np.cumsum(total)[:-1]])
+    out = np.empty(int(total.sum()), np.uint32)
+    for g in range(world):
+        ahead = counts[g + 1:].sum(axis=0)                # same key, ranks with higher input positions
+        start_local = np.concatenate([[0], np.cumsum(counts[g])[:-1]])
+        keys, vals = local[g]
+        j = np.arange(keys.size)
+        out[j + (before_key + ahead - start_local)[keys]] = vals
+    return out
+
+
+class ShardedSort:
+    """N processes, one GPU each: every rank sorts its slice of input positions and stores its part of the global order into
+    rank 0's sortedIndexes over NVLink (CUDA IPC); the IPC handles travel once through torch.distributed at set-up."""
+
+    def __init__(self, engine, rank: int, world: int):
+        import torch.distributed as dist
+        self.engine, self.rank, self.world = engine, rank, world
+        mine = engine.shard_export()
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine)
+        engine.shard_attach([h[0] for h in gathered], gathered[0][1])
+        dist.barrier()
+
+    def sort(self, mvp, sort_count: int, render_count: int, indexes=None, *, out=None, transforms=None, precomputed=None):
+        """Collective: every rank calls it with the same arguments.  Rank 0 gets (sortedIndexes, ms); others (None, ms)."""
+        if self.rank == 0 and out is None:
+            out = np.empty(render_count, np.uint32)
+        res, ms = self.engine.sort_sharded(mvp, sort_count, render_count, indexes, transforms=transforms, precomputed=precomputed,
+                                           out=out if self.rank == 0 else None)
+        return (res if self.rank == 0 else None), ms

@@ -245,6 +245,24 @@ GS_API int gs_synchronize(gs_engine *e);
 GS_API int gs_peer_export(gs_engine *e, void *frame_handle /*64 B out*/, void *sync_handle /*64 B out*/);      /* rank 0     */
 GS_API int gs_peer_attach(gs_engine *e, const void *frame_handle, const void *sync_handle);                    /* ranks > 0  */
 
+/* Sort-only on N GPUs (SURVEY.md 8(e) "depth + sort"): ONE sortIndexes call (sorter.cpp:17-168) split by input position.  Every
+ * rank holds all centres; rank g computes distances for, and sorts, positions [sortStart + n*g/N, sortStart + n*(g+1)/N) of the
+ * sort window.  Two exchanges over peer memory (NVLink), no NCCL, no host round trip: the global min/max before the range map
+ * (8 B per rank pair), and the per-bucket run lengths (8 B per bucket per rank pair) from which every rank derives where its runs
+ * sit in the reference's order (buckets descending, inside a bucket higher input positions first = rank N-1 ... 0).  Each rank
+ * then stores its 4 B/splat straight into RANK 0's sortedIndexes, which is bit-exact with the single-GPU gs_sort.
+ *   setup    every rank: gs_shard_export -> exchange the handles (any transport) -> gs_shard_attach with all N block handles
+ *            (index = rank) and rank 0's sorted handle.  gs_shard_attach_local: engines of one process on one device.
+ *   per sort every rank calls gs_sort_sharded with the SAME parameters; sorted_out is filled on rank 0 only (may be NULL elsewhere).
+ *            _async enqueues and returns; _finish waits, copies, reports errors (a missing peer gives GS_ERR_CUDA after ~2 s).   */
+#define GS_MAX_SHARD_RANKS 8
+GS_API int gs_shard_export(gs_engine *e, void *block_handle /*64 B out*/, void *sorted_handle /*64 B out*/);
+GS_API int gs_shard_attach(gs_engine *e, uint32_t world, const void *block_handles /* world x 64 B */, const void *root_sorted_handle);
+GS_API int gs_shard_attach_local(gs_engine *e, uint32_t world, gs_engine *const *engines /* [world], index = rank */);
+GS_API int gs_sort_sharded(gs_engine *e, const gs_sort_params *p, uint32_t *sorted_out /* host, rank 0 */, float *sort_time_ms);
+GS_API int gs_sort_sharded_async(gs_engine *e, const gs_sort_params *p);
+GS_API int gs_sort_sharded_finish(gs_engine *e, uint32_t *sorted_out /* host, rank 0 */, float *sort_time_ms);
+
 /* Page-locked host memory for callers: the counterpart of the SharedArrayBuffer views a shared-memory sort worker
  * hands to the main thread (SortWorker.js:180-191).  Buffers passed to gs_sort / gs_render from such memory are
  * copied asynchronously without an extra staging copy. */

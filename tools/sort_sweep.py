@@ -21,6 +21,9 @@ def main():
     ap.add_argument("--cpu", action="store_true")
     ap.add_argument("--shuffled", action="store_true")
     a = ap.parse_args()
+    import os
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        return main_sharded(a)
     import cases
     import gaussiansplats3d_b200 as gs
     peak = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())["hbm_gbs"] if (ROOT / "MEASURED_PEAKS.json").exists() else 6650.0
@@ -62,6 +65,54 @@ def main():
             oracle.ref_sort_indexes(*cases.call_args(c, 1 << 16))
             line["cpu_reference_ms"] = (time.perf_counter() - t0) * 1e3
         print(json.dumps(line), flush=True)
+
+
+def main_sharded(a):
+    """Under torchrun: ONE sort split over the ranks by input position (gs_sort_sharded); result assembled in rank 0's memory.
+    Time = CUDA events on every rank's stream around its part, max over ranks (rank 0's includes the wait for all peers)."""
+    import ctypes as C
+    import os
+    import torch
+    import torch.distributed as dist
+    import cases
+    import gaussiansplats3d_b200 as gs
+    from gaussiansplats3d_b200.parallel import ShardedSort
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    for m in [int(x) for x in a.sizes.split(",")]:
+        n = m * 1_000_000
+        c = cases.sort_case(seed=10 + m, n=n, index_kind="shuffled" if a.shuffled else "identity")
+        with gs.Engine(n, device=local, rank=rank, world_size=world) as e:
+            e.upload_centers(c["centers"])
+            idx_dev = None
+            want, _ = e.sort(c["mvp"], n, n, c["indexes"] if a.shuffled else None)      # single-GPU answer (also uploads the index list)
+            if a.shuffled:
+                idx_dev, _ = e.buffer_dev(gs._native.GS_BUF_INDEXES_TO_SORT)
+            ss = ShardedSort(e, rank, world)
+            p = e._sort_params(c["mvp"], n, n, None, None, None, indexes_dev=idx_dev)
+            out = np.empty(n, np.uint32) if rank == 0 else None
+            gs._native.check(e._lib.gs_sort_sharded(e._h, C.byref(p), gs._native.ptr(out), None), "gs_sort_sharded")
+            exact = bool(np.array_equal(out, want)) if rank == 0 else None
+            ev0, ev1 = e.event(), e.event()
+            times = []
+            for _ in range(a.reps + 2):
+                e.flush_l2()
+                e.synchronize()
+                dist.barrier()
+                ev0.record()
+                gs._native.check(e._lib.gs_sort_sharded(e._h, C.byref(p), None, None), "gs_sort_sharded")
+                ev1.record()
+                e.synchronize()
+                t = torch.tensor([ev0.elapsed_ms(ev1)], device="cuda", dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                times.append(float(t.item()))
+            dist.barrier()
+        if rank == 0:
+            ms = float(np.median(times[2:]))
+            print(json.dumps({"splats": n, "gpus": world, "indexes": "shuffled" if a.shuffled else "identity", "sort_ms": ms, "msplats_per_s": n / ms / 1e3,
+                              "bit_exact_vs_single_gpu": exact, "exchange": "peer memory (min/max, run lengths, 4 B/splat into rank 0)"}), flush=True)
+    dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -54,7 +54,11 @@ class ClockSampler:
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, gpu_index: int):
-        self.rows, self.proc, self.gpu = [], None, gpu_index
+        self.rows, self.proc, self.gpu, self.first = [], None, gpu_index, 0
+
+    def mark(self):
+        """Samples from here on count (nvidia-smi is started early: on an 8-GPU box it needs seconds before its first line)."""
+        self.first = len(self.rows)
 
     def start(self):
         try:
@@ -76,7 +80,7 @@ class ClockSampler:
             except Exception:
                 pass
         sm, mx, reasons = [], 0.0, set()
-        for r in self.rows:
+        for r in self.rows[self.first:]:
             try:
                 sm.append(float(r[0])); mx = max(mx, float(r[1]))
             except Exception:
@@ -206,6 +210,9 @@ def run_ours(args):
 
     K, W = args.steps, max(args.warmup, 3)
     n, sh, kind, seed, cam, width, height = WORKLOADS[args.workload]
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     v, raw = build_viewer(args.workload, rank, world, local)
     e = v.engine
     mvp = v.mvp_matrix().astype(np.float32)
@@ -242,11 +249,10 @@ def run_ours(args):
             torch.cuda.synchronize()
             dist.barrier()
 
-    sampler = ClockSampler(local)
     for _ in range(W):
         step_async()
     barrier()
-    sampler.start()
+    sampler.mark()
 
     # ---- value: device time, scene resident, L2 flushed before every step ----------------------------------------------
     ev0 = [e.event() for _ in range(K)]
@@ -347,7 +353,23 @@ def run_ours(args):
         e2e = {"value": K / float(np.sum(t_e2e)), "unit": "frames/s", "h2d_bytes_per_step": int(64 + 3000),
                "d2h_bytes_per_step": int(width * height * 4), "ms_per_step": 1000.0 * float(np.mean(t_e2e))}
 
+    # short runs end before nvidia-smi's 200 ms period has produced enough lines: keep the same frames running (untimed) until it has
+    t_wait = time.perf_counter()
+    extended = 0
+    while True:
+        need = 1 if (rank == 0 and sampler.proc is not None and len(sampler.rows) - sampler.first < 3 and time.perf_counter() - t_wait < 8.0) else 0
+        if dist is not None:       # rank 0 decides for everybody (the frames below are collective)
+            t = torch.tensor([need], device="cuda", dtype=torch.int32)
+            dist.broadcast(t, src=0)
+            need = int(t.item())
+        if not need:
+            break
+        for _ in range(50):
+            step_async()
+        barrier()
+        extended += 50
     clocks = sampler.stop()
+    clocks["window"] = "timed + per-kernel + e2e regions" + (f", extended by {extended} identical untimed frames" if extended else "")
 
     # ---- CPU baseline beside it (rank 0, N = 1 only; bounded sample) ---------------------------------------------------------------
     cpu = None

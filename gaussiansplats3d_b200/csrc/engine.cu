@@ -151,6 +151,7 @@ struct gs_engine {
         uint32_t world = 0, seq = 0;
         uint32_t pending_render_count = 0;
         bool attached = false, pending = false;
+        bool pending_unsplit = false;                // the pending call was below the split threshold: rank 0 sorted alone
     } shard;
 };
 
@@ -453,8 +454,7 @@ template <typename KeyT> static void shard_preload_keyed() {
 template <int MODE> static void shard_preload_depth() { preload_kernel(k_depth<MODE, true>); preload_kernel(k_depth<MODE, false>); }
 static void shard_preload(gs_engine *e) {
     preload_kernel(k_sort_init); preload_kernel(k_copy_head); preload_kernel(k_radix_scan);
-    preload_kernel(k_shard_push_minmax); preload_kernel(k_shard_wait_minmax); preload_kernel(k_shard_runs_init); preload_kernel(k_shard_publish_runs);
-    preload_kernel(k_shard_wait_runs); preload_kernel(k_shard_totals); preload_kernel(k_shard_delta); preload_kernel(k_shard_done); preload_kernel(k_shard_wait_done);
+    preload_kernel(k_shard_exchange_minmax); preload_kernel(k_shard_exchange_runs); preload_kernel(k_shard_totals); preload_kernel(k_shard_delta); preload_kernel(k_shard_done);
     shard_preload_depth<kIntStatic>(); shard_preload_depth<kIntDynamic>(); shard_preload_depth<kIntPrecomputed>();
     shard_preload_depth<kFloatStatic>(); shard_preload_depth<kFloatDynamic>(); shard_preload_depth<kFloatPrecomputed>();
     if (e->key_bits <= 16) shard_preload_keyed<uint16_t>(); else shard_preload_keyed<uint32_t>();
@@ -559,9 +559,8 @@ static int shard_local_sort(gs_engine *e, const uint32_t *d_indexes, uint32_t s0
                                          (unsigned long long)n, pl, e->ctl.p, e->lookback.p, stride, true, runs, st, launches, &e->prof, names, true, true, &final_keys);
     }
     // C2: publish my runs, wait for everybody's, turn them into the offsets of my runs in the global order
-    k_shard_publish_runs<<<1, 32, 0, st>>>(e->shard.peers, me, world, seq);
-    k_shard_wait_runs<<<1, 32, 0, st>>>(shard_hdr(e->shard.block.p), world, seq);
-    launches += 2;
+    k_shard_exchange_runs<<<1, 32, 0, st>>>(e->shard.peers, me, world, seq);
+    ++launches;
     e->prof.mark("k_shard_exchange_runs", st);
     if (n) {
         const uint32_t sblocks = (R + kShardScanThreads - 1) / kShardScanThreads;
@@ -590,9 +589,27 @@ extern "C" int gs_sort_sharded_async(gs_engine *e, const gs_sort_params *p) {
     if (q.sort_count > q.render_count) return fail(GS_ERR_BAD_ARG, "sortCount %u > renderCount %u", q.sort_count, q.render_count);
     const uint32_t *d_idx = nullptr;
     e->last_frame_was_graph = false;
+    const uint32_t me = e->cfg.rank, world = e->shard.world;
+    // The split pays only for large windows (three NVLink handshakes + offsets + placement vs a single sort that is
+    // latency bound below ~8 M splats).  Smaller calls are sorted by rank 0 alone; the decision depends only on the call's arguments,
+    // so every rank takes the same branch.  GS_SHARD_MIN overrides the threshold (0 = always split).
+    uint32_t split_min = 8000000u;
+    if (const char *sv = getenv("GS_SHARD_MIN")) split_min = (uint32_t)strtoul(sv, nullptr, 10);
+    if (world == 1 || q.sort_count < split_min) {
+        e->shard.pending = true;
+        e->shard.pending_unsplit = true;
+        e->shard.pending_render_count = q.render_count;
+        if (me != 0) return GS_OK;
+        if ((rc = stage_sort_inputs(e, &q, &d_idx)) ||
+            (rc = sort_on_device(e, d_idx, q.model_view_proj, q.sort_count, q.render_count, q.use_precomputed_distances != 0, false))) {
+            e->shard.pending = false;
+            return rc;
+        }
+        return GS_OK;
+    }
+    e->shard.pending_unsplit = false;
     if ((rc = stage_sort_inputs(e, &q, &d_idx))) return rc;
     cudaStream_t st = e->stream;
-    const uint32_t me = e->cfg.rank, world = e->shard.world;
     const uint32_t s0 = q.render_count - q.sort_count;
     const uint32_t lo = shard_bound(s0, q.sort_count, me, world), hi = shard_bound(s0, q.sort_count, me + 1, world);
     const uint32_t seq = ++e->shard.seq;
@@ -608,18 +625,16 @@ extern "C" int gs_sort_sharded_async(gs_engine *e, const gs_sort_params *p) {
         e->prof.mark("k_depth", st);
     }
     // C1: global min/max over peer memory
-    k_shard_push_minmax<<<1, 32, 0, st>>>(e->shard.peers, e->ctl.p, me, world, seq);
-    k_shard_wait_minmax<<<1, 32, 0, st>>>(shard_hdr(e->shard.block.p), e->ctl.p, world, seq, hi > lo ? 0 : 1);
-    k_shard_runs_init<<<std::min<uint32_t>((e->cfg.distance_map_range + 255) / 256, e->sm_count * 8), 256, 0, st>>>((uint2 *)shard_runs(e->shard.block.p), e->cfg.distance_map_range);
-    launches += 3;
+    k_shard_exchange_minmax<<<1, kShardSyncThreads, 0, st>>>(e->shard.peers, e->ctl.p, me, world, seq, hi > lo ? 0 : 1, (uint2 *)shard_runs(e->shard.block.p),
+                                                             e->cfg.distance_map_range);
+    ++launches;
     e->prof.mark("k_shard_exchange_minmax", st);
     CU(cudaEventRecord(e->ev[EV_DEPTH], st));
     CU(cudaEventRecord(e->ev[EV_BUCKET], st));
     rc = (e->key_bits <= 16) ? shard_local_sort<uint16_t>(e, d_idx, s0, lo, hi, launches) : shard_local_sort<uint32_t>(e, d_idx, s0, lo, hi, launches);
     if (rc) return rc;
-    k_shard_done<<<1, 1, 0, st>>>(e->shard.peers.hdr[0], me, seq);
+    k_shard_done<<<1, 32, 0, st>>>(e->shard.peers, me, world, seq);
     ++launches;
-    if (me == 0) { k_shard_wait_done<<<1, 32, 0, st>>>(shard_hdr(e->shard.block.p), world, seq); ++launches; }
     e->prof.mark("k_shard_done", st);
     CU(cudaEventRecord(e->ev[EV_SORT1], st));
     CU(cudaGetLastError());
@@ -638,9 +653,19 @@ extern "C" int gs_sort_sharded_finish(gs_engine *e, uint32_t *sorted_out, float 
     if (!e->shard.pending) return fail(GS_ERR_NOT_READY, "gs_sort_sharded_finish: nothing pending");
     e->shard.pending = false;
     const uint32_t rcnt = e->shard.pending_render_count;
+    if (e->shard.pending_unsplit && e->cfg.rank != 0) {   // rank 0 sorted alone
+        if (sort_time_ms) *sort_time_ms = 0.f;
+        return GS_OK;
+    }
     CU(cudaEventRecord(e->ev[EV_D2H0], e->stream));
     if (sorted_out && rcnt && e->cfg.rank == 0) CU(cudaMemcpyAsync(sorted_out, e->sorted.p, (size_t)rcnt * 4, cudaMemcpyDeviceToHost, e->stream));
     CU(cudaEventRecord(e->ev[EV_D2H1], e->stream));
+    if (e->shard.pending_unsplit) {
+        rc = finish_sort(e, sort_time_ms);
+        cudaEventElapsedTime(&e->tm.h2d_ms, e->ev[EV_H2D0], e->ev[EV_H2D1]);
+        cudaEventElapsedTime(&e->tm.d2h_ms, e->ev[EV_D2H0], e->ev[EV_D2H1]);
+        return rc;
+    }
     CU(cudaMemcpyAsync(e->h_ctl.p + 32, e->shard.block.p, sizeof(ShardHeader), cudaMemcpyDeviceToHost, e->stream));
     rc = finish_sort(e, sort_time_ms);
     cudaEventElapsedTime(&e->tm.h2d_ms, e->ev[EV_H2D0], e->ev[EV_H2D1]);

@@ -51,40 +51,42 @@ __device__ __forceinline__ bool wait_all_ranks(const uint32_t *flags, uint32_t w
     return __all_sync(0xffffffffu, ok);
 }
 
-// C1, send: my (min, max) into slot `me` of every rank's block
-__global__ void k_shard_push_minmax(ShardPeers peers, const SortControl *ctl, uint32_t me, uint32_t world, uint32_t seq) {
-    if (threadIdx.x < world) {
-        ShardHeader *h = peers.hdr[threadIdx.x];
-        h->mm[me][0] = ctl->dmin;
-        h->mm[me][1] = ctl->dmax;
-        __threadfence_system();
-        st_release_sys_u32(&h->mm_seq[me], seq);
+constexpr int kShardSyncThreads = 256;
+
+// C1: my (min, max) into slot `me` of every rank's block; wait for all N pairs in mine; the global min/max replaces the local one in
+// the control block (k_bucket reads it there).  Every peer having announced sort `seq` also means it has finished reading my run table
+// of sort seq-1 (stream order on its side), so the table is reset here, by the whole CTA, for this sort.
+__global__ void __launch_bounds__(kShardSyncThreads)
+k_shard_exchange_minmax(ShardPeers peers, SortControl *ctl, uint32_t me, uint32_t world, uint32_t seq, int reset_error, uint2 *runs, uint32_t R) {
+    ShardHeader *own = peers.hdr[me];
+    if (threadIdx.x < 32) {
+        if (threadIdx.x < world) {
+            ShardHeader *h = peers.hdr[threadIdx.x];
+            h->mm[me][0] = ctl->dmin;
+            h->mm[me][1] = ctl->dmax;
+            __threadfence_system();
+            st_release_sys_u32(&h->mm_seq[me], seq);
+        }
+        const bool ok = wait_all_ranks(own->mm_seq, world, seq);
+        int32_t lo = 2147483640, hi = -2147483640;   // sorter.cpp:24-25 seeds: an empty slice contributes nothing
+        if (threadIdx.x < world) { lo = own->mm[threadIdx.x][0]; hi = own->mm[threadIdx.x][1]; }
+        lo = warp_min(lo);
+        hi = warp_max(hi);
+        if (threadIdx.x == 0) {
+            ctl->dmin = lo;
+            ctl->dmax = hi;
+            if (reset_error) ctl->error = 0;   // empty slice: k_depth, which clears it otherwise, did not run
+            if (!ok) own->timeout = 1;
+        }
     }
+    __syncthreads();
+    for (uint32_t k = threadIdx.x; k < R; k += kShardSyncThreads) runs[k] = make_uint2(0xffffffffu, 0u);
 }
-// C1, receive: all pairs are in my block -> the global min/max replaces the local one in the control block (k_bucket reads it there)
-__global__ void k_shard_wait_minmax(ShardHeader *own, SortControl *ctl, uint32_t world, uint32_t seq, int reset_error) {
-    const bool ok = wait_all_ranks(own->mm_seq, world, seq);
-    int32_t lo = 2147483640, hi = -2147483640;   // sorter.cpp:24-25 seeds: an empty slice contributes nothing
-    if (threadIdx.x < world) { lo = own->mm[threadIdx.x][0]; hi = own->mm[threadIdx.x][1]; }
-    lo = warp_min(lo);
-    hi = warp_max(hi);
-    if (threadIdx.x == 0) {
-        ctl->dmin = lo;
-        ctl->dmax = hi;
-        if (reset_error) ctl->error = 0;   // empty slice: k_depth, which clears it otherwise, did not run
-        if (!ok) own->timeout = 1;
-    }
-}
-// every peer has started sort `seq` (it sent its min/max), hence finished reading my runs of sort seq-1: safe to reset them now
-__global__ void k_shard_runs_init(uint2 *runs, uint32_t R) {
-    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < R; k += gridDim.x * blockDim.x) runs[k] = make_uint2(0xffffffffu, 0u);
-}
-// C2, send: my runs are complete (previous kernels of this stream)
-__global__ void k_shard_publish_runs(ShardPeers peers, uint32_t me, uint32_t world, uint32_t seq) {
+// C2: my runs are complete (previous kernels of this stream) -> tell everybody, then wait for everybody's
+__global__ void k_shard_exchange_runs(ShardPeers peers, uint32_t me, uint32_t world, uint32_t seq) {
     __threadfence_system();
     if (threadIdx.x < world) st_release_sys_u32(&peers.hdr[threadIdx.x]->runs_seq[me], seq);
-}
-__global__ void k_shard_wait_runs(ShardHeader *own, uint32_t world, uint32_t seq) {
+    ShardHeader *own = peers.hdr[me];
     const bool ok = wait_all_ranks(own->runs_seq, world, seq);
     if (threadIdx.x == 0 && !ok) own->timeout = 1;
 }
@@ -139,15 +141,16 @@ k_shard_place(const KeyT *__restrict__ keys_sorted, const uint32_t *__restrict__
               uint32_t *__restrict__ out /* rank 0's sorted + sortStart */) {
     for (uint32_t j = blockIdx.x * 256u + threadIdx.x; j < n; j += gridDim.x * 256u) out[j + delta[(uint32_t)keys_sorted[j]]] = vals_sorted[j];
 }
-// my elements are in rank 0's buffer
-__global__ void k_shard_done(ShardHeader *root, uint32_t me, uint32_t seq) {
+// my elements are in rank 0's buffer; rank 0 then waits for everybody's
+__global__ void k_shard_done(ShardPeers peers, uint32_t me, uint32_t world, uint32_t seq) {
     __threadfence_system();
-    st_release_sys_u32(&root->done_seq[me], seq);
-}
-__global__ void k_shard_wait_done(ShardHeader *own, uint32_t world, uint32_t seq) {
-    const bool ok = wait_all_ranks(own->done_seq, world, seq);
-    if (threadIdx.x == 0 && !ok) own->timeout = 1;
-    __threadfence_system();
+    if (threadIdx.x == 0) st_release_sys_u32(&peers.hdr[0]->done_seq[me], seq);
+    if (me == 0) {
+        ShardHeader *own = peers.hdr[0];
+        const bool ok = wait_all_ranks(own->done_seq, world, seq);
+        if (threadIdx.x == 0 && !ok) own->timeout = 1;
+        __threadfence_system();
+    }
 }
 
 } // namespace gs

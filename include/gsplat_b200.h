@@ -254,7 +254,9 @@ GS_API int gs_peer_attach(gs_engine *e, const void *frame_handle, const void *sy
  *   setup    every rank: gs_shard_export -> exchange the handles (any transport) -> gs_shard_attach with all N block handles
  *            (index = rank) and rank 0's sorted handle.  gs_shard_attach_local: engines of one process on one device.
  *   per sort every rank calls gs_sort_sharded with the SAME parameters; sorted_out is filled on rank 0 only (may be NULL elsewhere).
- *            _async enqueues and returns; _finish waits, copies, reports errors (a missing peer gives GS_ERR_CUDA after ~2 s).   */
+ *            _async enqueues and returns; _finish waits, copies, reports errors (a missing peer gives GS_ERR_CUDA after ~2 s).
+ *   Windows below 8 M splats (env GS_SHARD_MIN overrides; 0 = always split) are sorted by rank 0 alone -- the single-GPU sort is
+ *   latency bound there and the exchange would cost more than it saves; the other ranks' calls then return at once.            */
 #define GS_MAX_SHARD_RANKS 8
 GS_API int gs_shard_export(gs_engine *e, void *block_handle /*64 B out*/, void *sorted_handle /*64 B out*/);
 GS_API int gs_shard_attach(gs_engine *e, uint32_t world, const void *block_handles /* world x 64 B */, const void *root_sorted_handle);

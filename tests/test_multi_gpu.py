@@ -252,10 +252,11 @@ SHARD_CASES = [
 @pytest.mark.gpu
 @pytest.mark.parametrize("world", [2, 3])
 @pytest.mark.parametrize("name,kw", SHARD_CASES)
-def test_sharded_sort_engines_on_one_device(gs, oracle_mod, world, name, kw):
+def test_sharded_sort_engines_on_one_device(gs, oracle_mod, monkeypatch, world, name, kw):
     """N engines on one GPU, each sorting its slice of input positions and storing into engine 0's sortedIndexes: the assembled order
     must be bit-identical to the reference's single sort.  (The multi-process variant differs only in how the peers' memory is mapped.)"""
     import cases
+    monkeypatch.setenv("GS_SHARD_MIN", "0")     # always split (the default splits only windows of >= 8 M splats)
     c = cases.sort_case(**kw)
     R = 1 << 16
     want = oracle_mod.port_sort_indexes(*cases.call_args(c, R))
@@ -282,6 +283,29 @@ def test_sharded_sort_engines_on_one_device(gs, oracle_mod, world, name, kw):
             e.close()
 
 
+@pytest.mark.gpu
+def test_sharded_sort_below_threshold_is_sorted_by_rank0(gs, oracle_mod, monkeypatch):
+    """Default threshold: a small window is not worth the exchange, so rank 0 sorts it alone and the other ranks' calls are no-ops."""
+    import cases
+    monkeypatch.delenv("GS_SHARD_MIN", raising=False)
+    c = cases.sort_case(seed=41, n=100_000, index_kind="shuffled")
+    R = 1 << 16
+    want = oracle_mod.port_sort_indexes(*cases.call_args(c, R))
+    engines = [gs.Engine(c["splat_count"], distance_map_range=R, rank=g, world_size=2) for g in range(2)]
+    try:
+        for e in engines:
+            e.upload_centers(c["centers"])
+            e.shard_attach_local(engines)
+        for e in engines:
+            e.sort_sharded_async(c["mvp"], c["sort_count"], c["render_count"], c["indexes"])
+        _, ms1 = engines[1].sort_sharded_finish(None)
+        out, ms0 = engines[0].sort_sharded_finish(np.empty(c["render_count"], np.uint32))
+        assert np.array_equal(out, want) and ms1 == 0.0 and ms0 > 0.0
+    finally:
+        for e in engines:
+            e.close()
+
+
 def _shard_worker(rank, world, port, q):
     import torch
     import torch.distributed as dist
@@ -292,6 +316,7 @@ def _shard_worker(rank, world, port, q):
     import gaussiansplats3d_b200 as gs
     from gaussiansplats3d_b200.parallel import ShardedSort
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    os.environ["GS_SHARD_MIN"] = "0"            # always split
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     ok = True

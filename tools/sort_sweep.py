@@ -20,9 +20,12 @@ def main():
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--cpu", action="store_true")
     ap.add_argument("--shuffled", action="store_true")
+    ap.add_argument("--auto-split", action="store_true", help="torchrun mode: keep the engine's split threshold (default: always split, GS_SHARD_MIN=0)")
     a = ap.parse_args()
     import os
     if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        if not a.auto_split:
+            os.environ["GS_SHARD_MIN"] = "0"
         return main_sharded(a)
     import cases
     import gaussiansplats3d_b200 as gs
@@ -111,7 +114,7 @@ def main_sharded(a):
         if rank == 0:
             ms = float(np.median(times[2:]))
             print(json.dumps({"splats": n, "gpus": world, "indexes": "shuffled" if a.shuffled else "identity", "sort_ms": ms, "msplats_per_s": n / ms / 1e3,
-                              "bit_exact_vs_single_gpu": exact, "exchange": "peer memory (min/max, run lengths, 4 B/splat into rank 0)"}), flush=True)
+                              "bit_exact_vs_single_gpu": exact, "split": "engine threshold" if a.auto_split else "forced", "exchange": "peer memory (min/max, run lengths, 4 B/splat into rank 0)"}), flush=True)
     dist.destroy_process_group()
 
 

@@ -193,7 +193,7 @@ extern "C" int gs_create(const gs_config *cfg, gs_engine **out) {
     const size_t n = std::max<uint32_t>(c.max_splat_count, 1);
     if ((rc = e->centers.ensure(n)) || (rc = e->indexes.ensure(n)) || (rc = e->dist.ensure(n)) || (rc = e->sorted.ensure(n)) ||
         (rc = e->vals[0].ensure(n)) || (rc = e->vals[1].ensure(n)) || (rc = e->keys[0].ensure(n)) || (rc = e->keys[1].ensure(n)) ||
-        (rc = e->ctl.ensure(1)) || (rc = e->depthp.ensure(1)) || (rc = e->transforms.ensure(16 * GS_MAX_SCENES)) || (rc = e->h_ctl.ensure(sizeof(SortControl) / 4 + 64))) {
+        (rc = e->ctl.ensure(1)) || (rc = e->depthp.ensure(1)) || (rc = e->transforms.ensure(16 * GS_MAX_SCENES)) || (rc = e->h_ctl.ensure(sizeof(SortControl) / 4 + 64 + sizeof(RasterControl) / 4 + sizeof(ShardHeader) / 4))) {
         gs_destroy(e);
         return rc;
     }
@@ -666,12 +666,12 @@ extern "C" int gs_sort_sharded_finish(gs_engine *e, uint32_t *sorted_out, float 
         cudaEventElapsedTime(&e->tm.d2h_ms, e->ev[EV_D2H0], e->ev[EV_D2H1]);
         return rc;
     }
-    CU(cudaMemcpyAsync(e->h_ctl.p + 32, e->shard.block.p, sizeof(ShardHeader), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaMemcpyAsync(e->h_ctl.p + 640, e->shard.block.p, sizeof(ShardHeader), cudaMemcpyDeviceToHost, e->stream));
     rc = finish_sort(e, sort_time_ms);
     cudaEventElapsedTime(&e->tm.h2d_ms, e->ev[EV_H2D0], e->ev[EV_H2D1]);
     cudaEventElapsedTime(&e->tm.d2h_ms, e->ev[EV_D2H0], e->ev[EV_D2H1]);
     ShardHeader hd;
-    memcpy(&hd, e->h_ctl.p + 32, sizeof(hd));
+    memcpy(&hd, e->h_ctl.p + 640, sizeof(hd));
     if (hd.timeout) {
         cudaMemsetAsync(&shard_hdr(e->shard.block.p)->timeout, 0, 4, e->stream);
         e->ctl_dirty = true;
@@ -848,7 +848,9 @@ static int finish_render(gs_engine *e, const gs_render_params *p, void *frame_ou
     RasterControl rc;
     memcpy(&rc, e->h_ctl.p + 16, sizeof(rc));
     e->tm.tile_instances = rc.total_instances;
-    e->tm.visible_splats = rc.visible;
+    uint32_t vis = 0;
+    for (int i = 0; i < kVisibleSlots; ++i) vis += rc.visible_slots[i * 8];
+    e->tm.visible_splats = vis;
     if (rc.peer_timeout) return fail(GS_ERR_CUDA, "multi-GPU tile gather: a peer did not arrive within the time limit (ranks must render the same frames)");
     if (rc.overflow) return fail(GS_ERR_CAPACITY, "tile-instance buffer overflow: %llu instances needed, capacity %llu (raise GS_INSTANCE_FACTOR)",
                                  (unsigned long long)rc.total_instances, (unsigned long long)e->rs.instance_capacity);

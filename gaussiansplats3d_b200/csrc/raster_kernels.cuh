@@ -28,6 +28,7 @@ struct __align__(16) SplatRecord {     // 48 bytes, read as 3 x 16 B
     float ndc_z;                       // outside [-1,1] (2.0 for culled splats) <=> not drawn
 };
 
+constexpr int kVisibleSlots = 64;
 struct RasterControl {
     unsigned long long total_instances;
     uint32_t overflow;
@@ -37,6 +38,9 @@ struct RasterControl {
     uint32_t peer_timeout;   // a peer handshake gave up waiting
     uint32_t pad[1];
     unsigned long long subset_count;   // sharded frames: splats whose rect touches one of this rank's coarse tiles
+    // visible-splat statistic, spread over 64 counters 32 B apart: one counter took ~1.6 ns per same-address atomic, which at one atomic
+    // per warp WAS the duration of k_project (16 M splats: 500 K atomics = 0.79 ms; 1.2 M: 26 K = 41 us of a 37 us kernel)
+    uint32_t visible_slots[kVisibleSlots * 8];
 };
 
 // Block in rank 0's memory that the other ranks map through CUDA IPC: the fused tile gather's handshake.
@@ -378,7 +382,7 @@ k_project(const uint4 *__restrict__ cc, const void *__restrict__ cov, const void
         }
     }
     const uint32_t nvis = __popc(__ballot_sync(0xffffffffu, visible));
-    if ((threadIdx.x & 31) == 0 && nvis) atomicAdd(&rctl->visible, nvis);
+    if ((threadIdx.x & 31) == 0 && nvis) atomicAdd(&rctl->visible_slots[((blockIdx.x * (kProjThreads / 32) + (threadIdx.x >> 5)) & (kVisibleSlots - 1)) * 8], nvis);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -434,11 +438,22 @@ constexpr int kBinThreads = 256;
 constexpr int kBinItems = 2;
 constexpr int kBinTile = kBinThreads * kBinItems;   // draw ranks per CTA
 
+// This thread's share of "instances of all chunks before mine": whole groups of kBinThreads chunks from the second-level sums,
+// the chunks of my own group one per thread.
+__device__ __forceinline__ unsigned long long chunk_prefix(const uint32_t *__restrict__ block_sums, const uint32_t *__restrict__ super_sums) {
+    const uint32_t grp = blockIdx.x / kBinThreads;
+    unsigned long long before = 0;
+    for (uint32_t g = threadIdx.x; g < grp; g += kBinThreads) before += super_sums[g];
+    const uint32_t b = grp * kBinThreads + threadIdx.x;
+    if (b < blockIdx.x) before += block_sums[b];
+    return before;
+}
+
 // pass 1: instances per warp (256 consecutive draw ranks) and per CTA chunk (rank p = 0 is the NEAREST splat = last in the
 // reference's draw order).  Warp-striped like pass 2: warp w of a CTA owns ranks [chunk + 256 w, +256), item k of lane l = +32k + l.
 __global__ void __launch_bounds__(kBinThreads)
 k_tile_count(const uint32_t *__restrict__ order, uint32_t render_count_host, const unsigned long long *__restrict__ n_dev,
-             const ushort4 *__restrict__ rects, uint32_t *__restrict__ block_sums, uint32_t *__restrict__ warp_sums, RasterControl *rctl,
+             const ushort4 *__restrict__ rects, uint32_t *__restrict__ block_sums, uint32_t *__restrict__ warp_sums, uint32_t *__restrict__ super_sums,
              OwnMask own, int sharded) {
     const uint32_t render_count = n_dev ? (uint32_t)*n_dev : render_count_host;
     __shared__ uint32_t s_w[kBinThreads / 32];
@@ -459,7 +474,7 @@ k_tile_count(const uint32_t *__restrict__ order, uint32_t render_count_host, con
 #pragma unroll
         for (int w = 0; w < kBinThreads / 32; ++w) total += s_w[w];
         block_sums[blockIdx.x] = total;
-        atomicAdd(&rctl->total_instances, (unsigned long long)total);
+        if (total) atomicAdd(&super_sums[blockIdx.x / kBinThreads], total);   // second level: one counter per kBinThreads chunks
     }
 }
 
@@ -467,21 +482,23 @@ k_tile_count(const uint32_t *__restrict__ order, uint32_t render_count_host, con
 // per-thread arrays): the warp's base offset comes from pass 1's sums, the offsets inside an item from a warp scan.
 __global__ void __launch_bounds__(kBinThreads)
 k_tile_emit(const uint32_t *__restrict__ order, uint32_t render_count_host, const unsigned long long *__restrict__ n_dev,
-            const ushort4 *__restrict__ rects, const uint32_t *__restrict__ block_sums, const uint32_t *__restrict__ warp_sums, int coarse_x,
+            const ushort4 *__restrict__ rects, const uint32_t *__restrict__ block_sums, const uint32_t *__restrict__ warp_sums,
+            const uint32_t *__restrict__ super_sums, int coarse_x,
             uint16_t *__restrict__ keys, unsigned long long *__restrict__ vals, unsigned long long capacity, RasterControl *rctl, OwnMask own,
             int sharded) {
     const uint32_t render_count = n_dev ? (uint32_t)*n_dev : render_count_host;
     __shared__ unsigned long long s_prefix;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // instances of all earlier chunks
-    unsigned long long before = 0;
-    for (uint32_t b = threadIdx.x; b < blockIdx.x; b += kBinThreads) before += block_sums[b];
+    // two levels (a flat sum over all earlier chunks is quadratic in the chunk count: 16 M splats = 31 K chunks = 0.5 G reads)
+    unsigned long long before = chunk_prefix(block_sums, super_sums);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(0xffffffffu, before, o);
     if (threadIdx.x == 0) s_prefix = 0;
     __syncthreads();
     if (lane == 0 && before) atomicAdd(&s_prefix, before);
     __syncthreads();
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) rctl->total_instances = s_prefix + block_sums[blockIdx.x];   // read by the tile sort
     unsigned long long w0 = s_prefix;
     for (int w = 0; w < warp; ++w) w0 += warp_sums[blockIdx.x * (kBinThreads / 32) + w];
     const uint32_t run = blockIdx.x * kBinTile + (uint32_t)warp * (32 * kBinItems) + lane;
@@ -576,7 +593,7 @@ k_tile_emit(const uint32_t *__restrict__ order, uint32_t render_count_host, cons
 // pass 1: survivors per warp / chunk of input positions;  pass 2: order-preserving compaction of (index, distance).
 __global__ void __launch_bounds__(kBinThreads)
 k_subset_count(const uint32_t *__restrict__ indexes, uint32_t count, const ushort4 *__restrict__ rects, OwnMask own,
-               uint32_t *__restrict__ block_sums, uint32_t *__restrict__ warp_sums, RasterControl *rctl) {
+               uint32_t *__restrict__ block_sums, uint32_t *__restrict__ warp_sums, uint32_t *__restrict__ super_sums) {
     __shared__ uint32_t s_w[kBinThreads / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t run = blockIdx.x * kBinTile + (uint32_t)warp * (32 * kBinItems) + lane;
@@ -595,23 +612,23 @@ k_subset_count(const uint32_t *__restrict__ indexes, uint32_t count, const ushor
 #pragma unroll
         for (int w = 0; w < kBinThreads / 32; ++w) total += s_w[w];
         block_sums[blockIdx.x] = total;
-        atomicAdd(&rctl->subset_count, (unsigned long long)total);
+        if (total) atomicAdd(&super_sums[blockIdx.x / kBinThreads], total);
     }
 }
 __global__ void __launch_bounds__(kBinThreads)
 k_subset_emit(const uint32_t *__restrict__ indexes, uint32_t count, const ushort4 *__restrict__ rects, OwnMask own,
-              const uint32_t *__restrict__ block_sums, const uint32_t *__restrict__ warp_sums, const int32_t *__restrict__ dist,
-              uint32_t *__restrict__ sub_idx, int32_t *__restrict__ sub_dist) {
+              const uint32_t *__restrict__ block_sums, const uint32_t *__restrict__ warp_sums, const uint32_t *__restrict__ super_sums,
+              const int32_t *__restrict__ dist, uint32_t *__restrict__ sub_idx, int32_t *__restrict__ sub_dist, RasterControl *rctl) {
     __shared__ uint32_t s_prefix;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t before = 0;
-    for (uint32_t b = threadIdx.x; b < blockIdx.x; b += kBinThreads) before += block_sums[b];
+    uint32_t before = (uint32_t)chunk_prefix(block_sums, super_sums);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(0xffffffffu, before, o);
     if (threadIdx.x == 0) s_prefix = 0;
     __syncthreads();
     if (lane == 0 && before) atomicAdd(&s_prefix, before);
     __syncthreads();
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) rctl->subset_count = (unsigned long long)s_prefix + block_sums[blockIdx.x];   // n of this rank's sort
     uint32_t w0 = s_prefix;
     for (int w = 0; w < warp; ++w) w0 += warp_sums[blockIdx.x * (kBinThreads / 32) + w];
     const uint32_t run = blockIdx.x * kBinTile + (uint32_t)warp * (32 * kBinItems) + lane;
@@ -634,7 +651,7 @@ k_subset_emit(const uint32_t *__restrict__ indexes, uint32_t count, const ushort
     }
 }
 
-__global__ void k_raster_init(RasterControl *rctl, SortControl *ctl, uint2 *ranges, uint32_t ntiles) {
+__global__ void k_raster_init(RasterControl *rctl, SortControl *ctl, uint2 *ranges, uint32_t ntiles, uint32_t *super_sums, uint32_t nsuper) {
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     if (tid == 0) {
@@ -646,6 +663,8 @@ __global__ void k_raster_init(RasterControl *rctl, SortControl *ctl, uint2 *rang
     uint32_t *h = &ctl->hist[0][0];
     for (size_t i = tid; i < 4 * kRadix; i += stride) h[i] = 0;
     for (size_t i = tid; i < ntiles; i += stride) ranges[i] = make_uint2(0xffffffffu, 0u); // empty: first > last
+    for (size_t i = tid; i < (size_t)kVisibleSlots * 8; i += stride) rctl->visible_slots[i] = 0;
+    for (size_t i = tid; i < nsuper; i += stride) super_sums[i] = 0;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -831,6 +850,8 @@ struct RasterState {
     RBuf<ushort4> rects;
     RBuf<uint32_t> block_sums; // coarse instances per chunk of draw ranks
     RBuf<uint32_t> warp_sums;  // ... and per warp (256 draw ranks) inside the chunk
+    RBuf<uint32_t> super_sums; // ... and per group of kBinThreads chunks: [0, S) binning, [S, 2S) subset compaction
+    uint32_t super_stride = 0;
     RBuf<uint16_t> ikeys[2];   // instance keys ping/pong (coarse tile ids)
     RBuf<unsigned long long> ivals[2];   // instance values ping/pong: {fine-tile mask, splat id}
     RBuf<unsigned long long> list;       // final per-coarse-tile lists
@@ -876,6 +897,8 @@ static int raster_init(RasterState &rs, const gs_config &c, int sm_count) {
         RCU(rs.rects.ensure(n));
         RCU(rs.block_sums.ensure((n + kBinTile - 1) / kBinTile + 1));
         RCU(rs.warp_sums.ensure(((n + kBinTile - 1) / kBinTile + 1) * (kBinThreads / 32)));
+        rs.super_stride = (uint32_t)(((n + kBinTile - 1) / kBinTile) / kBinThreads + 2);
+        RCU(rs.super_sums.ensure(2 * (size_t)rs.super_stride));
         const char *f = getenv("GS_INSTANCE_FACTOR");
         const double factor = f ? atof(f) : 4.0;
         const size_t tiles = (size_t)((c.max_width + kTile - 1) / kTile) * ((c.max_height + kTile - 1) / kTile);
@@ -892,7 +915,7 @@ static int raster_init(RasterState &rs, const gs_config &c, int sm_count) {
 
 static void raster_release(RasterState &rs) {
     rs.cc.release(); rs.cov.release(); rs.sh.release(); rs.scene_idx.release(); rs.records.release(); rs.rects.release();
-    rs.block_sums.release(); rs.warp_sums.release(); rs.ikeys[0].release(); rs.ikeys[1].release(); rs.ivals[0].release(); rs.ivals[1].release();
+    rs.block_sums.release(); rs.warp_sums.release(); rs.super_sums.release(); rs.ikeys[0].release(); rs.ikeys[1].release(); rs.ivals[0].release(); rs.ivals[1].release();
     rs.list.release(); rs.ranges.release(); rs.rctl.release(); rs.sctl.release(); rs.lookback.release();
     rs.dyn.release(); rs.projp.release(); rs.frame.release(); rs.peer_sync_local.release(); rs.exported.release();
 }
@@ -994,7 +1017,7 @@ static int raster_render(RasterState &rs, const gs_config &c, const gs_uniforms 
     while ((1u << tile_bits) < std::max(ncoarse, 2u)) ++tile_bits;
     const PassPlan pl = make_plan_bits(tile_bits);
     if (phases & 1) {
-        k_raster_init<<<8, 256, 0, st>>>(rs.rctl.p, rs.sctl.p, rs.ranges.p, ncoarse);
+        k_raster_init<<<8, 256, 0, st>>>(rs.rctl.p, rs.sctl.p, rs.ranges.p, ncoarse, rs.super_sums.p, 2 * rs.super_stride);
         ++launches;
         prof.mark("k_raster_init", st);
         const uint32_t count = rs.uploaded;
@@ -1006,10 +1029,10 @@ static int raster_render(RasterState &rs, const gs_config &c, const gs_uniforms 
     if (!(phases & 2)) { tm.kernel_launches = launches; return GS_OK; }
     if (p.render_count && local_tiles) {
         const uint32_t chunks = (p.render_count + kBinTile - 1) / kBinTile;
-        k_tile_count<<<chunks, kBinThreads, 0, st>>>(d_order, p.render_count, order_count_dev, rs.rects.p, rs.block_sums.p, rs.warp_sums.p, rs.rctl.p, make_own_mask(rank, world), world > 1 ? 1 : 0);
+        k_tile_count<<<chunks, kBinThreads, 0, st>>>(d_order, p.render_count, order_count_dev, rs.rects.p, rs.block_sums.p, rs.warp_sums.p, rs.super_sums.p, make_own_mask(rank, world), world > 1 ? 1 : 0);
         ++launches;
         prof.mark("k_tile_count", st);
-        k_tile_emit<<<chunks, kBinThreads, 0, st>>>(d_order, p.render_count, order_count_dev, rs.rects.p, rs.block_sums.p, rs.warp_sums.p, coarse_x, rs.ikeys[0].p, rs.ivals[0].p,
+        k_tile_emit<<<chunks, kBinThreads, 0, st>>>(d_order, p.render_count, order_count_dev, rs.rects.p, rs.block_sums.p, rs.warp_sums.p, rs.super_sums.p, coarse_x, rs.ikeys[0].p, rs.ivals[0].p,
                                                    rs.instance_capacity, rs.rctl.p, make_own_mask(rank, world), world > 1 ? 1 : 0);
         ++launches;
         prof.mark("k_tile_emit", st);
@@ -1056,10 +1079,10 @@ static int raster_subset(RasterState &rs, const gs_config &c, const uint32_t *d_
                          int32_t *sub_dist, cudaStream_t st, Profiler &prof, uint32_t &launches) {
     const uint32_t chunks = (count + kBinTile - 1) / kBinTile;
     const OwnMask own = make_own_mask(c.rank, c.world_size);
-    k_subset_count<<<chunks, kBinThreads, 0, st>>>(d_indexes, count, rs.rects.p, own, rs.block_sums.p, rs.warp_sums.p, rs.rctl.p);
+    k_subset_count<<<chunks, kBinThreads, 0, st>>>(d_indexes, count, rs.rects.p, own, rs.block_sums.p, rs.warp_sums.p, rs.super_sums.p + rs.super_stride);
     ++launches;
     prof.mark("k_subset_count", st);
-    k_subset_emit<<<chunks, kBinThreads, 0, st>>>(d_indexes, count, rs.rects.p, own, rs.block_sums.p, rs.warp_sums.p, dist, sub_idx, sub_dist);
+    k_subset_emit<<<chunks, kBinThreads, 0, st>>>(d_indexes, count, rs.rects.p, own, rs.block_sums.p, rs.warp_sums.p, rs.super_sums.p + rs.super_stride, dist, sub_idx, sub_dist, rs.rctl.p);
     ++launches;
     prof.mark("k_subset_emit", st);
     return GS_OK;

@@ -108,7 +108,6 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *s
 struct SortControl {
     int32_t dmin, dmax;          // running min / max of the distances (seeds +-2147483640, sorter.cpp:24-25)
     uint32_t error;              // sticky error bits (see kErr*)
-    uint32_t ticket[4];          // dynamic tile ids, one per radix pass
     uint32_t hist[4][kRadix];    // per-pass global digit histograms
 };
 constexpr uint32_t kErrDegenerate = 1u;   // dmax == dmin  (reference: NaN bucket -> wasm trap)

@@ -108,7 +108,7 @@ struct gs_engine {
     DevBuf<float> transforms;        // 32 x mat4
     DevBuf<SortControl> ctl;
     DevBuf<DepthParams> depthp;      // per-frame depth parameters (device copy read by k_depth)
-    DevBuf<uint32_t> lookback;       // radix tile histograms / offsets [pass][digit][tile]
+    DevBuf<uint32_t> tile_hist;       // radix tile histograms / offsets [pass][digit][tile]
     DevBuf<uint32_t> freq;           // scratch reproduction for gs_sort_indexes
     DevBuf<uint32_t> sub_idx;        // sharded frames: this rank's subset of the sort input (index, distance)
     DevBuf<int32_t> sub_dist;
@@ -217,7 +217,7 @@ extern "C" void gs_destroy(gs_engine *e) {
     if (e->stream) cudaStreamSynchronize(e->stream);
     e->centers.release(); e->scene_idx.release(); e->indexes.release(); e->precomputed.release(); e->dist.release();
     e->keys[0].release(); e->keys[1].release(); e->vals[0].release(); e->vals[1].release(); e->sorted.release();
-    e->transforms.release(); e->ctl.release(); e->depthp.release(); e->lookback.release(); e->freq.release(); e->sub_idx.release(); e->sub_dist.release();
+    e->transforms.release(); e->ctl.release(); e->depthp.release(); e->tile_hist.release(); e->freq.release(); e->sub_idx.release(); e->sub_dist.release();
     e->h_indexes.release(); e->h_sorted.release(); e->h_ctl.release(); e->h_frame.release(); e->flush.release(); e->prof.release();
     e->shard.block.release(); e->shard.total.release(); e->shard.ahead.release(); e->shard.block_total.release(); e->shard.delta.release(); e->shard.local_sorted.release();
     for (void *m : e->shard.opened) if (m) cudaIpcCloseMemHandle(m);
@@ -291,7 +291,7 @@ static int sort_on_device(gs_engine *e, const uint32_t *d_indexes, const float *
     const PassPlan pl = make_plan_bits(e->key_bits);
     uint32_t launches = 0;
     uint32_t stride = 0;
-    int rc = e->lookback.ensure(radix_tile_hist_words(std::max(n, 1u), pl.npasses, &stride));
+    int rc = e->tile_hist.ensure(radix_tile_hist_words(std::max(n, 1u), pl.npasses, &stride));
     if (rc) return rc;
     if (!capturing) CU(cudaEventRecord(e->ev[EV_SORT0], st));
     if (!e->have_prof_begin) e->prof.begin(st);
@@ -325,19 +325,19 @@ static int sort_on_device(gs_engine *e, const uint32_t *d_indexes, const float *
                                          {"k_radix_scan[depth,0]", "k_radix_scan[depth,1]", "k_radix_scan[depth,2]", "k_radix_scan[depth,3]"},
                                          {"k_radix_scatter[depth,0]", "k_radix_scatter[depth,1]", "k_radix_scatter[depth,2]", "k_radix_scatter[depth,3]"}};
         if (e->key_bits <= 16) {
-            k_bucket<uint16_t><<<tiles, kRadixThreads, 0, st>>>(dist_sorted, (uint16_t *)e->keys[0].p, n, n_dev, R, pl, write_buckets ? 1 : 0, e->ctl.p, e->lookback.p, stride);
+            k_bucket<uint16_t><<<tiles, kRadixThreads, 0, st>>>(dist_sorted, (uint16_t *)e->keys[0].p, n, n_dev, R, pl, write_buckets ? 1 : 0, e->ctl.p, e->tile_hist.p, stride);
             ++launches;
             e->prof.mark("k_bucket", st);
             if (!capturing) CU(cudaEventRecord(e->ev[EV_BUCKET], st));
             radix_sort_pairs<uint16_t, uint32_t>((uint16_t *)e->keys[0].p, (uint16_t *)e->keys[1].p, vsrc, render_count - 1u, vmode, e->vals[0].p, e->vals[1].p,
-                                       e->sorted.p + s0, n, n_dev, (unsigned long long)n, pl, e->ctl.p, e->lookback.p, stride, true, nullptr, st, launches, &e->prof, names, true);
+                                       e->sorted.p + s0, n, n_dev, (unsigned long long)n, pl, e->ctl.p, e->tile_hist.p, stride, true, nullptr, st, launches, &e->prof, names, true);
         } else {
-            k_bucket<uint32_t><<<tiles, kRadixThreads, 0, st>>>(dist_sorted, e->keys[0].p, n, n_dev, R, pl, write_buckets ? 1 : 0, e->ctl.p, e->lookback.p, stride);
+            k_bucket<uint32_t><<<tiles, kRadixThreads, 0, st>>>(dist_sorted, e->keys[0].p, n, n_dev, R, pl, write_buckets ? 1 : 0, e->ctl.p, e->tile_hist.p, stride);
             ++launches;
             e->prof.mark("k_bucket", st);
             if (!capturing) CU(cudaEventRecord(e->ev[EV_BUCKET], st));
             radix_sort_pairs<uint32_t, uint32_t>(e->keys[0].p, e->keys[1].p, vsrc, render_count - 1u, vmode, e->vals[0].p, e->vals[1].p, e->sorted.p + s0, n,
-                                       n_dev, (unsigned long long)n, pl, e->ctl.p, e->lookback.p, stride, true, nullptr, st, launches, &e->prof, names, true);
+                                       n_dev, (unsigned long long)n, pl, e->ctl.p, e->tile_hist.p, stride, true, nullptr, st, launches, &e->prof, names, true);
         }
     } else if (!capturing) {
         CU(cudaEventRecord(e->ev[EV_DEPTH], st));
@@ -433,7 +433,7 @@ static int shard_prepare(gs_engine *e) {
         return rc;
     // everything the per-sort path could otherwise grow (cudaFree synchronises the device: not while a peer's wait kernel may be spinning)
     const PassPlan pl = make_plan_bits(e->key_bits);
-    if ((rc = e->lookback.ensure(radix_tile_hist_words(std::max(e->cfg.max_splat_count, 1u), pl.npasses, nullptr))) || (rc = e->precomputed.ensure(e->cfg.max_splat_count))) return rc;
+    if ((rc = e->tile_hist.ensure(radix_tile_hist_words(std::max(e->cfg.max_splat_count, 1u), pl.npasses, nullptr))) || (rc = e->precomputed.ensure(e->cfg.max_splat_count))) return rc;
     return GS_OK;
 }
 // CUDA loads a kernel's code on its first launch (lazy module loading) and that load can wait for running kernels to finish.  The
@@ -540,7 +540,7 @@ static int shard_local_sort(gs_engine *e, const uint32_t *d_indexes, uint32_t s0
     const uint32_t n = hi - lo, R = e->cfg.distance_map_range;
     const PassPlan pl = make_plan_bits(e->key_bits);
     uint32_t stride = 0;
-    int rc = e->lookback.ensure(radix_tile_hist_words(std::max(n, 1u), pl.npasses, &stride));
+    int rc = e->tile_hist.ensure(radix_tile_hist_words(std::max(n, 1u), pl.npasses, &stride));
     if (rc) return rc;
     const bool identity = (d_indexes == nullptr);
     static const RadixNames names = {{"k_radix_hist[shard,0]", "k_radix_hist[shard,1]", "k_radix_hist[shard,2]", "k_radix_hist[shard,3]"},
@@ -551,12 +551,12 @@ static int shard_local_sort(gs_engine *e, const uint32_t *d_indexes, uint32_t s0
     KeyT *final_keys = nullptr;
     if (n) {   // slice -> keys with the GLOBAL range map -> local order + per-key runs of that order
         const uint32_t tiles = (n + kRadixTile - 1) / kRadixTile;
-        k_bucket<KeyT><<<tiles, kRadixThreads, 0, st>>>(e->dist.p + lo, (KeyT *)e->keys[0].p, n, nullptr, R, pl, 0, e->ctl.p, e->lookback.p, stride);
+        k_bucket<KeyT><<<tiles, kRadixThreads, 0, st>>>(e->dist.p + lo, (KeyT *)e->keys[0].p, n, nullptr, R, pl, 0, e->ctl.p, e->tile_hist.p, stride);
         ++launches;
         e->prof.mark("k_bucket", st);
         radix_sort_pairs<KeyT, uint32_t>((KeyT *)e->keys[0].p, (KeyT *)e->keys[1].p, identity ? nullptr : d_indexes + lo, hi - 1u,
                                          identity ? kValIotaReversed : kValArrayReversed, e->vals[0].p, e->vals[1].p, e->shard.local_sorted.p, n, nullptr,
-                                         (unsigned long long)n, pl, e->ctl.p, e->lookback.p, stride, true, runs, st, launches, &e->prof, names, true, true, &final_keys);
+                                         (unsigned long long)n, pl, e->ctl.p, e->tile_hist.p, stride, true, runs, st, launches, &e->prof, names, true, true, &final_keys);
     }
     // C2: publish my runs, wait for everybody's, turn them into the offsets of my runs in the global order
     k_shard_exchange_runs<<<1, 32, 0, st>>>(e->shard.peers, me, world, seq);
@@ -931,7 +931,7 @@ static int enqueue_frame(gs_engine *e, const gs_sort_params *s, const gs_uniform
             // buffers that the enqueue path may grow must be sized BEFORE capture (no allocation inside a capture)
             uint32_t stride = 0;
             const PassPlan pl = make_plan_bits(e->key_bits);
-            if ((rc = e->lookback.ensure(radix_tile_hist_words(std::max(q.sort_count, 1u), pl.npasses, &stride)))) return rc;
+            if ((rc = e->tile_hist.ensure(radix_tile_hist_words(std::max(q.sort_count, 1u), pl.npasses, &stride)))) return rc;
             CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
             // fork: the projection does not depend on the draw order, so it runs beside the (latency-bound) depth sort
             CU(cudaEventRecord(e->ev_fork, st));

@@ -33,7 +33,7 @@ struct RasterControl {
     unsigned long long total_instances;
     uint32_t overflow;
     uint32_t visible;
-    uint32_t scan_ticket;
+    uint32_t reserved0;
     uint32_t frame_seq;      // frames rendered so far (never reset): the peer-gather handshake counts in frames
     uint32_t peer_timeout;   // a peer handshake gave up waiting
     uint32_t pad[1];
@@ -655,10 +655,9 @@ __global__ void k_raster_init(RasterControl *rctl, SortControl *ctl, uint2 *rang
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     if (tid == 0) {
-        rctl->total_instances = 0; rctl->overflow = 0; rctl->visible = 0; rctl->scan_ticket = 0; rctl->subset_count = 0;
+        rctl->total_instances = 0; rctl->overflow = 0; rctl->visible = 0; rctl->subset_count = 0;
         rctl->frame_seq += 1;
         ctl->error = 0;
-        for (int i = 0; i < 4; ++i) ctl->ticket[i] = 0;
     }
     uint32_t *h = &ctl->hist[0][0];
     for (size_t i = tid; i < 4 * kRadix; i += stride) h[i] = 0;
@@ -858,7 +857,7 @@ struct RasterState {
     RBuf<uint2> ranges;
     RBuf<RasterControl> rctl;
     RBuf<SortControl> sctl;
-    RBuf<uint32_t> lookback;   // radix tile histograms
+    RBuf<uint32_t> tile_hist;   // radix tile histograms
     RBuf<DynamicUniforms> dyn;
     RBuf<ProjParams> projp;     // per-frame projection parameters (device copy read by k_project)
     RBuf<unsigned char> frame;
@@ -908,7 +907,7 @@ static int raster_init(RasterState &rs, const gs_config &c, int sm_count) {
         RCU(rs.list.ensure(rs.instance_capacity));
         RCU(rs.ranges.ensure(65536));
         RCU(rs.frame.ensure((size_t)c.max_width * (c.max_height + kTile) * 16));
-        RCU(rs.lookback.ensure(radix_tile_hist_words(rs.instance_capacity, 2, &rs.hist_stride)));
+        RCU(rs.tile_hist.ensure(radix_tile_hist_words(rs.instance_capacity, 2, &rs.hist_stride)));
     }
     return GS_OK;
 }
@@ -916,7 +915,7 @@ static int raster_init(RasterState &rs, const gs_config &c, int sm_count) {
 static void raster_release(RasterState &rs) {
     rs.cc.release(); rs.cov.release(); rs.sh.release(); rs.scene_idx.release(); rs.records.release(); rs.rects.release();
     rs.block_sums.release(); rs.warp_sums.release(); rs.super_sums.release(); rs.ikeys[0].release(); rs.ikeys[1].release(); rs.ivals[0].release(); rs.ivals[1].release();
-    rs.list.release(); rs.ranges.release(); rs.rctl.release(); rs.sctl.release(); rs.lookback.release();
+    rs.list.release(); rs.ranges.release(); rs.rctl.release(); rs.sctl.release(); rs.tile_hist.release();
     rs.dyn.release(); rs.projp.release(); rs.frame.release(); rs.peer_sync_local.release(); rs.exported.release();
 }
 
@@ -1042,7 +1041,7 @@ static int raster_render(RasterState &rs, const gs_config &c, const gs_uniforms 
         // The instance count lives on the device only: the radix grids are sized for the capacity and surplus CTAs exit.
         const unsigned long long *n_dev = &rs.rctl.p->total_instances;
         radix_sort_pairs<uint16_t, unsigned long long>(rs.ikeys[0].p, rs.ikeys[1].p, rs.ivals[0].p, 0u, kValArray, rs.ivals[1].p, rs.ivals[0].p, rs.list.p, 0u,
-                                                       n_dev, rs.instance_capacity, pl, rs.sctl.p, rs.lookback.p, rs.hist_stride, false, rs.ranges.p, st, launches,
+                                                       n_dev, rs.instance_capacity, pl, rs.sctl.p, rs.tile_hist.p, rs.hist_stride, false, rs.ranges.p, st, launches,
                                                        &prof, names);
     }
     if (record_events) RCU(cudaEventRecord(ev_bin, st));

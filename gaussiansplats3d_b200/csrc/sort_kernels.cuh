@@ -1,4 +1,4 @@
-// sort_kernels.cuh -- depth + bucket + one-sweep radix kernels (sm_100a).
+// sort_kernels.cuh -- depth + bucket + histogram/scan/scatter radix kernels (sm_100a).
 //
 // Replaces the reference's sortIndexes() (src/worker/sorter.cpp:17-168) stage by stage:
 //   k_depth      : distance pass, all six branches            sorter.cpp:29-140   (+ running min/max :24-25)
@@ -31,7 +31,6 @@ __global__ void k_sort_init(SortControl *ctl) {
         ctl->dmin = 2147483640;
         ctl->dmax = -2147483640;
         ctl->error = 0;
-        for (int i = 0; i < 4; ++i) ctl->ticket[i] = 0;
     }
     uint32_t *h = &ctl->hist[0][0];
     for (uint32_t i = tid; i < 4 * kRadix; i += blockDim.x) h[i] = 0;
@@ -154,7 +153,7 @@ k_depth(const uint32_t *__restrict__ indexes, const void *__restrict__ centers, 
 // Stable LSD radix sort, 8-bit digits, three kernels per pass and NO cross-CTA dependency chain:
 //   H  k_radix_hist    per-tile digit histogram            -> tile_hist[digit][tile]   (+ global digit totals)
 //   S  k_radix_scan    per digit: exclusive scan over tiles + global digit base (in place: counts become offsets)
-//   P  k_radix_scatter rank inside the tile (warp match), reorder through shared memory, coalesced scatter
+//   P  k_radix_scatter rank inside the tile (peer masks from warp votes), reorder through shared memory, coalesced scatter
 // A one-sweep (decoupled look-back) variant was measured first: at the sizes of this path (1M-16M keys, ~300 co-resident
 // CTAs) the look-back chain of the first wave costs ~k/2 L2 round trips for tile k and dominated the pass (profiles/).
 //   tile = kRadixThreads * kRadixItems consecutive elements; warp w owns a contiguous 32*ITEMS run, item k of lane l
@@ -172,12 +171,13 @@ constexpr int kRadixWarps = kRadixThreads / 32;
 
 enum ValMode : int { kValArray = 0, kValArrayReversed = 1, kValIotaReversed = 2 };
 
-// Lanes of the warp holding the same (<= 9-bit) value, from 9 warp votes.  MATCH.ANY does this in one instruction but retires only
+// Lanes of the warp holding the same (<= NB-bit) value, from NB warp votes (8 for a full tile, 9 when tail items use the private bin 256).  MATCH.ANY does this in one instruction but retires only
 // about one per ~50 cycles per SM on sm_100 (measured: it was the limiter of the scatter kernel); VOTE is full rate.
-__device__ __forceinline__ uint32_t warp_peers9(uint32_t d) {
+template <int NB>
+__device__ __forceinline__ uint32_t warp_peers(uint32_t d) {
     uint32_t peers = 0xffffffffu;
 #pragma unroll
-    for (int b = 0; b < 9; ++b) {
+    for (int b = 0; b < NB; ++b) {
         const bool bit = (d >> b) & 1u;
         const uint32_t vote = __ballot_sync(0xffffffffu, bit);
         peers &= bit ? vote : ~vote;
@@ -300,7 +300,7 @@ k_radix_scan(uint32_t *__restrict__ tile_hist, uint32_t stride, uint32_t n_host,
 // P: stable scatter of one tile.  RANGES (final pass of the tile-instance sort): the tile's reorder buffer is fully sorted by
 // key, so [first, last+1) of every key's run is found from neighbours; runs may continue in other tiles -> atomicMin/Max.
 // Register diet (3 CTAs/SM): values are loaded only after ranking, element indices are 32-bit, full tiles skip bounds checks,
-// and the 8 MATCH.ANY of a thread are issued back to back before the serial counter updates that consume them.
+// and the peer masks of a thread's 8 items are computed back to back before the serial counter updates that consume them.
 template <typename KeyT, typename ValT, int VALMODE, bool WRITE_KEYS, bool RANGES, bool FULL>
 __device__ __forceinline__ void radix_scatter_tile(const KeyT *__restrict__ keys_in, const ValT *__restrict__ vals_in, uint32_t iota_top,
                                                    KeyT *__restrict__ keys_out, ValT *__restrict__ vals_out, uint32_t n, uint32_t tile,
@@ -326,7 +326,7 @@ __device__ __forceinline__ void radix_scatter_tile(const KeyT *__restrict__ keys
 #pragma unroll
     for (int k = 0; k < kRadixItems; ++k) {
         const uint32_t d = (FULL || key[k] != 0xffffffffu) ? ((key[k] >> shift) & dmask) : (uint32_t)kRadix; // tail items: private bin
-        peers[k] = warp_peers9(d);
+        peers[k] = warp_peers<FULL ? 8 : 9>(d);
     }
     __syncthreads();
     uint32_t rank[kRadixItems];

@@ -79,6 +79,89 @@ def compute_covariances(scales: np.ndarray, rotations_xyzw: np.ndarray, transfor
     return out.astype(np.float32)
 
 
+# ---- static-scene transform baked at load (SplatMesh.fillSplatDataArrays, SplatMesh.js:1853-1897) ------------------------------------
+def rotation_of_transform(transform16) -> np.ndarray:
+    """The rotation a scene transform applies to spherical harmonics (SplatBuffer.js:628-632): Matrix4.decompose -> quaternion ->
+    normalize -> makeRotationFromQuaternion.  `transform16`: column-major 4x4.  Returns the 3x3 rotation (row, column)."""
+    m = np.asarray(transform16, np.float64).reshape(4, 4).T[:3, :3]
+    sx, sy, sz = (np.linalg.norm(m[:, k]) for k in range(3))
+    if np.linalg.det(m) < 0:      # three.js flips the x scale for a mirrored basis
+        sx = -sx
+    r = m / np.array([sx, sy, sz])[None, :]
+    # Quaternion.setFromRotationMatrix (the four trace cases), then normalize
+    t = r[0, 0] + r[1, 1] + r[2, 2]
+    if t > 0:
+        k = 0.5 / np.sqrt(t + 1.0)
+        q = np.array([(r[2, 1] - r[1, 2]) * k, (r[0, 2] - r[2, 0]) * k, (r[1, 0] - r[0, 1]) * k, 0.25 / k])
+    elif r[0, 0] > r[1, 1] and r[0, 0] > r[2, 2]:
+        k = 2.0 * np.sqrt(1.0 + r[0, 0] - r[1, 1] - r[2, 2])
+        q = np.array([0.25 * k, (r[0, 1] + r[1, 0]) / k, (r[0, 2] + r[2, 0]) / k, (r[2, 1] - r[1, 2]) / k])
+    elif r[1, 1] > r[2, 2]:
+        k = 2.0 * np.sqrt(1.0 + r[1, 1] - r[0, 0] - r[2, 2])
+        q = np.array([(r[0, 1] + r[1, 0]) / k, 0.25 * k, (r[1, 2] + r[2, 1]) / k, (r[0, 2] - r[2, 0]) / k])
+    else:
+        k = 2.0 * np.sqrt(1.0 + r[2, 2] - r[0, 0] - r[1, 1])
+        q = np.array([(r[0, 2] + r[2, 0]) / k, (r[1, 2] + r[2, 1]) / k, 0.25 * k, (r[1, 0] - r[0, 1]) / k])
+    q = q / np.linalg.norm(q)
+    x, y, z, w = q
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+                     [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+                     [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
+
+
+def sh_rotation_matrices(rot3x3: np.ndarray) -> tuple[np.ndarray, np.ndarray]:
+    """Band-1 (3x3) and band-2 (5x5) coefficient rotations in the reference's coefficient order and sign convention
+    (SplatBuffer.js:632-634 for band 1, rotateSphericalHarmonics5 :780-816 for band 2).  Row l holds the weights of the INPUT
+    coefficients that make OUTPUT coefficient l."""
+    r = np.asarray(rot3x3, np.float64)
+    m1 = np.array([[r[1, 1], -r[1, 2], r[1, 0]],
+                   [-r[2, 1], r[2, 2], -r[2, 0]],
+                   [r[0, 1], -r[0, 2], r[0, 0]]])
+    a, b, c = m1[0], m1[1], m1[2]          # tsh11, tsh12, tsh13
+    k14, k34, k13, k43, k112 = np.sqrt(1 / 4), np.sqrt(3 / 4), np.sqrt(1 / 3), np.sqrt(4 / 3), np.sqrt(1 / 12)
+
+    def sym(u, v):     # the (u, v) product pattern shared by rows 1, 2 and 4
+        return np.array([k14 * ((u[2] * v[0] + u[0] * v[2]) + (v[2] * u[0] + v[0] * u[2])),
+                         u[1] * v[0] + v[1] * u[0],
+                         k34 * (u[1] * v[1] + v[1] * u[1]),
+                         u[1] * v[2] + v[1] * u[2],
+                         k14 * ((u[2] * v[2] - u[0] * v[0]) + (v[2] * u[2] - v[0] * u[0]))])
+
+    row3 = np.array([k13 * (b[2] * b[0] + b[0] * b[2]) - k112 * ((c[2] * c[0] + c[0] * c[2]) + (a[2] * a[0] + a[0] * a[2])),
+                     k43 * b[1] * b[0] - k13 * (c[1] * c[0] + a[1] * a[0]),
+                     b[1] * b[1] - k14 * (c[1] * c[1] + a[1] * a[1]),
+                     k43 * b[1] * b[2] - k13 * (c[1] * c[2] + a[1] * a[2]),
+                     k13 * (b[2] * b[2] - b[0] * b[0]) - k112 * ((c[2] * c[2] - c[0] * c[0]) + (a[2] * a[2] - a[0] * a[0]))])
+    row5 = np.array([k14 * ((c[2] * c[0] + c[0] * c[2]) - (a[2] * a[0] + a[0] * a[2])),
+                     c[1] * c[0] - a[1] * a[0],
+                     k34 * (c[1] * c[1] - a[1] * a[1]),
+                     c[1] * c[2] - a[1] * a[2],
+                     k14 * ((c[2] * c[2] - c[0] * c[0]) - (a[2] * a[2] - a[0] * a[0]))])
+    m2 = np.stack([sym(c, a), sym(b, a), row3, sym(b, c), row5])
+    return m1, m2
+
+
+def transform_scene(raw: RawScene, transform16) -> tuple[RawScene, np.ndarray]:
+    """Centres and spherical harmonics of `raw` under a static scene transform, as the reference bakes them at load:
+    centre.applyMatrix4 (SplatBuffer.js:340-342; f64 arithmetic, f32 storage) and the SH rotation above (:684-716).  Scales and
+    quaternions stay as they are -- the covariance takes the transform's upper 3x3 instead (computeCovariance :461-466), which is
+    returned as the second value for `compute_covariances`."""
+    m = np.asarray(transform16, np.float64).reshape(4, 4).T
+    c = raw.centers.astype(np.float64)
+    w = c @ m[3, :3] + m[3, 3]                               # applyMatrix4 divides by w (1 for affine transforms)
+    centers = ((c @ m[:3, :3].T + m[:3, 3]) / w[:, None]).astype(np.float32)
+    sh = raw.sh
+    if sh is not None and raw.sh_degree >= 1:
+        m1, m2 = sh_rotation_matrices(rotation_of_transform(transform16))
+        src = sh.astype(np.float64)
+        out = np.empty_like(src)
+        out[:, 0:3] = np.einsum("lk,nkc->nlc", m1, src[:, 0:3])
+        if raw.sh_degree >= 2:
+            out[:, 3:8] = np.einsum("lk,nkc->nlc", m2, src[:, 3:8])
+        sh = out.astype(np.float32)
+    return RawScene(centers, raw.scales, raw.rotations, raw.colors, sh, raw.sh_degree), m[:3, :3].copy()
+
+
 def pack_centers_colors(centers: np.ndarray, colors: np.ndarray, minimum_alpha: int = 1) -> np.ndarray:
     """SplatMesh.updateCenterColorsPaddedData (SplatMesh.js:1143-1153) + fillSplatColorArray's alpha floor
     (SplatBuffer.js:541-542): uvec4 {r | g<<8 | b<<16 | a<<24, bits(x), bits(y), bits(z)}."""
@@ -119,8 +202,12 @@ class PackedScene:
 
 
 def pack_scene(raw: RawScene, *, half_covariances: bool = False, sh_format: str = "f16", minimum_alpha: int = 1,
-               sh8_range: tuple[float, float] = (-1.5, 1.5)) -> PackedScene:
-    cov = compute_covariances(raw.scales, raw.rotations)
+               sh8_range: tuple[float, float] = (-1.5, 1.5), transform16=None) -> PackedScene:
+    """`transform16` (column-major 4x4): the static scene transform baked into centres, covariances and SH (non-dynamic meshes)."""
+    t3 = None
+    if transform16 is not None:
+        raw, t3 = transform_scene(raw, transform16)
+    cov = compute_covariances(raw.scales, raw.rotations, t3)
     if half_covariances:  # halfPrecisionCovariancesOnGPU
         cov = cov.astype(np.float16)
     sh = None

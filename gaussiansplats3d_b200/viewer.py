@@ -53,15 +53,24 @@ class SplatMesh:
         self.fadeInComplete = True
         self.sceneCenter = (0.0, 0.0, 0.0)
 
-    def build(self, raw_scene: RawScene, *, sh_format: str = "f16") -> None:
-        """Decode + pack the scene like refreshGPUDataFromSplatBuffers (SplatMesh.js:588-603) and keep it for upload."""
-        self.raw = raw_scene
+    def build(self, raw_scene: RawScene, *, sh_format: str = "f16", transform16=None) -> None:
+        """Decode + pack the scene like refreshGPUDataFromSplatBuffers (SplatMesh.js:588-603) and keep it for upload.
+        `transform16` (column-major 4x4, the SplatScene's position/quaternion/scale): baked into centres, covariances and SH when
+        the mesh is static (fillSplatDataArrays' applySceneTransform default, SplatMesh.js:1872-1883); a dynamic mesh keeps the
+        data untouched and applies its transforms per frame in the sorter and the vertex stage."""
+        if transform16 is not None and self.dynamicMode:
+            transform16 = None
+        if transform16 is not None:
+            from .scenes import transform_scene
+            self.raw = transform_scene(raw_scene, transform16)[0]      # what the sorter's centres are taken from
+        else:
+            self.raw = raw_scene
         degree = min(self.sphericalHarmonicsDegree, raw_scene.sh_degree)
         if degree < raw_scene.sh_degree:  # minSphericalHarmonicsDegree clamp (SplatMesh.js:680-683)
             ncoef = 0 if degree == 0 else (3 if degree == 1 else 8)
             raw_scene = RawScene(raw_scene.centers, raw_scene.scales, raw_scene.rotations, raw_scene.colors,
                                  None if degree == 0 else raw_scene.sh[:, :ncoef], degree)
-        self.packed = pack_scene(raw_scene, half_covariances=self.halfPrecisionCovariancesOnGPU, sh_format=sh_format)
+        self.packed = pack_scene(raw_scene, half_covariances=self.halfPrecisionCovariancesOnGPU, sh_format=sh_format, transform16=transform16)
 
     def getSplatCount(self) -> int:  # noqa: N802
         return 0 if self.packed is None else self.packed.count
@@ -135,12 +144,16 @@ class Viewer:
         self._sorted_on_device = False
 
     # -- scene set-up (addSplatBuffers / setupSortWorker, Viewer.js:1094-1300) ------------------------------------------------
-    def addSplatScene(self, raw_scene: RawScene, *, separate_sort_worker: bool = False) -> None:  # noqa: N802
+    def addSplatScene(self, raw_scene: RawScene, *, separate_sort_worker: bool = False, position=(0.0, 0.0, 0.0),  # noqa: N802
+                      rotation=(0.0, 0.0, 0.0, 1.0), scale=(1.0, 1.0, 1.0)) -> None:
+        """Viewer.addSplatScene's `position` / `rotation` (quaternion x, y, z, w) / `scale` options (Viewer.js:736-760): the
+        SplatScene transform, baked at load for a static mesh."""
         self.splatMesh = SplatMesh(dynamicMode=self.dynamicScene, halfPrecisionCovariancesOnGPU=self.halfPrecisionCovariancesOnGPU,
                                    devicePixelRatio=self.devicePixelRatio, antialiased=self.antialiased,
                                    maxScreenSpaceSplatSize=self.maxScreenSpaceSplatSize, sphericalHarmonicsDegree=self.sphericalHarmonicsDegree,
                                    kernel2DSize=self.kernel2DSize)
-        self.splatMesh.build(raw_scene)
+        identity = tuple(position) == (0.0, 0.0, 0.0) and tuple(rotation) == (0.0, 0.0, 0.0, 1.0) and tuple(scale) == (1.0, 1.0, 1.0)
+        self.splatMesh.build(raw_scene, transform16=None if identity else TM.compose(position, rotation, scale))
         n = self.splatMesh.getSplatCount()
         self.engine = Engine(n, device=self.device, distance_map_range=1 << self.splatSortDistanceMapPrecision,
                              integer_based_sort=self.integerBasedSort, dynamic_mode=self.dynamicScene,

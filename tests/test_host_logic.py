@@ -93,3 +93,106 @@ def test_blend_order_dependence(oracle_mod):
     assert np.isclose(c[3], 1 - 0.2 * 0.2, atol=1e-6) and np.isclose(c[1], 0.8, atol=1e-6) and np.isclose(c[0], 0.8 * 0.2, atol=1e-6)
     assert np.isclose(f10[10, 10][0], 0.8, atol=1e-6)
     assert f01[0, 0, 3] == 0.0  # outside the quad's inscribed disc
+
+
+# ---- static scene transform baked at load (scenes.transform_scene / pack_scene(transform16=...)) ------------------------------------
+def _demo_transform():
+    from gaussiansplats3d_b200 import three_math as TM
+    q = np.array([0.31, -0.52, 0.18, 0.77])
+    q /= np.linalg.norm(q)
+    return TM.compose((0.7, -1.1, 0.4), q, (1.6, 1.6, 1.6)), q
+
+
+def test_baked_transform_matches_scalar_restatement():
+    """Vectorised packing vs the per-splat restatement of SplatBuffer.js (oracle/pack_oracle.py): centres, covariances, SH bands 1 and 2."""
+    from oracle import pack_oracle as PO
+    from gaussiansplats3d_b200.scenes import compute_covariances, rotation_of_transform, synthetic_scene, transform_scene
+    raw = synthetic_scene(300, seed=5, sh_degree=2)
+    T, _ = _demo_transform()
+    baked, t3 = transform_scene(raw, T)
+    cov = compute_covariances(baked.scales, baked.rotations, t3)
+    R = rotation_of_transform(T)
+    for i in range(raw.count):
+        c, cov6, sh = PO.bake_one([float(v) for v in raw.centers[i]], [float(v) for v in raw.scales[i]], [float(v) for v in raw.rotations[i]],
+                                  [[float(v) for v in t] for t in raw.sh[i]], 2, [float(v) for v in T], R.tolist())
+        assert np.allclose(baked.centers[i], c, rtol=1e-6, atol=1e-6)
+        assert np.allclose(cov[i], cov6, rtol=2e-6, atol=1e-9)
+        assert np.allclose(baked.sh[i], np.array(sh), rtol=1e-5, atol=1e-6)
+
+
+def test_sh_rotation_composes_and_inverts():
+    """Rotating by A then B equals rotating by B*A; the identity rotates nothing; band matrices are orthogonal."""
+    from gaussiansplats3d_b200.scenes import sh_rotation_matrices
+    rng = np.random.default_rng(3)
+    qa, qb = rng.normal(size=4), rng.normal(size=4)
+
+    def rot(q):
+        x, y, z, w = q / np.linalg.norm(q)
+        return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)], [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+                         [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
+    A, B = rot(qa), rot(qb)
+    a1, a2 = sh_rotation_matrices(A)
+    b1, b2 = sh_rotation_matrices(B)
+    c1, c2 = sh_rotation_matrices(B @ A)
+    assert np.allclose(b1 @ a1, c1, atol=1e-12) and np.allclose(b2 @ a2, c2, atol=1e-12)
+    assert np.allclose(a2 @ a2.T, np.eye(5), atol=1e-12)
+    i1, i2 = sh_rotation_matrices(np.eye(3))
+    assert np.allclose(i1, np.eye(3)) and np.allclose(i2, np.eye(5))
+
+
+@pytest.mark.parametrize("degree", [0, 1, 2])
+def test_baked_transform_renders_like_the_same_transform_as_model_matrix(oracle_mod, degree):
+    """The rendering invariant that pins the baking (incl. the direction of the SH rotation): a scene with transform T baked in, seen
+    by camera V, must give the picture of the untouched scene drawn with model matrix T (modelView = V*T, camera position T^-1 * eye)
+    -- which is also exactly what the reference's dynamic mode does in the shader."""
+    from gaussiansplats3d_b200 import three_math as TM
+    from gaussiansplats3d_b200.engine import Uniforms
+    from gaussiansplats3d_b200.scenes import pack_scene, synthetic_scene
+    W, H = 320, 200
+    raw = synthetic_scene(3000, seed=9, kind="bonsai", sh_degree=degree)
+    T, _ = _demo_transform()
+    cam = TM.PerspectiveCamera(50, W / H, 0.1, 1000)
+    cam.position = np.array([2.0, 3.5, -11.0]); cam.look_at((0.5, -1.0, 0.5))
+    fx, fy = cam.projectionMatrix[0] * 0.5 * W, cam.projectionMatrix[5] * 0.5 * H
+    base = dict(projection=cam.projectionMatrix.astype(np.float32), focal=(fx, fy), viewport=(W, H), sh_degree=degree)
+    baked = pack_scene(raw, sh_format="f32", transform16=T)
+    plain = pack_scene(raw, sh_format="f32")
+    # one draw order for both pictures: back to front by view-space depth of the transformed centres
+    V = TM.to_mat(cam.matrixWorldInverse)
+    centres_t = baked.centers_colors[:, 1:].view(np.float32).astype(np.float64)
+    order = np.argsort((centres_t @ V[:3, :3].T + V[:3, 3])[:, 2], kind="stable").astype(np.uint32)
+    ua = Uniforms(model_view=cam.matrixWorldInverse.astype(np.float32), camera_position=cam.position.astype(np.float32), **base)
+    eye_model = TM.to_mat(TM.invert(T)) @ np.append(cam.position, 1.0)
+    ub = Uniforms(model_view=TM.multiply(cam.matrixWorldInverse, T).astype(np.float32), camera_position=eye_model[:3].astype(np.float32), **base)
+    fa, pa = oracle_mod.render(ua, baked.centers_colors, baked.covariances, order, W, H, sh=baked.sh, sh_degree=baked.sh_degree)
+    fb, pb = oracle_mod.render(ub, plain.centers_colors, plain.covariances, order, W, H, sh=plain.sh, sh_degree=plain.sh_degree)
+    assert pa["valid"].sum() > 1000 and np.array_equal(pa["valid"], pb["valid"])
+    assert np.abs(fa - fb).max() < 4e-3 and np.abs(fa - fb).mean() < 2e-5
+    if degree > 0:   # the test has teeth: without the SH rotation the colours differ visibly
+        unrot = pack_scene(raw, sh_format="f32")
+        fc, _ = oracle_mod.render(ua, baked.centers_colors, baked.covariances, order, W, H, sh=unrot.sh, sh_degree=degree)
+        assert np.abs(fa - fc).max() > 2e-2
+
+
+def test_splat_mesh_bakes_transform_only_when_static():
+    """SplatMesh.js:1872-1883: a static mesh bakes the scene transform (the sorter's centres included); a dynamic one does not."""
+    from gaussiansplats3d_b200 import three_math as TM
+    from gaussiansplats3d_b200.scenes import synthetic_scene
+    from gaussiansplats3d_b200.viewer import SplatMesh
+    raw = synthetic_scene(200, seed=2, sh_degree=1)
+    T = TM.compose((1.0, 2.0, 3.0), (0.0, 0.0, 0.0, 1.0), (2.0, 2.0, 2.0))
+    static = SplatMesh(sphericalHarmonicsDegree=1)
+    static.build(raw, transform16=T)
+    want = raw.centers * 2.0 + np.array([1.0, 2.0, 3.0], np.float32)
+    assert np.allclose(static.getFloatCenters(0, 199)[:, :3], want, atol=1e-5)
+    assert np.array_equal(static.getIntegerCenters(0, 199, True)[:, :3], np.floor(static.raw.centers.astype(np.float64) * 1000.0 + 0.5).astype(np.int32))
+    assert np.allclose(static.packed.centers_colors[:, 1:].view(np.float32), want, atol=1e-5)
+    assert np.allclose(static.packed.covariances, 4.0 * _plain_cov(raw), rtol=1e-5)      # T3 = 2 I: Sigma scales by 4
+    dynamic = SplatMesh(dynamicMode=True, sphericalHarmonicsDegree=1)
+    dynamic.build(raw, transform16=T)
+    assert np.array_equal(dynamic.getFloatCenters(0, 199)[:, :3], raw.centers)
+
+
+def _plain_cov(raw):
+    from gaussiansplats3d_b200.scenes import compute_covariances
+    return compute_covariances(raw.scales, raw.rotations)

@@ -369,6 +369,17 @@ def run_ours(args):
         barrier()
         extended += 50
     clocks = sampler.stop()
+
+    # ---- on-chip work of the blend, the figure SURVEY 8(d) asks for beside its HBM fraction: pixels of the reference's quads
+    # (+-basis1 +-basis2 parallelograms = its fragment-shader invocations, unclipped) per second of k_blend.  Untimed read-back.
+    quad_pixels = None
+    try:
+        if world == 1:
+            ps = e.read_projected(n)
+            ok = ps["valid"] != 0
+            quad_pixels = float(np.sum(4.0 * np.abs(ps["b1x"][ok].astype(np.float64) * ps["b2y"][ok] - ps["b1y"][ok].astype(np.float64) * ps["b2x"][ok])))
+    except Exception as ex:      # a statistic must never cost the bench line
+        print(f"[bench] quad-pixel statistic skipped: {ex}", file=sys.stderr)
     clocks["window"] = "timed + per-kernel + e2e regions" + (f", extended by {extended} identical untimed frames" if extended else "")
 
     # ---- CPU baseline beside it (rank 0, N = 1 only; bounded sample) ---------------------------------------------------------------
@@ -399,6 +410,9 @@ def run_ours(args):
                               "frame_frac": path_bytes / (frame_kernel_ms * 1e-3) / 1e9 / peak,
                               "sort_bytes": sort_bytes, "sort_gbs": sort_bytes / (sort_ms * 1e-3) / 1e9 if sort_ms else None,
                               "sort_frac": sort_bytes / (sort_ms * 1e-3) / 1e9 / peak if sort_ms else None},
+            "blend_work": None if not quad_pixels or "k_blend" not in kernels else
+            {"quad_pixels_per_frame": quad_pixels, "gpixels_per_sec": quad_pixels / (kernels["k_blend"] * 1e-3) / 1e9,
+             "note": "reference fragment invocations (unclipped quad areas of the visible splats) / k_blend time"},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)

@@ -202,3 +202,24 @@ def test_precision_20bit_and_float_sort_feed_the_same_frame(gs, oracle_mod):
         want, _ = _oracle_frame(oracle_mod, v, order)
         _check_frame(got, want)
         v.dispose()
+
+
+@pytest.mark.parametrize("name", ["bonsai-sh0-160x100", "bonsai-sh2-128x96", "garden-sh1-200x120"])
+def test_frame_and_order_match_committed_fixture(gs, name):
+    """Against tests/golden/raster_golden.npz (no oracle call at run time): the Viewer-driven sort must reproduce the stored draw
+    order bit for bit (that order is the compiled reference sorter's) and the frame must meet the stated tolerance."""
+    import sys
+    from pathlib import Path
+    sys.path.insert(0, str(Path(__file__).resolve().parent / "golden"))
+    import raster_cases
+    from gaussiansplats3d_b200.scenes import synthetic_scene
+    gold = np.load(Path(__file__).resolve().parent / "golden" / "raster_golden.npz")
+    n, seed, kind, sh, w, h, cam = raster_cases.CASES[name]
+    raw = synthetic_scene(n, seed=seed, kind=kind, sh_degree=sh)
+    v = _viewer(gs, raw, w, h, cam=cam, sphericalHarmonicsDegree=sh)
+    v.update()
+    got = v.render(frame_format=gs._native.GS_FRAME_RGBA32F, flip_y=False)
+    order, _ = v.engine.sort(v.mvp_matrix().astype(np.float32), n, n, None)
+    assert np.array_equal(order, gold[name + "|order"])
+    _check_frame(got, gold[name + "|frame"])
+    v.dispose()

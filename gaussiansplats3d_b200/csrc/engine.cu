@@ -110,6 +110,8 @@ struct gs_engine {
     DevBuf<DepthParams> depthp;      // per-frame depth parameters (device copy read by k_depth)
     DevBuf<uint32_t> tile_hist;       // radix tile histograms / offsets [pass][digit][tile]
     DevBuf<uint32_t> freq;           // scratch reproduction for gs_sort_indexes
+    DevBuf<int32_t> dist_rows_i;     // gs_compute_distances: per-scene integer / float rows
+    DevBuf<float> dist_rows_f;
     DevBuf<uint32_t> sub_idx;        // sharded frames: this rank's subset of the sort input (index, distance)
     DevBuf<int32_t> sub_dist;
     uint32_t uploaded_splats = 0;    // 'uploadedSplatCount' SortWorker.js:97
@@ -162,6 +164,16 @@ static int check_engine(gs_engine *e) {
     return GS_OK;
 }
 
+extern "C" void gs_destroy(gs_engine *e);
+// inside gs_create after the engine object exists: a failing CUDA call must not leak it
+#define CUE(call)                                                                                                 \
+    do {                                                                                                          \
+        cudaError_t _e = (call);                                                                                  \
+        if (_e != cudaSuccess) {                                                                                  \
+            gs_destroy(e);                                                                                        \
+            return fail(GS_ERR_CUDA, "%s -> %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__);      \
+        }                                                                                                         \
+    } while (0)
 extern "C" int gs_create(const gs_config *cfg, gs_engine **out) {
     if (!cfg || !out) return fail(GS_ERR_BAD_ARG, "gs_create: null argument");
     *out = nullptr;
@@ -179,13 +191,13 @@ extern "C" int gs_create(const gs_config *cfg, gs_engine **out) {
     if (!e) return fail(GS_ERR_BAD_ARG, "out of host memory");
     e->cfg = c;
     cudaDeviceProp prop{};
-    CU(cudaGetDeviceProperties(&prop, c.device));
+    CUE(cudaGetDeviceProperties(&prop, c.device));
     e->sm_count = prop.multiProcessorCount;
-    CU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
-    CU(cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking));
-    CU(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
-    CU(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
-    for (int i = 0; i < EV_COUNT; ++i) CU(cudaEventCreate(&e->ev[i]));
+    CUE(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    CUE(cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking));
+    CUE(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+    CUE(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
+    for (int i = 0; i < EV_COUNT; ++i) CUE(cudaEventCreate(&e->ev[i]));
     int kb = 0;
     while ((1u << kb) < c.distance_map_range) ++kb;
     e->key_bits = kb;
@@ -198,18 +210,20 @@ extern "C" int gs_create(const gs_config *cfg, gs_engine **out) {
         return rc;
     }
     if (c.dynamic_mode && (rc = e->scene_idx.ensure(n))) { gs_destroy(e); return rc; }
-    cudaMemsetAsync(e->scene_idx.p, 0, e->scene_idx.n * 4, e->stream);
+    if (e->scene_idx.p) CUE(cudaMemsetAsync(e->scene_idx.p, 0, e->scene_idx.n * 4, e->stream));
     {   // identity transforms until the caller provides some
         std::vector<float> id(16 * GS_MAX_SCENES, 0.f);
         for (int s = 0; s < GS_MAX_SCENES; ++s) id[16 * s] = id[16 * s + 5] = id[16 * s + 10] = id[16 * s + 15] = 1.f;
-        CU(cudaMemcpy(e->transforms.p, id.data(), id.size() * 4, cudaMemcpyHostToDevice));
+        CUE(cudaMemcpy(e->transforms.p, id.data(), id.size() * 4, cudaMemcpyHostToDevice));
     }
     rc = raster_init(e->rs, c, e->sm_count);
     if (rc) { gs_destroy(e); return fail(rc, "raster_init failed: %s", g_err); }
-    CU(cudaStreamSynchronize(e->stream));
+    CUE(cudaStreamSynchronize(e->stream));
     *out = e;
     return GS_OK;
 }
+
+#undef CUE
 
 extern "C" void gs_destroy(gs_engine *e) {
     if (!e) return;
@@ -217,7 +231,7 @@ extern "C" void gs_destroy(gs_engine *e) {
     if (e->stream) cudaStreamSynchronize(e->stream);
     e->centers.release(); e->scene_idx.release(); e->indexes.release(); e->precomputed.release(); e->dist.release();
     e->keys[0].release(); e->keys[1].release(); e->vals[0].release(); e->vals[1].release(); e->sorted.release();
-    e->transforms.release(); e->ctl.release(); e->depthp.release(); e->tile_hist.release(); e->freq.release(); e->sub_idx.release(); e->sub_dist.release();
+    e->transforms.release(); e->ctl.release(); e->depthp.release(); e->tile_hist.release(); e->freq.release(); e->dist_rows_i.release(); e->dist_rows_f.release(); e->sub_idx.release(); e->sub_dist.release();
     e->h_indexes.release(); e->h_sorted.release(); e->h_ctl.release(); e->h_frame.release(); e->flush.release(); e->prof.release();
     e->shard.block.release(); e->shard.total.release(); e->shard.ahead.release(); e->shard.block_total.release(); e->shard.delta.release(); e->shard.local_sorted.release();
     for (void *m : e->shard.opened) if (m) cudaIpcCloseMemHandle(m);
@@ -734,7 +748,6 @@ extern "C" int gs_sort_indexes(const uint32_t *indexes, const void *centers, con
     const bool want_scratch = (mappedDistances != nullptr) || (frequencies != nullptr);
     if ((rc = sort_on_device(e, e->indexes.p, modelViewProj, sortCount, renderCount, usePrecomputedDistances, want_scratch))) return rc;
     // wasm-trap emulation: results are only written back when the device reported no range error
-    std::vector<uint32_t> out_stage;
     if ((rc = finish_sort(e, nullptr))) return rc;
     if (renderCount) CU(cudaMemcpyAsync(indexesOut, e->sorted.p, (size_t)renderCount * 4, cudaMemcpyDeviceToHost, st));
     const uint32_t s0 = renderCount - sortCount;
@@ -784,7 +797,8 @@ extern "C" int gs_compute_distances(gs_engine *e, const double *mvp, const doubl
             frows[4 * s + k] = (float)m[2 + 4 * k];
         }
     }
-    DevBuf<int32_t> d_ir; DevBuf<float> d_fr;
+    DevBuf<int32_t> &d_ir = e->dist_rows_i;   // engine-owned scratch: an early error return must not leak it
+    DevBuf<float> &d_fr = e->dist_rows_f;
     if ((rc = d_ir.ensure(irows.size())) || (rc = d_fr.ensure(frows.size()))) return rc;
     cudaStream_t st = e->stream;
     CU(cudaMemcpyAsync(d_ir.p, irows.data(), irows.size() * 4, cudaMemcpyHostToDevice, st));
@@ -798,7 +812,6 @@ extern "C" int gs_compute_distances(gs_engine *e, const double *mvp, const doubl
     CU(cudaMemcpyAsync(out, e->precomputed.p, (size_t)count * 4, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     CU(cudaGetLastError());
-    d_ir.release(); d_fr.release();
     return GS_OK;
 }
 

@@ -7,6 +7,10 @@
  * CUDA device every compute entry returns GS_ERR_NO_DEVICE.
  *
  * Memory kinds: pointers are HOST pointers unless the parameter name ends in `_dev`.
+ *
+ * Threading: like the reference's worker (one sort in flight, SortWorker.js `sortRunning`), an engine handle is driven by one
+ * thread at a time; different handles may be used from different threads.  The stateless drop-in (section 1) keeps one cached
+ * private engine and is NOT re-entrant.  gs_last_error_message() is per thread.
  */
 #ifndef GSPLAT_B200_H
 #define GSPLAT_B200_H

@@ -946,6 +946,10 @@ static int enqueue_frame(gs_engine *e, const gs_sort_params *s, const gs_uniform
             const PassPlan pl = make_plan_bits(e->key_bits);
             if ((rc = e->tile_hist.ensure(radix_tile_hist_words(std::max(q.sort_count, 1u), pl.npasses, &stride)))) return rc;
             CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            struct CaptureGuard {   // an early error return must not leave the stream capturing
+                cudaStream_t st; bool armed;
+                ~CaptureGuard() { if (armed) { cudaGraph_t g = nullptr; cudaStreamEndCapture(st, &g); if (g) cudaGraphDestroy(g); (void)cudaGetLastError(); } }
+            } guard{st, true};
             // fork: the projection does not depend on the draw order, so it runs beside the (latency-bound) depth sort
             CU(cudaEventRecord(e->ev_fork, st));
             CU(cudaStreamWaitEvent(e->stream2, e->ev_fork, 0));
@@ -965,6 +969,7 @@ static int enqueue_frame(gs_engine *e, const gs_sort_params *s, const gs_uniform
             if (!rc2) rc2 = rc ? rc : render_on_device(e, u, &rp, e->sorted.p, true, 2, order_count);
             e->graph_launches = e->tm.kernel_launches + sort_launches + proj_launches;
             cudaGraph_t g = nullptr;
+            guard.armed = false;
             cudaError_t ce = cudaStreamEndCapture(st, &g);
             if (rc2) { if (g) cudaGraphDestroy(g); return rc2; }
             if (ce != cudaSuccess) return fail(GS_ERR_CUDA, "cudaStreamEndCapture -> %s", cudaGetErrorString(ce));
@@ -1105,12 +1110,16 @@ extern "C" int gs_upload_ksplat(gs_engine *e, const void *data, size_t bytes, co
     if ((ce = rs.cov.ensure(n * (o.half_covariances ? 12 : 24) + 16)) != cudaSuccess) return fail(GS_ERR_CUDA, "cudaMalloc -> %s", cudaGetErrorString(ce));
     if (ncomp_out && (ce = rs.sh.ensure(n * ncomp_out * (level == 2 ? 1 : 2) + 16)) != cudaSuccess) return fail(GS_ERR_CUDA, "cudaMalloc -> %s", cudaGetErrorString(ce));
     DevBuf<unsigned char> d_file; DevBuf<uint32_t> d_pre;
+    struct Scratch {   // the staged file and the bucket prefixes live for this call only, whichever way it returns
+        DevBuf<unsigned char> &a; DevBuf<uint32_t> &b;
+        ~Scratch() { a.release(); b.release(); }
+    } scratch{d_file, d_pre};
     if ((rc = d_file.ensure(bytes))) return rc;
     cudaStream_t st = e->stream;
     CU(cudaMemcpyAsync(d_file.p, data, bytes, cudaMemcpyHostToDevice, st));
     size_t pre_words = 0;
     for (auto &p : prefixes) pre_words += p.size();
-    if ((rc = d_pre.ensure(pre_words))) { d_file.release(); return rc; }
+    if ((rc = d_pre.ensure(pre_words))) return rc;
     size_t at = 0;
     for (size_t i = 0; i < secs.size(); ++i) {
         CU(cudaMemcpyAsync(d_pre.p + at, prefixes[i].data(), prefixes[i].size() * 4, cudaMemcpyHostToDevice, st));
@@ -1122,7 +1131,6 @@ extern "C" int gs_upload_ksplat(gs_engine *e, const void *data, size_t bytes, co
     }
     CU(cudaStreamSynchronize(st));
     CU(cudaGetLastError());
-    d_file.release(); d_pre.release();
     rs.uploaded = total;
     rs.have_scene_idx = false;
     if (o.upload_sort_centers) e->uploaded_splats = total;

@@ -196,3 +196,18 @@ def test_splat_mesh_bakes_transform_only_when_static():
 def _plain_cov(raw):
     from gaussiansplats3d_b200.scenes import compute_covariances
     return compute_covariances(raw.scales, raw.rotations)
+
+
+def test_ellipse_tile_masks_never_drop_a_covered_tile(tmp_path):
+    """csrc/ellipse_mask.h (the optional exact fine-tile masks) on the host: brute force over pixel centres for 150 K random splats --
+    a tile holding a covered pixel always keeps its bit, and the coarse-tile extraction agrees with the bitmap."""
+    import json
+    import subprocess
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    exe = tmp_path / "ellipse_mask_check"
+    subprocess.run(["/usr/bin/g++", "-O2", "-std=c++17", "-o", str(exe), str(root / "oracle" / "ellipse_mask_check.cpp")], check=True)
+    out = subprocess.run([str(exe), "150000"], capture_output=True, text=True)
+    stats = json.loads(out.stdout)
+    assert out.returncode == 0 and stats["dropped_hits"] == 0 and stats["coarse_mismatch"] == 0
+    assert stats["exact"] <= stats["kept"] < stats["tiles_in_rects"]          # conservative, yet it prunes

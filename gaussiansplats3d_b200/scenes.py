@@ -82,31 +82,43 @@ def compute_covariances(scales: np.ndarray, rotations_xyzw: np.ndarray, transfor
 # ---- static-scene transform baked at load (SplatMesh.fillSplatDataArrays, SplatMesh.js:1853-1897) ------------------------------------
 def rotation_of_transform(transform16) -> np.ndarray:
     """The rotation a scene transform applies to spherical harmonics (SplatBuffer.js:628-632): Matrix4.decompose -> quaternion ->
-    normalize -> makeRotationFromQuaternion.  `transform16`: column-major 4x4.  Returns the 3x3 rotation (row, column)."""
-    m = np.asarray(transform16, np.float64).reshape(4, 4).T[:3, :3]
-    sx, sy, sz = (np.linalg.norm(m[:, k]) for k in range(3))
+    normalize -> makeRotationFromQuaternion, in three.js's own operation order (reciprocal multiplies, x2 = x + x products).
+    `transform16`: column-major 4x4.  Returns the 3x3 rotation (row, column)."""
+    e = [float(v) for v in np.asarray(transform16, np.float64).reshape(16)]
+    sx = np.sqrt(e[0] * e[0] + e[1] * e[1] + e[2] * e[2])
+    sy = np.sqrt(e[4] * e[4] + e[5] * e[5] + e[6] * e[6])
+    sz = np.sqrt(e[8] * e[8] + e[9] * e[9] + e[10] * e[10])
+    m = np.array(e).reshape(4, 4).T[:3, :3]
     if np.linalg.det(m) < 0:      # three.js flips the x scale for a mirrored basis
         sx = -sx
-    r = m / np.array([sx, sy, sz])[None, :]
-    # Quaternion.setFromRotationMatrix (the four trace cases), then normalize
-    t = r[0, 0] + r[1, 1] + r[2, 2]
-    if t > 0:
+    isx, isy, isz = 1.0 / sx, 1.0 / sy, 1.0 / sz
+    m11, m21, m31 = e[0] * isx, e[1] * isx, e[2] * isx          # m<row><col>, column-major elements
+    m12, m22, m32 = e[4] * isy, e[5] * isy, e[6] * isy
+    m13, m23, m33 = e[8] * isz, e[9] * isz, e[10] * isz
+    t = m11 + m22 + m33
+    if t > 0:                      # Quaternion.setFromRotationMatrix
         k = 0.5 / np.sqrt(t + 1.0)
-        q = np.array([(r[2, 1] - r[1, 2]) * k, (r[0, 2] - r[2, 0]) * k, (r[1, 0] - r[0, 1]) * k, 0.25 / k])
-    elif r[0, 0] > r[1, 1] and r[0, 0] > r[2, 2]:
-        k = 2.0 * np.sqrt(1.0 + r[0, 0] - r[1, 1] - r[2, 2])
-        q = np.array([0.25 * k, (r[0, 1] + r[1, 0]) / k, (r[0, 2] + r[2, 0]) / k, (r[2, 1] - r[1, 2]) / k])
-    elif r[1, 1] > r[2, 2]:
-        k = 2.0 * np.sqrt(1.0 + r[1, 1] - r[0, 0] - r[2, 2])
-        q = np.array([(r[0, 1] + r[1, 0]) / k, 0.25 * k, (r[1, 2] + r[2, 1]) / k, (r[0, 2] - r[2, 0]) / k])
+        w, x, y, z = 0.25 / k, (m32 - m23) * k, (m13 - m31) * k, (m21 - m12) * k
+    elif m11 > m22 and m11 > m33:
+        k = 2.0 * np.sqrt(1.0 + m11 - m22 - m33)
+        w, x, y, z = (m32 - m23) / k, 0.25 * k, (m12 + m21) / k, (m13 + m31) / k
+    elif m22 > m33:
+        k = 2.0 * np.sqrt(1.0 + m22 - m11 - m33)
+        w, x, y, z = (m13 - m31) / k, (m12 + m21) / k, 0.25 * k, (m23 + m32) / k
     else:
-        k = 2.0 * np.sqrt(1.0 + r[2, 2] - r[0, 0] - r[1, 1])
-        q = np.array([(r[0, 2] + r[2, 0]) / k, (r[1, 2] + r[2, 1]) / k, 0.25 * k, (r[1, 0] - r[0, 1]) / k])
-    q = q / np.linalg.norm(q)
-    x, y, z, w = q
-    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
-                     [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
-                     [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
+        k = 2.0 * np.sqrt(1.0 + m33 - m11 - m22)
+        w, x, y, z = (m21 - m12) / k, (m13 + m31) / k, (m23 + m32) / k, 0.25 * k
+    ln = np.sqrt(x * x + y * y + z * z + w * w)      # Quaternion.normalize
+    if ln == 0:
+        x, y, z, w = 0.0, 0.0, 0.0, 1.0
+    else:
+        ln = 1.0 / ln
+        x, y, z, w = x * ln, y * ln, z * ln, w * ln
+    x2, y2, z2 = x + x, y + y, z + z                 # Matrix4.makeRotationFromQuaternion = compose(zero, q, one)
+    xx, xy, xz, yy, yz, zz, wx, wy, wz = x * x2, x * y2, x * z2, y * y2, y * z2, z * z2, w * x2, w * y2, w * z2
+    return np.array([[1 - (yy + zz), xy - wz, xz + wy],
+                     [xy + wz, 1 - (xx + zz), yz - wx],
+                     [xz - wy, yz + wx, 1 - (xx + yy)]])
 
 
 def sh_rotation_matrices(rot3x3: np.ndarray) -> tuple[np.ndarray, np.ndarray]:

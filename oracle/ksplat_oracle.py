@@ -1,7 +1,7 @@
 """oracle/ksplat_oracle.py -- TEST INFRASTRUCTURE ONLY.
 
 NumPy restatement of how the reference turns a `.ksplat` buffer into the arrays its renderer and sorter consume
-(static scene, identity scene transform), following /root/reference/src/loaders/SplatBuffer.js:
+(static scene; `transform16` = the SplatScene transform baked at load, None = identity), following /root/reference/src/loaders/SplatBuffer.js:
   centres   fillSplatCenterArray      :307-347  (level >= 1: (u16 - range) * (halfBlock / range) + bucketCentre, evaluated in f64, stored f32)
   bucket    getBucketIndex            :199-219
   cov       fillSplatCovarianceArray  :488-520 -> computeCovariance :440-486 (f64, stored f32 / f16)
@@ -34,7 +34,15 @@ def _rotation_matrices(q_xyzw: np.ndarray) -> np.ndarray:
     return R
 
 
-def decode(data: bytes, *, minimum_alpha: int = 1, half_covariances: bool = False) -> dict:
+def _ordered3(a0, b0, a1, b1, a2, b2):
+    """a0*b0 + a1*b1 + a2*b2 evaluated left to right (Matrix3.multiplyMatrices / Vector3.applyMatrix4 order), f64."""
+    return (a0 * b0 + a1 * b1) + a2 * b2
+
+
+def decode(data: bytes, *, minimum_alpha: int = 1, half_covariances: bool = False, transform16=None) -> dict:
+    """`transform16` (column-major 4x4, f64): baked like fillSplatDataArrays does for a static mesh (SplatMesh.js:1872-1897):
+    centre.applyMatrix4 (:340-342), T3 (M M^T) T3^T (:461-466), SH decoded to floats, rotated (:684-716) and re-encoded at the
+    GPU-side level (toHalfFloat / toUint8, :663-676)."""
     h = K.parse(data)
     buf = np.frombuffer(data, np.uint8)
     level = h.compression_level
@@ -77,15 +85,52 @@ def decode(data: bytes, *, minimum_alpha: int = 1, half_covariances: bool = Fals
             out["sh"].append(np.concatenate(parts, 1))
     centers = np.concatenate(out["centers"]); scales = np.concatenate(out["scales"]); rot = np.concatenate(out["rot"]); colors = np.concatenate(out["colors"])
     n = centers.shape[0]
+    T = None if transform16 is None else np.asarray(transform16, np.float64).reshape(16)
+    if T is not None:     # Vector3.applyMatrix4 on the decoded (f32) centre, JS doubles, stored back into a Float32Array
+        x, y, z = (centers[:, k].astype(np.float64) for k in range(3))
+        w = 1.0 / (((T[3] * x + T[7] * y) + T[11] * z) + T[15])
+        centers = np.stack([(((T[0] * x + T[4] * y) + T[8] * z) + T[12]) * w, (((T[1] * x + T[5] * y) + T[9] * z) + T[13]) * w,
+                            (((T[2] * x + T[6] * y) + T[10] * z) + T[14]) * w], 1).astype(np.float32)
     sh = None
     if ncomp_out:
         sh = np.concatenate(out["sh"])
-        if level == 0:
-            sh = K.to_half_three(sh).view(np.float16)      # stored at compression level max(1, 0) = 1 on the GPU (THREE toHalfFloat)
+        if T is None:
+            if level == 0:
+                sh = K.to_half_three(sh).view(np.float16)      # stored at compression level max(1, 0) = 1 on the GPU (THREE toHalfFloat)
+        else:
+            from gaussiansplats3d_b200.scenes import rotation_of_transform, sh_rotation_matrices
+            lo = h.min_sh if h.min_sh != 0 else -1.5
+            hi = h.max_sh if h.max_sh != 0 else 1.5
+            if level == 2:        # fromUint8 (:27-30) with the file's range, JS doubles
+                f = sh.astype(np.float64) / 255 * (float(hi) - float(lo)) + float(lo)
+            else:                 # f32 as is / fromHalfFloat (exact)
+                f = sh.astype(np.float64)
+            m1, m2 = sh_rotation_matrices(rotation_of_transform(T))
+            tri = f.reshape(n, -1, 3)
+            shr = np.empty_like(tri)
+            for l in range(3):    # dot3: ((0 + in1 t0) + in2 t1) + in3 t2, per colour channel (:736-746)
+                shr[:, l] = (tri[:, 0] * m1[l, 0] + tri[:, 1] * m1[l, 1]) + tri[:, 2] * m1[l, 2]
+            if sh_degree >= 2:
+                for l in range(5):    # dot5 (:752-772)
+                    shr[:, 3 + l] = ((((tri[:, 3] * m2[l, 0] + tri[:, 4] * m2[l, 1]) + tri[:, 5] * m2[l, 2]) + tri[:, 6] * m2[l, 3]) + tri[:, 7] * m2[l, 4])
+            flat = shr.reshape(n, -1)
+            if level == 2:        # toUint8 (:21-25)
+                v = np.clip(flat, float(lo), float(hi))
+                sh = np.clip(np.floor((v - float(lo)) / (float(hi) - float(lo)) * 255), 0, 255).astype(np.uint8)
+            else:                 # toHalfFloat of the f32-rounded value
+                sh = K.to_half_three(flat.astype(np.float32)).view(np.float16)
     M = _rotation_matrices(rot) * scales.astype(np.float64)[:, None, :]
     def dot(r0, r1):  # Matrix3.multiplyMatrices: a1*b1 + a2*b2 + a3*b3, left to right, unfused
         return (M[:, r0, 0] * M[:, r1, 0] + M[:, r0, 1] * M[:, r1, 1]) + M[:, r0, 2] * M[:, r1, 2]
     cov6 = np.stack([dot(0, 0), dot(0, 1), dot(0, 2), dot(1, 1), dot(1, 2), dot(2, 2)], 1)
+    if T is not None:     # transformedCovariance.multiply(T3^T).premultiply(T3): X = S T3^T, then Y = T3 X, ordered sums (:461-466)
+        t3 = [[T[0], T[4], T[8]], [T[1], T[5], T[9]], [T[2], T[6], T[10]]]        # t3[row][col]
+        S = {(0, 0): cov6[:, 0], (0, 1): cov6[:, 1], (0, 2): cov6[:, 2], (1, 1): cov6[:, 3], (1, 2): cov6[:, 4], (2, 2): cov6[:, 5]}
+        sym = lambda i, j: S[(i, j)] if i <= j else S[(j, i)]
+        X = [[_ordered3(sym(i, 0), t3[j][0], sym(i, 1), t3[j][1], sym(i, 2), t3[j][2]) for j in range(3)] for i in range(3)]
+        Y = lambda i, j: _ordered3(t3[i][0], X[0][j], t3[i][1], X[1][j], t3[i][2], X[2][j])
+        # elements [0], [3], [6], [4], [7], [8] of the column-major result = (0,0), (0,1), (0,2), (1,1), (1,2), (2,2)
+        cov6 = np.stack([Y(0, 0), Y(0, 1), Y(0, 2), Y(1, 1), Y(1, 2), Y(2, 2)], 1)
     cov6 = K.to_half_three(cov6.astype(np.float32)).view(np.float16) if half_covariances else cov6.astype(np.float32)
     a = colors[:, 3].astype(np.uint32)
     a = np.where(a >= minimum_alpha, a, 0)

@@ -102,3 +102,47 @@ def test_frame_from_ksplat_equals_frame_from_arrays(gs, oracle_mod):
     err = np.abs(got - want)
     assert err.max() <= 8 / 255 and (err <= 2 / 255).mean() >= 0.999
     v.dispose()
+
+
+@pytest.mark.parametrize("level,deg", [(0, 2), (1, 2), (2, 2), (1, 1), (0, 0)])
+def test_oracle_decode_with_scene_transform(level, deg):
+    """The .ksplat restatement with a baked scene transform (the specification the GPU decode will follow): per splat it must agree
+    with the scalar restatement of SplatBuffer.js (oracle/pack_oracle.py) applied to the values the identity decode produced, and an
+    identity transform must reproduce the identity decode bit for bit in centres and covariances."""
+    from oracle import ksplat_oracle as KO
+    from oracle import pack_oracle as PO
+    from gaussiansplats3d_b200 import ksplat as K
+    from gaussiansplats3d_b200 import three_math as TM
+    from gaussiansplats3d_b200.scenes import rotation_of_transform, synthetic_scene
+    raw = synthetic_scene(400, seed=12, kind="bonsai", sh_degree=deg)
+    data = K.write(raw.centers, raw.scales, raw.rotations, raw.colors, raw.sh, deg, compression_level=level)
+    plain = KO.decode(data)
+    q = np.array([0.21, 0.43, -0.36, 0.8]); q /= np.linalg.norm(q)
+    T = TM.compose((0.4, -0.9, 1.3), q, (1.3, 1.3, 1.3))
+    baked = KO.decode(data, transform16=T)
+    ident = KO.decode(data, transform16=TM.identity())
+    assert np.array_equal(ident["centers"], plain["centers"]) and np.array_equal(ident["covariances"], plain["covariances"])
+    R = rotation_of_transform(T).tolist()
+    lo, hi = plain["header"].min_sh, plain["header"].max_sh
+    n = plain["count"]
+    sh_plain = None
+    if deg:
+        sp = plain["sh"]
+        sh_plain = (sp.astype(np.float64) / 255 * (hi - lo) + lo) if sp.dtype == np.uint8 else sp.astype(np.float64)
+        if level == 0:      # the identity decode already rounded level-0 SH to half; the transform path rotates the f32 values
+            sh_plain = None
+    for i in range(0, n, 7):
+        tri = [] if sh_plain is None else [[float(v) for v in t] for t in sh_plain[i].reshape(-1, 3)]
+        c, cov6, sh = PO.bake_one([float(v) for v in plain["centers"][i]], [float(v) for v in plain["scales"][i]], [float(v) for v in plain["rotations"][i]],
+                                  tri, deg if sh_plain is not None else 0, [float(v) for v in T], R)
+        assert np.array_equal(baked["centers"][i], np.array(c, np.float32))
+        assert np.allclose(baked["covariances"][i], np.array(cov6, np.float32), rtol=3e-7, atol=0)
+        if sh_plain is not None:
+            got = baked["sh"][i]
+            if got.dtype == np.uint8:
+                want = np.clip(np.floor((np.clip(np.array(sh).reshape(-1), lo, hi) - lo) / (hi - lo) * 255), 0, 255)
+                assert np.abs(got.astype(np.int32) - want.astype(np.int32)).max() <= 0
+            else:
+                assert np.array_equal(got.view(np.uint16), K.to_half_three(np.array(sh, np.float32).reshape(-1)).view(np.uint16))
+    # the sorter's integer centres follow the transformed centres
+    assert np.array_equal(baked["int_centers"][:, :3], np.floor(baked["centers"].astype(np.float64) * 1000.0 + 0.5).astype(np.int32))

@@ -104,7 +104,7 @@ class gs_timings(C.Structure):
 
 class gs_ksplat_options(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("minimum_alpha", C.c_uint32), ("half_covariances", C.c_uint8), ("upload_sort_centers", C.c_uint8),
-                ("reserved", C.c_uint8 * 2)]
+                ("has_transform", C.c_uint8), ("reserved", C.c_uint8 * 1), ("transform", C.c_double * 16)]
 
 
 class gs_ksplat_info(C.Structure):

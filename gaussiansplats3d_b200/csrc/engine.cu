@@ -8,6 +8,7 @@
 #include "sort_kernels.cuh"
 #include "raster_kernels.cuh"
 #include "shard_kernels.cuh"
+#include "ksplat_transform.h"
 #include "ksplat_kernels.cuh"
 
 #include <algorithm>
@@ -1109,14 +1110,21 @@ extern "C" int gs_upload_ksplat(gs_engine *e, const void *data, size_t bytes, co
     cudaError_t ce;
     if ((ce = rs.cov.ensure(n * (o.half_covariances ? 12 : 24) + 16)) != cudaSuccess) return fail(GS_ERR_CUDA, "cudaMalloc -> %s", cudaGetErrorString(ce));
     if (ncomp_out && (ce = rs.sh.ensure(n * ncomp_out * (level == 2 ? 1 : 2) + 16)) != cudaSuccess) return fail(GS_ERR_CUDA, "cudaMalloc -> %s", cudaGetErrorString(ce));
-    DevBuf<unsigned char> d_file; DevBuf<uint32_t> d_pre;
+    DevBuf<unsigned char> d_file; DevBuf<uint32_t> d_pre; DevBuf<KTransform> d_xf;
     struct Scratch {   // the staged file and the bucket prefixes live for this call only, whichever way it returns
-        DevBuf<unsigned char> &a; DevBuf<uint32_t> &b;
-        ~Scratch() { a.release(); b.release(); }
-    } scratch{d_file, d_pre};
+        DevBuf<unsigned char> &a; DevBuf<uint32_t> &b; DevBuf<KTransform> &c;
+        ~Scratch() { a.release(); b.release(); c.release(); }
+    } scratch{d_file, d_pre, d_xf};
     if ((rc = d_file.ensure(bytes))) return rc;
     cudaStream_t st = e->stream;
     CU(cudaMemcpyAsync(d_file.p, data, bytes, cudaMemcpyHostToDevice, st));
+    if (o.has_transform) {
+        KTransform K;
+        const float lo = rdf(f + 36), hi = rdf(f + 40);
+        ksplat_transform_params(o.transform, lo != 0.f ? (double)lo : -1.5, hi != 0.f ? (double)hi : 1.5, K);
+        if ((rc = d_xf.ensure(1))) return rc;
+        CU(cudaMemcpyAsync(d_xf.p, &K, sizeof(K), cudaMemcpyHostToDevice, st));   // pageable source: staged before return
+    }
     size_t pre_words = 0;
     for (auto &p : prefixes) pre_words += p.size();
     if ((rc = d_pre.ensure(pre_words))) return rc;
@@ -1126,7 +1134,10 @@ extern "C" int gs_upload_ksplat(gs_engine *e, const void *data, size_t bytes, co
         KSectionParams P = secs[i];
         P.sh_degree_out = (int)min_degree;
         P.minimum_alpha = o.minimum_alpha; P.half_cov = o.half_covariances; P.integer_centers = e->cfg.integer_based_sort; P.write_sort_centers = o.upload_sort_centers;
-        if (P.count) k_ksplat_decode<<<(P.count + 127) / 128, 128, 0, st>>>(d_file.p, P, d_pre.p + at, rs.cc.p, rs.cov.p, rs.sh.p, e->centers.p);
+        if (P.count) {
+            if (o.has_transform) k_ksplat_decode<true><<<(P.count + 127) / 128, 128, 0, st>>>(d_file.p, P, d_pre.p + at, rs.cc.p, rs.cov.p, rs.sh.p, e->centers.p, d_xf.p);
+            else k_ksplat_decode<false><<<(P.count + 127) / 128, 128, 0, st>>>(d_file.p, P, d_pre.p + at, rs.cc.p, rs.cov.p, rs.sh.p, e->centers.p, nullptr);
+        }
         at += prefixes[i].size();
     }
     CU(cudaStreamSynchronize(st));

@@ -9,6 +9,7 @@
 #pragma once
 #include "common.cuh"
 #include <cuda_fp16.h>
+#include "ksplat_transform.h"   // KTransform
 
 namespace gs {
 
@@ -49,9 +50,12 @@ __device__ __forceinline__ uint16_t to_half_three(float val) {
     return (uint16_t)((base | sign) + (mant >> shift));
 }
 
+// XF: bake the scene transform (centre.applyMatrix4 :340-342, T3 (M M^T) T3^T :461-466, SH decode -> rotate -> re-encode :663-716).
+template <bool XF>
 __global__ void __launch_bounds__(128)
 k_ksplat_decode(const unsigned char *__restrict__ file, KSectionParams P, const uint32_t *__restrict__ partial_prefix,
-                uint4 *__restrict__ cc, void *__restrict__ cov, void *__restrict__ sh_out, int4 *__restrict__ sort_centers) {
+                uint4 *__restrict__ cc, void *__restrict__ cov, void *__restrict__ sh_out, int4 *__restrict__ sort_centers,
+                const KTransform *__restrict__ xf) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.count) return;
     const unsigned char *rec = file + P.data_base + (size_t)i * P.bytes_per_splat;
@@ -88,6 +92,14 @@ k_ksplat_decode(const unsigned char *__restrict__ file, KSectionParams P, const 
         shp = rec + 24;
     }
     const uint32_t g = P.splat_offset + i;
+    if (XF) {   // Vector3.applyMatrix4 in f64 on the decoded f32 centre, stored back as f32
+        const double *T = xf->t;
+        const double x = c[0], y = c[1], z = c[2];
+        const double w = __ddiv_rn(1.0, __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(T[3], x), __dmul_rn(T[7], y)), __dmul_rn(T[11], z)), T[15]));
+        c[0] = (float)__dmul_rn(__dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(T[0], x), __dmul_rn(T[4], y)), __dmul_rn(T[8], z)), T[12]), w);
+        c[1] = (float)__dmul_rn(__dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(T[1], x), __dmul_rn(T[5], y)), __dmul_rn(T[9], z)), T[13]), w);
+        c[2] = (float)__dmul_rn(__dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(T[2], x), __dmul_rn(T[6], y)), __dmul_rn(T[10], z)), T[14]), w);
+    }
     // ---- centres + colours texel ----------------------------------------------------------------------------------------
     const uint32_t a = rgba.w >= P.minimum_alpha ? rgba.w : 0u;
     cc[g] = make_uint4((uint32_t)rgba.x | ((uint32_t)rgba.y << 8) | ((uint32_t)rgba.z << 16) | (a << 24), __float_as_uint(c[0]), __float_as_uint(c[1]),
@@ -115,7 +127,20 @@ k_ksplat_decode(const unsigned char *__restrict__ file, KSectionParams P, const 
 #pragma unroll
             for (int k = 0; k < 3; ++k) M[r][k] = __dmul_rn(R[r][k], (double)s[k]);
         auto dot = [&](int r0, int r1) { return __dadd_rn(__dadd_rn(__dmul_rn(M[r0][0], M[r1][0]), __dmul_rn(M[r0][1], M[r1][1])), __dmul_rn(M[r0][2], M[r1][2])); };
-        const double v[6] = {dot(0, 0), dot(0, 1), dot(0, 2), dot(1, 1), dot(1, 2), dot(2, 2)};
+        double v[6] = {dot(0, 0), dot(0, 1), dot(0, 2), dot(1, 1), dot(1, 2), dot(2, 2)};
+        if (XF) {   // X = S T3^T, Y = T3 X with Matrix3.multiplyMatrices' left-to-right sums
+            const double *T = xf->t;
+            const double t3[3][3] = {{T[0], T[4], T[8]}, {T[1], T[5], T[9]}, {T[2], T[6], T[10]}};
+            const double S[3][3] = {{v[0], v[1], v[2]}, {v[1], v[3], v[4]}, {v[2], v[4], v[5]}};
+            double X[3][3];
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int k = 0; k < 3; ++k)
+                    X[r][k] = __dadd_rn(__dadd_rn(__dmul_rn(S[r][0], t3[k][0]), __dmul_rn(S[r][1], t3[k][1])), __dmul_rn(S[r][2], t3[k][2]));
+            auto Y = [&](int r, int k) { return __dadd_rn(__dadd_rn(__dmul_rn(t3[r][0], X[0][k]), __dmul_rn(t3[r][1], X[1][k])), __dmul_rn(t3[r][2], X[2][k])); };
+            v[0] = Y(0, 0); v[1] = Y(0, 1); v[2] = Y(0, 2); v[3] = Y(1, 1); v[4] = Y(1, 2); v[5] = Y(2, 2);
+        }
         if (P.half_cov) {
             uint16_t *o = reinterpret_cast<uint16_t *>(cov) + (size_t)g * 6;
 #pragma unroll
@@ -129,13 +154,53 @@ k_ksplat_decode(const unsigned char *__restrict__ file, KSectionParams P, const 
     // ---- spherical harmonics: file [band][channel][coef] -> GPU [coef][channel] ------------------------------------------------
     if (P.sh_degree_out >= 1) {
         const int ncomp = P.sh_degree_out >= 2 ? 24 : 9;
-        for (int o = 0; o < ncomp; ++o) {
-            int src;
-            if (o < 9) { const int coef = o / 3, ch = o % 3; src = ch * 3 + coef; }
-            else { const int coef = (o - 9) / 3, ch = (o - 9) % 3; src = 9 + ch * 5 + coef; }
-            if (P.level == 2) reinterpret_cast<unsigned char *>(sh_out)[(size_t)g * ncomp + o] = shp[src];
-            else if (P.level == 1) reinterpret_cast<uint16_t *>(sh_out)[(size_t)g * ncomp + o] = load_unaligned<uint16_t>(shp + 2 * src);
-            else reinterpret_cast<uint16_t *>(sh_out)[(size_t)g * ncomp + o] = to_half_three(load_unaligned<float>(shp + 4 * src));
+        auto src_of = [](int o) {
+            if (o < 9) { const int coef = o / 3, ch = o % 3; return ch * 3 + coef; }
+            const int coef = (o - 9) / 3, ch = (o - 9) % 3;
+            return 9 + ch * 5 + coef;
+        };
+        if (!XF) {
+            for (int o = 0; o < ncomp; ++o) {
+                const int src = src_of(o);
+                if (P.level == 2) reinterpret_cast<unsigned char *>(sh_out)[(size_t)g * ncomp + o] = shp[src];
+                else if (P.level == 1) reinterpret_cast<uint16_t *>(sh_out)[(size_t)g * ncomp + o] = load_unaligned<uint16_t>(shp + 2 * src);
+                else reinterpret_cast<uint16_t *>(sh_out)[(size_t)g * ncomp + o] = to_half_three(load_unaligned<float>(shp + 4 * src));
+            }
+        } else {
+            // decode to JS numbers (toUncompressedFloat :12-20), rotate band by band (dot3 / dot5: sums in coefficient order), re-encode
+            const double lo = xf->sh_lo, range = __dsub_rn(xf->sh_hi, xf->sh_lo);
+            auto value = [&](int o) -> double {
+                const int src = src_of(o);
+                if (P.level == 2) return __dadd_rn(__dmul_rn(__ddiv_rn((double)shp[src], 255.0), range), lo);   // fromUint8: v / 255 * range + min
+                if (P.level == 1) return (double)half_bits_to_float(load_unaligned<uint16_t>(shp + 2 * src));
+                return (double)load_unaligned<float>(shp + 4 * src);
+            };
+            auto store = [&](int o, double r) {
+                if (P.level == 2) {   // toUint8 (:21-25)
+                    const double cl = fmin(fmax(r, lo), xf->sh_hi);
+                    const double q = floor(__dmul_rn(__ddiv_rn(__dsub_rn(cl, lo), range), 255.0));
+                    reinterpret_cast<unsigned char *>(sh_out)[(size_t)g * ncomp + o] = (unsigned char)fmin(fmax(q, 0.0), 255.0);
+                } else reinterpret_cast<uint16_t *>(sh_out)[(size_t)g * ncomp + o] = to_half_three((float)r);
+            };
+#pragma unroll 1
+            for (int ch = 0; ch < 3; ++ch) {
+                const double i0 = value(0 + ch), i1 = value(3 + ch), i2 = value(6 + ch);
+#pragma unroll
+                for (int l = 0; l < 3; ++l)
+                    store(3 * l + ch, __dadd_rn(__dadd_rn(__dmul_rn(i0, xf->m1[l][0]), __dmul_rn(i1, xf->m1[l][1])), __dmul_rn(i2, xf->m1[l][2])));
+                if (ncomp == 24) {
+                    double in[5];
+#pragma unroll
+                    for (int k = 0; k < 5; ++k) in[k] = value(9 + 3 * k + ch);
+#pragma unroll
+                    for (int l = 0; l < 5; ++l) {
+                        double acc = __dmul_rn(in[0], xf->m2[l][0]);
+#pragma unroll
+                        for (int k = 1; k < 5; ++k) acc = __dadd_rn(acc, __dmul_rn(in[k], xf->m2[l][k]));
+                        store(9 + 3 * l + ch, acc);
+                    }
+                }
+            }
         }
     }
 }

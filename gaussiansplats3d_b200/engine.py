@@ -243,11 +243,16 @@ class Engine:
             keep.append(si)
         N.check(self._lib.gs_upload_splat_data(self._h, C.byref(d)), "gs_upload_splat_data")
 
-    def upload_ksplat(self, data: bytes, *, minimum_alpha: int = 1, half_covariances: bool = False, upload_sort_centers: bool = True) -> dict:
-        """Decode a .ksplat buffer on the GPU into the splat data AND the sorter's centres (gs_upload_ksplat)."""
+    def upload_ksplat(self, data: bytes, *, minimum_alpha: int = 1, half_covariances: bool = False, upload_sort_centers: bool = True,
+                      transform16=None) -> dict:
+        """Decode a .ksplat buffer on the GPU into the splat data AND the sorter's centres (gs_upload_ksplat).
+        `transform16` (column-major 4x4): static scene transform baked into centres, covariances and spherical harmonics."""
         o = N.gs_ksplat_options()
         o.struct_size = C.sizeof(N.gs_ksplat_options)
         o.minimum_alpha, o.half_covariances, o.upload_sort_centers = minimum_alpha, 1 if half_covariances else 0, 1 if upload_sort_centers else 0
+        if transform16 is not None:
+            o.has_transform = 1
+            o.transform[:] = [float(v) for v in np.asarray(transform16, np.float64).reshape(16)]
         info = N.gs_ksplat_info()
         buf = np.frombuffer(data, dtype=np.uint8)
         N.check(self._lib.gs_upload_ksplat(self._h, N.ptr(buf), buf.size, C.byref(o), C.byref(info)), "gs_upload_ksplat")

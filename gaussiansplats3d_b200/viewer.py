@@ -171,9 +171,10 @@ class Viewer:
             self.engine.upload_centers(centers)
         self.splatRenderCount = n
 
-    def addSplatSceneFromKSplat(self, data: bytes) -> dict:  # noqa: N802
+    def addSplatSceneFromKSplat(self, data: bytes, *, position=(0.0, 0.0, 0.0), rotation=(0.0, 0.0, 0.0, 1.0), scale=(1.0, 1.0, 1.0)) -> dict:  # noqa: N802
         """Viewer.addSplatScene for a `.ksplat` buffer (KSplatLoader.loadFromFileData -> new SplatBuffer -> SplatMesh.build ->
-        'centers' message, Viewer.js:736-868, 1094-1167): header parsing on the host, every per-splat decode on the GPU."""
+        'centers' message, Viewer.js:736-868, 1094-1167): header parsing on the host, every per-splat decode on the GPU.
+        position / rotation (x, y, z, w) / scale: the SplatScene transform, baked by the decode kernel (static mesh)."""
         from . import ksplat as K
         hdr = K.parse(data)
         n = hdr.max_splat_count
@@ -184,7 +185,9 @@ class Viewer:
         self.engine = Engine(n, device=self.device, distance_map_range=1 << self.splatSortDistanceMapPrecision,
                              integer_based_sort=self.integerBasedSort, dynamic_mode=False, max_width=self.renderWidth, max_height=self.renderHeight,
                              rank=self.rank, world_size=self.world_size)
-        info = self.engine.upload_ksplat(data, half_covariances=self.halfPrecisionCovariancesOnGPU)
+        identity = tuple(position) == (0.0, 0.0, 0.0) and tuple(rotation) == (0.0, 0.0, 0.0, 1.0) and tuple(scale) == (1.0, 1.0, 1.0)
+        info = self.engine.upload_ksplat(data, half_covariances=self.halfPrecisionCovariancesOnGPU,
+                                         transform16=None if identity else TM.compose(position, rotation, scale))
         self.splatMesh.engine = self.engine
         degree = min(self.sphericalHarmonicsDegree, info["sh_degree"])
         self.splatMesh.packed = PackedScene(None, None, None, degree, None, info["splat_count"])

@@ -154,7 +154,9 @@ typedef struct gs_ksplat_options {
     uint32_t minimum_alpha;          /* splatAlphaRemovalThreshold (Viewer.js), default 1: alpha below it renders as 0            */
     uint8_t half_covariances;        /* halfPrecisionCovariancesOnGPU                                                            */
     uint8_t upload_sort_centers;     /* also fill the sorter's centres (integer or float per gs_config), default 1              */
-    uint8_t reserved[2];
+    uint8_t has_transform;           /* bake `transform` into centres, covariances and SH (static scene: SplatMesh.js:1872-1897)  */
+    uint8_t reserved[1];
+    double transform[16];            /* column-major Matrix4 of the SplatScene (position, quaternion, scale), JS doubles          */
 } gs_ksplat_options;
 typedef struct gs_ksplat_info {
     uint32_t struct_size;

@@ -146,3 +146,56 @@ def test_oracle_decode_with_scene_transform(level, deg):
                 assert np.array_equal(got.view(np.uint16), K.to_half_three(np.array(sh, np.float32).reshape(-1)).view(np.uint16))
     # the sorter's integer centres follow the transformed centres
     assert np.array_equal(baked["int_centers"][:, :3], np.floor(baked["centers"].astype(np.float64) * 1000.0 + 0.5).astype(np.int32))
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(__import__("os").environ.get("GS_TEST_KSPLAT_TRANSFORM") != "1", reason="k_ksplat_decode<true> is written but not yet validated on a GPU: set GS_TEST_KSPLAT_TRANSFORM=1")
+@pytest.mark.parametrize("level,deg", [(0, 2), (1, 2), (2, 2), (1, 1), (0, 0)])
+def test_gpu_decode_with_scene_transform(gs, level, deg):
+    """gs_upload_ksplat with a static scene transform vs the restatement (bit-exact: both follow the reference's operation order)."""
+    from gaussiansplats3d_b200 import ksplat as K
+    from gaussiansplats3d_b200 import _native as N
+    from gaussiansplats3d_b200 import three_math as TM
+    from oracle import ksplat_oracle as KO
+    raw, sh = _scene(n=20000, seed=14 + level, deg=deg)
+    q = np.array([0.21, 0.43, -0.36, 0.8]); q /= np.linalg.norm(q)
+    T = TM.compose((0.4, -0.9, 1.3), q, (1.3, 1.3, 1.3))
+    data = K.write(raw.centers, raw.scales, raw.rotations, raw.colors, sh, deg, compression_level=level, bucket_size=100 if level else K.BUCKET_SIZE)
+    want = KO.decode(data, transform16=T)
+    n = want["count"]
+    with gs.Engine(n, max_width=64, max_height=64) as e:
+        e.upload_ksplat(data, transform16=T)
+        cc = e.read_buffer(N.GS_BUF_CENTERS_COLORS, np.uint32, 4 * n).reshape(n, 4)
+        assert np.array_equal(cc, want["centers_colors"])
+        cov = e.read_buffer(N.GS_BUF_COVARIANCES, np.float32, 6 * n).reshape(n, 6)
+        assert np.array_equal(cov.view(np.uint32), want["covariances"].view(np.uint32))
+        if deg:
+            ncomp = 9 if deg == 1 else 24
+            shd = e.read_buffer(N.GS_BUF_SH, np.uint8 if level == 2 else np.uint16, ncomp * n).reshape(n, ncomp)
+            assert np.array_equal(shd, want["sh"].view(np.uint8 if level == 2 else np.uint16).reshape(n, ncomp))
+        cen = e.read_buffer(N.GS_BUF_CENTERS, np.int32, 4 * n).reshape(n, 4)
+        assert np.array_equal(cen, want["int_centers"])
+
+
+def test_host_transform_parameters_match_python(tmp_path):
+    """csrc/ksplat_transform.h (what gs_upload_ksplat hands the decode kernel) against scenes.sh_rotation_matrices, incl. a mirrored
+    and a non-uniformly scaled transform (decompose's sign / scale handling)."""
+    import subprocess
+    from pathlib import Path
+    from gaussiansplats3d_b200 import three_math as TM
+    from gaussiansplats3d_b200.scenes import rotation_of_transform, sh_rotation_matrices
+    root = Path(__file__).resolve().parent.parent
+    exe = tmp_path / "ktc"
+    subprocess.run(["/usr/bin/g++", "-O1", "-std=c++17", "-ffp-contract=off", "-o", str(exe), str(root / "oracle" / "ksplat_transform_check.cpp")], check=True)
+    rng = np.random.default_rng(6)
+    for trial in range(12):
+        q = rng.normal(size=4); q /= np.linalg.norm(q)
+        scale = (1.7, 1.7, 1.7) if trial % 3 == 0 else tuple(rng.uniform(0.4, 2.5, 3))
+        if trial % 4 == 3:
+            scale = (-scale[0], scale[1], scale[2])
+        T = TM.compose(rng.normal(size=3), q, scale)
+        out = subprocess.run([str(exe)] + [repr(float(v)) for v in T], capture_output=True, text=True, check=True)
+        vals = np.array([float(v) for v in out.stdout.split()])
+        m1, m2 = sh_rotation_matrices(rotation_of_transform(T))
+        assert np.allclose(vals[:9].reshape(3, 3), m1, rtol=0, atol=1e-15)
+        assert np.allclose(vals[9:].reshape(5, 5), m2, rtol=0, atol=1e-15)

@@ -1,5 +1,5 @@
 // ksplat_transform.h -- host-only: the doubles k_ksplat_decode<true> needs to bake a static scene transform (plain C++, no CUDA,
-// so that the same code is checked on the host by oracle/ksplat_transform_check.cpp against the Python restatement).
+// so that the very same code can be compiled and checked on the host by the test suite against the Python restatement).
 #pragma once
 #include <cmath>
 #include <cstring>

@@ -14,7 +14,7 @@ HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 LIB = CSRC / "libgsplat_b200.so"
 SOURCES = [CSRC / "engine.cu"]
-HEADERS = [CSRC / "common.cuh", CSRC / "sort_kernels.cuh", CSRC / "raster_kernels.cuh", HERE.parent / "include" / "gsplat_b200.h"]
+HEADERS = sorted(CSRC.glob("*.cuh")) + sorted(CSRC.glob("*.h")) + [HERE.parent / "include" / "gsplat_b200.h"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -149,7 +149,6 @@ def test_oracle_decode_with_scene_transform(level, deg):
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(__import__("os").environ.get("GS_TEST_KSPLAT_TRANSFORM") != "1", reason="k_ksplat_decode<true> is written but not yet validated on a GPU: set GS_TEST_KSPLAT_TRANSFORM=1")
 @pytest.mark.parametrize("level,deg", [(0, 2), (1, 2), (2, 2), (1, 1), (0, 0)])
 def test_gpu_decode_with_scene_transform(gs, level, deg):
     """gs_upload_ksplat with a static scene transform vs the restatement (bit-exact: both follow the reference's operation order)."""
@@ -199,3 +198,109 @@ def test_host_transform_parameters_match_python(tmp_path):
         m1, m2 = sh_rotation_matrices(rotation_of_transform(T))
         assert np.allclose(vals[:9].reshape(3, 3), m1, rtol=0, atol=1e-15)
         assert np.allclose(vals[9:].reshape(5, 5), m2, rtol=0, atol=1e-15)
+
+
+# ---- hand-assembled byte fixtures (tests/golden/ksplat_handmade.py): built with struct.pack from the format tables, expected values from
+# scalar arithmetic; imports neither the product nor oracle/ -- the third party that pins both ------------------------------------------------
+def _handmade(name):
+    import sys
+    from pathlib import Path
+    sys.path.insert(0, str(Path(__file__).resolve().parent / "golden"))
+    import ksplat_handmade as HM
+    data, exp = HM.fixture(name)
+    return HM, data, exp
+
+
+def _handmade_names():
+    import sys
+    from pathlib import Path
+    sys.path.insert(0, str(Path(__file__).resolve().parent / "golden"))
+    import ksplat_handmade as HM
+    return list(HM.FIXTURES)
+
+
+def _expected_arrays(exp):
+    n = exp["count"]
+    centers = np.array(exp["centers"], np.float32).reshape(n, 3)
+    cc = np.empty((n, 4), np.uint32)
+    cc[:, 0] = np.array(exp["rgba"], np.uint32)
+    cc[:, 1:] = centers.view(np.uint32)
+    cov = np.array(exp["cov"], np.float32).reshape(n, 6)
+    ic = np.array(exp["int_centers"], np.int64).astype(np.int32).reshape(n, 4)
+    sh = None
+    if exp["sh_degree"]:
+        sh = np.array(exp["sh"], np.uint8 if exp["level"] == 2 else np.uint16)
+    return centers, cc, cov, ic, sh
+
+
+@pytest.mark.parametrize("name", _handmade_names())
+def test_committed_handmade_fixture_is_current(name):
+    from pathlib import Path
+    _, data, _ = _handmade(name)
+    assert (Path(__file__).resolve().parent / "golden" / f"ksplat_handmade_{name}.ksplat").read_bytes() == data
+
+
+@pytest.mark.parametrize("name", _handmade_names())
+def test_oracle_decodes_handmade_fixture(name):
+    """Pins oracle/ksplat_oracle.py (the decoder the GPU tests compare against) to bytes and values it did not produce."""
+    from oracle import ksplat_oracle as KO
+    _, data, exp = _handmade(name)
+    centers, cc, cov, ic, sh = _expected_arrays(exp)
+    d = KO.decode(data)
+    assert d["count"] == exp["count"] and d["sh_degree"] == exp["sh_degree"]
+    assert np.array_equal(d["centers"].view(np.uint32), centers.view(np.uint32))
+    assert np.array_equal(d["centers_colors"], cc)
+    assert np.array_equal(d["int_centers"], ic)
+    assert np.array_equal(d["covariances"].view(np.uint32), cov.view(np.uint32))
+    assert np.allclose(d["scales"], np.array(exp["scales"], np.float32), rtol=0, atol=0)
+    assert np.allclose(d["rotations"], np.array(exp["rot_xyzw"], np.float32), rtol=0, atol=0)
+    if sh is not None:
+        assert np.array_equal(d["sh"].view(sh.dtype).reshape(sh.shape), sh)
+    h = d["header"]
+    assert (h.min_sh, h.max_sh) == exp["sh_range"] and tuple(h.scene_center) == exp["scene_center"] and len(h.sections) == exp["sections"]
+    # half covariances: THREE toHalfFloat (truncation) of the f32 values, via the fixture's own IEEE-based truncation
+    HM, _, _ = _handmade(name)
+    dh = KO.decode(data, half_covariances=True)
+    want = np.array([[HM.half_bits_truncated(float(v)) for v in row] for row in cov], np.uint16)
+    ok = (np.abs(cov) >= 6.2e-5) | (cov == 0)            # the fixture's truncation helper covers the normal half range
+    assert np.array_equal(dh["covariances"].view(np.uint16)[ok], want[ok])
+
+
+@pytest.mark.parametrize("name", _handmade_names())
+def test_product_parser_reads_handmade_fixture(name):
+    from gaussiansplats3d_b200 import ksplat as K
+    _, data, exp = _handmade(name)
+    h = K.parse(data)
+    assert h.compression_level == exp["level"] and h.max_splat_count == exp["count"] and h.splat_count == exp["count"]
+    assert len(h.sections) == exp["sections"] and all(s.sh_degree == exp["sh_degree"] and s.bytes_per_splat == exp["bytes_per_splat"] for s in h.sections)
+    assert (h.min_sh, h.max_sh) == exp["sh_range"] and tuple(h.scene_center) == exp["scene_center"]
+    assert h.sections[-1].data_base + h.sections[-1].max_splat_count * exp["bytes_per_splat"] == len(data)
+    assert sum(s.max_splat_count for s in h.sections) == exp["count"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", _handmade_names())
+@pytest.mark.parametrize("half_cov", [False, True])
+def test_gpu_decodes_handmade_fixture(gs, name, half_cov):
+    """gs_upload_ksplat on bytes assembled by hand, against values computed by hand (no product writer, no oracle in the loop)."""
+    from gaussiansplats3d_b200 import _native as N
+    HM, data, exp = _handmade(name)
+    centers, cc, cov, ic, sh = _expected_arrays(exp)
+    n = exp["count"]
+    with gs.Engine(n + 3, max_width=64, max_height=64) as e:
+        info = e.upload_ksplat(data, half_covariances=half_cov)
+        assert info["splat_count"] == n and info["sh_degree"] == exp["sh_degree"] and info["compression_level"] == exp["level"]
+        assert info["section_count"] == exp["sections"]
+        assert (np.float32(info["min_sh_coeff"]), np.float32(info["max_sh_coeff"])) == tuple(np.float32(v) for v in exp["sh_range"])
+        assert np.array_equal(e.read_buffer(N.GS_BUF_CENTERS_COLORS, np.uint32, 4 * n).reshape(n, 4), cc)
+        assert np.array_equal(e.read_buffer(N.GS_BUF_CENTERS, np.int32, 4 * n).reshape(n, 4), ic)
+        if half_cov:
+            got = e.read_buffer(N.GS_BUF_COVARIANCES, np.uint16, 6 * n).reshape(n, 6)
+            want = np.array([[HM.half_bits_truncated(float(v)) for v in row] for row in cov], np.uint16)
+            ok = (np.abs(cov) >= 6.2e-5) | (cov == 0)
+            assert np.array_equal(got[ok], want[ok])
+        else:
+            assert np.array_equal(e.read_buffer(N.GS_BUF_COVARIANCES, np.uint32, 6 * n).reshape(n, 6), cov.view(np.uint32))
+        if sh is not None:
+            got = e.read_buffer(N.GS_BUF_SH, sh.dtype, sh.size).reshape(sh.shape)
+            assert np.array_equal(got, sh)

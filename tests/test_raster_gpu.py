@@ -225,7 +225,6 @@ def test_frame_and_order_match_committed_fixture(gs, name):
     v.dispose()
 
 
-@pytest.mark.skipif(__import__("os").environ.get("GS_TEST_EXACT_MASKS") != "1", reason="experimental path: set GS_TEST_EXACT_MASKS=1 (validated per round before the default flips)")
 def test_exact_fine_tile_masks_render_the_same_frame(gs, oracle_mod, monkeypatch):
     """GS_EXACT_MASKS=1: ellipse-exact tile masks only drop tiles without a covered pixel, so the frame must stay within the stated
     tolerance of the oracle and (almost) bit-equal to the default path; the binned instance count does not change."""

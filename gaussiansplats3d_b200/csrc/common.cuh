@@ -9,8 +9,35 @@ extern thread_local char g_gs_err[512];
 
 #include <vector>
 #include <string.h>
+#include <stdlib.h>
 
 namespace gs {
+
+// Programmatic dependent launch (PDL): every kernel of the frame chain starts with pdl_enter() -- "my dependents may be scheduled
+// now" followed by "wait until the grids I depend on have completed and their memory is visible" -- and is launched through
+// gs_launch() with the programmatic-stream-serialization attribute.  The next kernel's CTAs are then already resident (spinning at
+// their own wait) when this one drains, which removes the launch latency and ramp-up from every kernel boundary of the frame;
+// the data dependence itself is unchanged (griddepcontrol.wait returns only after FULL completion of the predecessor).
+// A kernel launched without the attribute sees both instructions as no-ops.  GS_PDL=0 disables the attribute (A/B measurements).
+__device__ __forceinline__ void pdl_enter() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+inline bool pdl_enabled() {
+    static int on = -1;
+    if (on < 0) { const char *v = getenv("GS_PDL"); on = (v && v[0] == '0') ? 0 : 1; }
+    return on != 0;
+}
+template <typename... KArgs, typename... Args>
+static inline void gs_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    (void)cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);   // errors surface through cudaGetLastError() like a <<<>>> launch
+}
 
 // Optional per-kernel timeline: one CUDA event after every kernel launch (gs_set_profiling).  Durations are the gaps
 // between consecutive events on the engine's stream, i.e. device time of each kernel including its launch gap.

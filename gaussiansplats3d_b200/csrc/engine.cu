@@ -143,6 +143,15 @@ struct gs_engine {
     bool pending_async = false;
     gs_render_params pending_rp{};
     DevBuf<uint32_t> flush;          // L2 flush scratch (bench hygiene)
+    // pipelined frames (gs_frame_begin / gs_frame_end): device frames alternate between two buffers, the D2H copy of frame i runs on
+    // copy_stream while frame i+1 computes on `stream`
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_frame_done[2] = {nullptr, nullptr}, ev_copy_done[2] = {nullptr, nullptr};
+    cudaGraphExec_t graph_exec_alt = nullptr;     // the same frame graph with the alternate frame buffer as target
+    unsigned long long graph_key_alt[8] = {0};
+    PinBuf<uint32_t> h_pipe;                       // 2 slots x (SortControl head + RasterControl) read back per pipelined frame
+    struct PipeSlot { bool busy = false; gs_render_params rp{}; bool copied = false; } pipe[2];
+    uint32_t pipe_next = 0, pipe_oldest = 0, pipe_inflight = 0;
 
     // --- sort-only sharding by input position (shard_kernels.cuh) ---
     struct Shard {
@@ -233,7 +242,7 @@ extern "C" void gs_destroy(gs_engine *e) {
     e->centers.release(); e->scene_idx.release(); e->indexes.release(); e->precomputed.release(); e->dist.release();
     e->keys[0].release(); e->keys[1].release(); e->vals[0].release(); e->vals[1].release(); e->sorted.release();
     e->transforms.release(); e->ctl.release(); e->depthp.release(); e->tile_hist.release(); e->freq.release(); e->dist_rows_i.release(); e->dist_rows_f.release(); e->sub_idx.release(); e->sub_dist.release();
-    e->h_indexes.release(); e->h_sorted.release(); e->h_ctl.release(); e->h_frame.release(); e->flush.release(); e->prof.release();
+    e->h_indexes.release(); e->h_sorted.release(); e->h_ctl.release(); e->h_frame.release(); e->h_pipe.release(); e->flush.release(); e->prof.release();
     e->shard.block.release(); e->shard.total.release(); e->shard.ahead.release(); e->shard.block_total.release(); e->shard.delta.release(); e->shard.local_sorted.release();
     for (void *m : e->shard.opened) if (m) cudaIpcCloseMemHandle(m);
     if (e->rs.peer_attached) { if (e->rs.peer_frame) cudaIpcCloseMemHandle(e->rs.peer_frame); if (e->rs.peer_sync) cudaIpcCloseMemHandle(e->rs.peer_sync); }
@@ -241,6 +250,10 @@ extern "C" void gs_destroy(gs_engine *e) {
     for (int i = 0; i < EV_COUNT; ++i) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
     if (e->stream) cudaStreamDestroy(e->stream);
     if (e->stream2) cudaStreamDestroy(e->stream2);
+    if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+    for (int i = 0; i < 2; ++i) { if (e->ev_frame_done[i]) cudaEventDestroy(e->ev_frame_done[i]); if (e->ev_copy_done[i]) cudaEventDestroy(e->ev_copy_done[i]); }
+    if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
+    if (e->graph_exec_alt) cudaGraphExecDestroy(e->graph_exec_alt);
     if (e->ev_fork) cudaEventDestroy(e->ev_fork);
     if (e->ev_join) cudaEventDestroy(e->ev_join);
     delete e;
@@ -263,8 +276,8 @@ extern "C" int gs_upload_centers(gs_engine *e, const void *centers, const uint32
 template <int MODE>
 static void launch_depth(bool identity, int blocks, cudaStream_t st, const uint32_t *idx, const void *centers, const void *pre,
                          const uint32_t *scene, const float *tr, const DepthParams *P, uint32_t s0, uint32_t rc, int32_t *dist, SortControl *ctl) {
-    if (identity) k_depth<MODE, true><<<blocks, kDepthThreads, 0, st>>>(idx, centers, pre, scene, tr, P, s0, rc, dist, ctl);
-    else k_depth<MODE, false><<<blocks, kDepthThreads, 0, st>>>(idx, centers, pre, scene, tr, P, s0, rc, dist, ctl);
+    if (identity) gs_launch(k_depth<MODE, true>, blocks, kDepthThreads, 0, st, idx, centers, pre, scene, tr, P, s0, rc, dist, ctl);
+    else gs_launch(k_depth<MODE, false>, blocks, kDepthThreads, 0, st, idx, centers, pre, scene, tr, P, s0, rc, dist, ctl);
 }
 
 // Distance pass (sorter.cpp:29-140) over positions [lo, hi) of the index list: dist[i] and the running min/max in the control block.
@@ -311,11 +324,11 @@ static int sort_on_device(gs_engine *e, const uint32_t *d_indexes, const float *
     if (!capturing) CU(cudaEventRecord(e->ev[EV_SORT0], st));
     if (!e->have_prof_begin) e->prof.begin(st);
     if (e->ctl_dirty && !capturing) {   // first sort, or the previous one failed part-way; a completed sort leaves the block clean
-        k_sort_init<<<1, 256, 0, st>>>(e->ctl.p);
+        gs_launch(k_sort_init, 1, 256, 0, st, e->ctl.p);
         ++launches;
     }
     if (!capturing) e->ctl_dirty = true;
-    if (s0 > 0) { k_copy_head<<<std::min<uint32_t>((s0 + 255) / 256, e->sm_count * 8), 256, 0, st>>>(d_indexes, e->sorted.p, s0); ++launches; e->prof.mark("k_copy_head", st); }
+    if (s0 > 0) { gs_launch(k_copy_head, std::min<uint32_t>((s0 + 255) / 256, e->sm_count * 8), 256, 0, st, d_indexes, e->sorted.p, s0); ++launches; e->prof.mark("k_copy_head", st); }
     if (n > 0) {
         if ((rc = enqueue_depth(e, d_indexes, mvp, use_pre, s0, render_count, capturing))) return rc;
         const bool identity = (d_indexes == nullptr);
@@ -340,14 +353,14 @@ static int sort_on_device(gs_engine *e, const uint32_t *d_indexes, const float *
                                          {"k_radix_scan[depth,0]", "k_radix_scan[depth,1]", "k_radix_scan[depth,2]", "k_radix_scan[depth,3]"},
                                          {"k_radix_scatter[depth,0]", "k_radix_scatter[depth,1]", "k_radix_scatter[depth,2]", "k_radix_scatter[depth,3]"}};
         if (e->key_bits <= 16) {
-            k_bucket<uint16_t><<<tiles, kRadixThreads, 0, st>>>(dist_sorted, (uint16_t *)e->keys[0].p, n, n_dev, R, pl, write_buckets ? 1 : 0, e->ctl.p, e->tile_hist.p, stride);
+            gs_launch(k_bucket<uint16_t>, tiles, kRadixThreads, 0, st, dist_sorted, (uint16_t *)e->keys[0].p, n, n_dev, R, pl, write_buckets ? 1 : 0, e->ctl.p, e->tile_hist.p, stride);
             ++launches;
             e->prof.mark("k_bucket", st);
             if (!capturing) CU(cudaEventRecord(e->ev[EV_BUCKET], st));
             radix_sort_pairs<uint16_t, uint32_t>((uint16_t *)e->keys[0].p, (uint16_t *)e->keys[1].p, vsrc, render_count - 1u, vmode, e->vals[0].p, e->vals[1].p,
                                        e->sorted.p + s0, n, n_dev, (unsigned long long)n, pl, e->ctl.p, e->tile_hist.p, stride, true, nullptr, st, launches, &e->prof, names, true);
         } else {
-            k_bucket<uint32_t><<<tiles, kRadixThreads, 0, st>>>(dist_sorted, e->keys[0].p, n, n_dev, R, pl, write_buckets ? 1 : 0, e->ctl.p, e->tile_hist.p, stride);
+            gs_launch(k_bucket<uint32_t>, tiles, kRadixThreads, 0, st, dist_sorted, e->keys[0].p, n, n_dev, R, pl, write_buckets ? 1 : 0, e->ctl.p, e->tile_hist.p, stride);
             ++launches;
             e->prof.mark("k_bucket", st);
             if (!capturing) CU(cudaEventRecord(e->ev[EV_BUCKET], st));
@@ -566,7 +579,7 @@ static int shard_local_sort(gs_engine *e, const uint32_t *d_indexes, uint32_t s0
     KeyT *final_keys = nullptr;
     if (n) {   // slice -> keys with the GLOBAL range map -> local order + per-key runs of that order
         const uint32_t tiles = (n + kRadixTile - 1) / kRadixTile;
-        k_bucket<KeyT><<<tiles, kRadixThreads, 0, st>>>(e->dist.p + lo, (KeyT *)e->keys[0].p, n, nullptr, R, pl, 0, e->ctl.p, e->tile_hist.p, stride);
+        gs_launch(k_bucket<KeyT>, tiles, kRadixThreads, 0, st, e->dist.p + lo, (KeyT *)e->keys[0].p, n, nullptr, R, pl, 0, e->ctl.p, e->tile_hist.p, stride);
         ++launches;
         e->prof.mark("k_bucket", st);
         radix_sort_pairs<KeyT, uint32_t>((KeyT *)e->keys[0].p, (KeyT *)e->keys[1].p, identity ? nullptr : d_indexes + lo, hi - 1u,
@@ -631,9 +644,9 @@ extern "C" int gs_sort_sharded_async(gs_engine *e, const gs_sort_params *p) {
     uint32_t launches = 0;
     CU(cudaEventRecord(e->ev[EV_SORT0], st));
     e->prof.begin(st);
-    if (e->ctl_dirty) { k_sort_init<<<1, 256, 0, st>>>(e->ctl.p); ++launches; }
+    if (e->ctl_dirty) { gs_launch(k_sort_init, 1, 256, 0, st, e->ctl.p); ++launches; }
     e->ctl_dirty = true;
-    if (me == 0 && s0 > 0) { k_copy_head<<<std::min<uint32_t>((s0 + 255) / 256, e->sm_count * 8), 256, 0, st>>>(d_idx, e->sorted.p, s0); ++launches; e->prof.mark("k_copy_head", st); }
+    if (me == 0 && s0 > 0) { gs_launch(k_copy_head, std::min<uint32_t>((s0 + 255) / 256, e->sm_count * 8), 256, 0, st, d_idx, e->sorted.p, s0); ++launches; e->prof.mark("k_copy_head", st); }
     if (hi > lo) {
         if ((rc = enqueue_depth(e, d_idx, q.model_view_proj, q.use_precomputed_distances != 0, lo, hi, false))) return rc;
         ++launches;
@@ -940,8 +953,10 @@ static int enqueue_frame(gs_engine *e, const gs_sort_params *s, const gs_uniform
                                            (unsigned long long)(uintptr_t)d_idx, ((unsigned long long)e->rs.cov_format << 16) | ((unsigned long long)e->rs.sh_format << 8) | e->rs.sh_degree,
                                            e->rs.uploaded, ((unsigned long long)rp.render_count << 1) | (subset ? 1ull : 0ull)};
         if ((rc = upload_frame_params(e, q.model_view_proj, *u, rp))) return rc;
-        if (!e->graph_exec || memcmp(key, e->graph_key, sizeof(key)) != 0) {
-            if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
+        cudaGraphExec_t &gexec = e->rs.frame_parity ? e->graph_exec_alt : e->graph_exec;      // one instantiated graph per target frame buffer
+        unsigned long long *gkey = e->rs.frame_parity ? e->graph_key_alt : e->graph_key;
+        if (!gexec || memcmp(key, gkey, sizeof(key)) != 0) {
+            if (gexec) { cudaGraphExecDestroy(gexec); gexec = nullptr; }
             // buffers that the enqueue path may grow must be sized BEFORE capture (no allocation inside a capture)
             uint32_t stride = 0;
             const PassPlan pl = make_plan_bits(e->key_bits);
@@ -974,15 +989,15 @@ static int enqueue_frame(gs_engine *e, const gs_sort_params *s, const gs_uniform
             cudaError_t ce = cudaStreamEndCapture(st, &g);
             if (rc2) { if (g) cudaGraphDestroy(g); return rc2; }
             if (ce != cudaSuccess) return fail(GS_ERR_CUDA, "cudaStreamEndCapture -> %s", cudaGetErrorString(ce));
-            ce = cudaGraphInstantiate(&e->graph_exec, g, 0);
+            ce = cudaGraphInstantiate(&gexec, g, 0);
             cudaGraphDestroy(g);
-            if (ce != cudaSuccess) { e->graph_exec = nullptr; return fail(GS_ERR_CUDA, "cudaGraphInstantiate -> %s", cudaGetErrorString(ce)); }
-            memcpy(e->graph_key, key, sizeof(key));
+            if (ce != cudaSuccess) { gexec = nullptr; return fail(GS_ERR_CUDA, "cudaGraphInstantiate -> %s", cudaGetErrorString(ce)); }
+            memcpy(gkey, key, sizeof(key));
         }
-        if (e->ctl_dirty) k_sort_init<<<1, 256, 0, st>>>(e->ctl.p);   // the captured sort assumes (and leaves) a clean control block
+        if (e->ctl_dirty) gs_launch(k_sort_init, 1, 256, 0, st, e->ctl.p);   // the captured sort assumes (and leaves) a clean control block
         e->ctl_dirty = true;
         CU(cudaEventRecord(e->ev[EV_SORT0], st));
-        CU(cudaGraphLaunch(e->graph_exec, st));
+        CU(cudaGraphLaunch(gexec, st));
         e->ctl_dirty = false;
         CU(cudaEventRecord(e->ev[EV_R1], st));
         e->tm.kernel_launches = e->graph_launches;
@@ -1019,6 +1034,8 @@ extern "C" int gs_frame(gs_engine *e, const gs_sort_params *s, const gs_uniforms
     int rc = check_engine(e);
     if (rc) return rc;
     if (!s || !u || !p) return fail(GS_ERR_BAD_ARG, "gs_frame: null argument");
+    if (e->pipe_inflight) return fail(GS_ERR_NOT_READY, "gs_frame: pipelined frames are in flight (gs_frame_end first)");
+    e->rs.frame_parity = 0;
     gs_sort_params q; gs_render_params rp;
     e->no_subset = (sorted_out != nullptr);
     rc = enqueue_frame(e, s, u, p, q, rp);
@@ -1041,6 +1058,83 @@ extern "C" int gs_frame_async(gs_engine *e, const gs_sort_params *s, const gs_un
     if ((rc = enqueue_frame(e, s, u, p, q, rp))) return rc;
     e->pending_async = true;
     e->pending_rp = rp;
+    return GS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Pipelined frames: gs_frame_begin enqueues frame i (camera H2D, sort, render) and a D2H copy of its picture on a separate copy
+// stream; gs_frame_end waits for the OLDEST frame in flight and reports its errors.  Up to two frames are in flight: the device
+// frames alternate between two buffers, so frame i+1 renders while frame i's picture crosses PCIe (begin(0); loop { begin(i+1);
+// end(i); }).  Per-frame latency is that of gs_frame; throughput approaches max(compute, copy).  Multi-GPU engines that gather
+// tiles into rank 0's exported frame keep ONE buffer (the peers store into it), so there the copy only overlaps the host side.
+constexpr size_t kPipeSlotWords = 4 + (sizeof(RasterControl) + 3) / 4 + 12;   // SortControl head (3 words) + RasterControl
+static int pipe_init(gs_engine *e) {
+    if (e->copy_stream) return GS_OK;
+    CU(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        CU(cudaEventCreateWithFlags(&e->ev_frame_done[i], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&e->ev_copy_done[i], cudaEventDisableTiming));
+    }
+    int rc = e->h_pipe.ensure(2 * kPipeSlotWords);
+    if (rc) return rc;
+    const bool single = e->cfg.world_size > 1;
+    if (!single && !e->rs.frame_alt.p) {
+        cudaError_t ce = e->rs.frame_alt.ensure(e->rs.frame.n);
+        if (ce != cudaSuccess) return fail(GS_ERR_CUDA, "cudaMalloc(second frame buffer) -> %s", cudaGetErrorString(ce));
+    }
+    return GS_OK;
+}
+
+extern "C" int gs_frame_begin(gs_engine *e, const gs_sort_params *s, const gs_uniforms *u, const gs_render_params *p, void *frame_out) {
+    int rc = check_engine(e);
+    if (rc) return rc;
+    if (!s || !u || !p) return fail(GS_ERR_BAD_ARG, "gs_frame_begin: null argument");
+    if (e->pipe_inflight >= 2) return fail(GS_ERR_NOT_READY, "gs_frame_begin: two frames already in flight (call gs_frame_end)");
+    if (e->pending_async) return fail(GS_ERR_NOT_READY, "gs_frame_begin: an asynchronous frame is pending (gs_synchronize first)");
+    if ((rc = pipe_init(e))) return rc;
+    const uint32_t slot = e->pipe_next;
+    // the buffer this frame renders into must have been copied out (frame i-2, or i-1 with a single buffer)
+    CU(cudaStreamWaitEvent(e->stream, e->ev_copy_done[slot], 0));
+    if (e->cfg.world_size > 1) CU(cudaStreamWaitEvent(e->stream, e->ev_copy_done[slot ^ 1], 0));
+    e->rs.frame_parity = (e->rs.frame_alt.p && slot) ? 1 : 0;
+    gs_sort_params q; gs_render_params rp;
+    rc = enqueue_frame(e, s, u, p, q, rp);
+    if (rc) { e->rs.frame_parity = 0; return rc; }
+    cudaStream_t st = e->stream;
+    uint32_t *hs = e->h_pipe.p + slot * kPipeSlotWords;
+    CU(cudaMemcpyAsync(hs, e->ctl.p, 12, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(hs + 4, e->rs.rctl.p, sizeof(RasterControl), cudaMemcpyDeviceToHost, st));
+    CU(cudaEventRecord(e->ev_frame_done[slot], st));
+    CU(cudaStreamWaitEvent(e->copy_stream, e->ev_frame_done[slot], 0));
+    if (frame_out) CU(cudaMemcpyAsync(frame_out, raster_frame_ptr(e->rs, rp.frame_format), frame_bytes(&rp), cudaMemcpyDeviceToHost, e->copy_stream));
+    CU(cudaEventRecord(e->ev_copy_done[slot], e->copy_stream));
+    e->pipe[slot].busy = true;
+    e->pipe[slot].rp = rp;
+    e->pipe_next = slot ^ 1;
+    if (e->pipe_inflight++ == 0) e->pipe_oldest = slot;
+    return GS_OK;
+}
+
+extern "C" int gs_frame_end(gs_engine *e) {
+    int rc = check_engine(e);
+    if (rc) return rc;
+    if (e->pipe_inflight == 0) return fail(GS_ERR_NOT_READY, "gs_frame_end: no frame in flight");
+    const uint32_t slot = e->pipe_oldest;
+    CU(cudaEventSynchronize(e->ev_copy_done[slot]));
+    e->pipe[slot].busy = false;
+    e->pipe_oldest = slot ^ 1;
+    --e->pipe_inflight;
+    const uint32_t *hs = e->h_pipe.p + slot * kPipeSlotWords;
+    RasterControl rctl;
+    memcpy(&rctl, hs + 4, sizeof(rctl));
+    e->tm.tile_instances = rctl.total_instances;
+    uint32_t vis = 0;
+    for (int i = 0; i < kVisibleSlots; ++i) vis += rctl.visible_slots[i * 8];
+    e->tm.visible_splats = vis;
+    if (hs[2] & kErrBucketRange) return fail(GS_ERR_BUCKET_RANGE, "a bucket index fell outside [0,%u): distances overflow the int32/f32 range map", e->cfg.distance_map_range);
+    if (rctl.peer_timeout) return fail(GS_ERR_CUDA, "multi-GPU tile gather: a peer did not arrive within the time limit (ranks must render the same frames)");
+    if (rctl.overflow) return fail(GS_ERR_CAPACITY, "tile-instance buffer overflow: %llu instances needed, capacity %llu (raise GS_INSTANCE_FACTOR)",
+                                   (unsigned long long)rctl.total_instances, (unsigned long long)e->rs.instance_capacity);
     return GS_OK;
 }
 
@@ -1089,9 +1183,21 @@ extern "C" int gs_upload_ksplat(gs_engine *e, const void *data, size_t bytes, co
         P.splat_offset = offset; P.level = (int)level;
         P.scale_factor = ((double)block / 2.0) / (double)P.scale_range;
         if (P.data_base + (unsigned long long)P.bytes_per_splat * P.count > bytes) return fail(GS_ERR_BAD_ARG, ".ksplat truncated (section %u data)", i);
-        if (level >= 1 && P.partial_count == 0 && (unsigned long long)P.full_bucket_count * P.bucket_size < P.count) return fail(GS_ERR_BAD_ARG, ".ksplat section %u: buckets do not cover its splats", i);
+        // an untrusted file must not make the decode kernel read bucket centres or write splats outside its buffers
+        if (level >= 1 && P.count) {
+            if (P.bucket_size == 0 || storage != 12) return fail(GS_ERR_BAD_ARG, ".ksplat section %u: bucket size %u / bucket storage %u bytes (expected > 0 / 12)", i, P.bucket_size, storage);
+            if ((unsigned long long)P.full_bucket_count + P.partial_count > bucket_count) return fail(GS_ERR_BAD_ARG, ".ksplat section %u: %u full + %u partial buckets exceed its %u bucket centres", i, P.full_bucket_count, P.partial_count, bucket_count);
+        }
+        if (P.data_base > bytes || P.buckets_base > P.data_base) return fail(GS_ERR_BAD_ARG, ".ksplat truncated (section %u buckets)", i);
         std::vector<uint32_t> pre(P.partial_count + 1, 0);
-        for (uint32_t k = 0; k < P.partial_count; ++k) pre[k + 1] = pre[k] + rd32(f + P.base + 4ull * k);
+        for (uint32_t k = 0; k < P.partial_count; ++k) {
+            const unsigned long long len = rd32(f + P.base + 4ull * k);
+            if (len > P.count) return fail(GS_ERR_BAD_ARG, ".ksplat section %u: partial bucket %u claims %llu splats", i, k, len);
+            pre[k + 1] = pre[k] + (uint32_t)len;
+        }
+        if (level >= 1 && (unsigned long long)P.full_bucket_count * P.bucket_size + pre[P.partial_count] < P.count) return fail(GS_ERR_BAD_ARG, ".ksplat section %u: buckets do not cover its splats", i);
+        if ((unsigned long long)offset + P.count > max_splats || (unsigned long long)offset + P.count > e->cfg.max_splat_count)
+            return fail(GS_ERR_CAPACITY, ".ksplat sections hold more than the %u splats its header declares (engine capacity %u)", max_splats, e->cfg.max_splat_count);
         prefixes.push_back(pre);
         min_degree = std::min<uint32_t>(min_degree, (uint32_t)P.sh_degree_file);
         base += (unsigned long long)P.bytes_per_splat * P.count + buckets_bytes;
@@ -1251,6 +1357,7 @@ extern "C" int gs_peer_export(gs_engine *e, void *frame_handle, void *sync_handl
     e->rs.peer_sync = e->rs.peer_sync_local.p;
     e->rs.peer_root = true;
     if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
+    if (e->graph_exec_alt) { cudaGraphExecDestroy(e->graph_exec_alt); e->graph_exec_alt = nullptr; }
     return GS_OK;
 }
 extern "C" int gs_peer_attach(gs_engine *e, const void *frame_handle, const void *sync_handle) {

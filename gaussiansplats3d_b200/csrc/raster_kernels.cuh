@@ -101,6 +101,7 @@ struct ProjParams {
     int tiles_x, tiles_y;
     uint32_t rank, world;
     int width, height;
+    int tile_shift;                    // log2 of the fine-tile edge in pixels: 4 (16 px) or 5 (32 px, frames beyond ~2048x1024)
 };
 
 struct DynamicUniforms {               // only read in dynamic / optional-effects / 8-bit SH modes
@@ -158,6 +159,7 @@ __global__ void __launch_bounds__(kProjThreads)
 k_project(const uint4 *__restrict__ cc, const void *__restrict__ cov, const void *__restrict__ sh, int sh_data_degree,
           const uint32_t *__restrict__ scene_idx, const DynamicUniforms *__restrict__ dyn, const ProjParams *__restrict__ Pp, uint32_t count,
           SplatRecord *__restrict__ rec, ushort4 *__restrict__ rects, RasterControl *rctl) {
+    pdl_enter();
     // per-frame parameters: device memory -> shared memory once per CTA (graph-replayable, broadcast reads afterwards)
     __shared__ ProjParams s_P;
     {
@@ -354,8 +356,8 @@ k_project(const uint4 *__restrict__ cc, const void *__restrict__ cov, const void
                     if (fx1 >= 0.f && fy1 >= 0.f && fx0 <= W1 && fy0 <= H1 && fx0 <= fx1 && fy0 <= fy1) {
                         const int px0 = (int)fmaxf(fx0, 0.f), px1 = (int)fminf(fx1, W1);
                         const int py0 = (int)fmaxf(fy0, 0.f), py1 = (int)fminf(fy1, H1);
-                        rect = make_ushort4((unsigned short)(px0 >> kTileShift), (unsigned short)(py0 >> kTileShift),
-                                            (unsigned short)(px1 >> kTileShift), (unsigned short)(py1 >> kTileShift));
+                        rect = make_ushort4((unsigned short)(px0 >> P.tile_shift), (unsigned short)(py0 >> P.tile_shift),
+                                            (unsigned short)(px1 >> P.tile_shift), (unsigned short)(py1 >> P.tile_shift));
                         visible = 1;
                     }
                 }
@@ -384,25 +386,6 @@ k_project(const uint4 *__restrict__ cc, const void *__restrict__ cov, const void
     }
     const uint32_t nvis = __popc(__ballot_sync(0xffffffffu, visible));
     if ((threadIdx.x & 31) == 0 && nvis) atomicAdd(&rctl->visible_slots[((blockIdx.x * (kProjThreads / 32) + (threadIdx.x >> 5)) & (kVisibleSlots - 1)) * 8], nvis);
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// Optional (GS_EXACT_MASKS=1, off by default until measured on the GPU): per splat, the tiles of its rect that can hold a covered
-// pixel (ellipse_mask.h) instead of the whole AABB -- on the 1.2 M bonsai frame 35 % of the (splat, fine tile) pairs the blend walks
-// are AABB corners the ellipse never reaches (CPU count over the oracle's projection).  k_tile_emit ANDs the result into the
-// instance masks; instance counts and the tile sort are unchanged, the blend's list filter drops the empty tiles.
-__global__ void __launch_bounds__(256)
-k_fine_masks(const SplatRecord *__restrict__ rec, const ushort4 *__restrict__ rects, uint32_t count, unsigned long long *__restrict__ fmask) {
-    const uint32_t s = blockIdx.x * 256u + threadIdx.x;
-    if (s >= count) return;
-    const ushort4 r = rects[s];
-    unsigned long long bits = 0;
-    if (r.z >= r.x && r.w >= r.y) {
-        const float4 a0 = __ldg(reinterpret_cast<const float4 *>(rec + s));          // cx, cy, g1x, g1y
-        const float4 a1 = __ldg(reinterpret_cast<const float4 *>(rec + s) + 1);      // g2x, g2y, ...
-        bits = ellipse_tile_bitmap((int)r.x, (int)r.y, (int)r.z, (int)r.w, a0.x, a0.y, a0.z, a0.w, a1.x, a1.y);
-    }
-    fmask[s] = bits;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -475,6 +458,7 @@ __global__ void __launch_bounds__(kBinThreads)
 k_tile_count(const uint32_t *__restrict__ order, uint32_t render_count_host, const unsigned long long *__restrict__ n_dev,
              const ushort4 *__restrict__ rects, uint32_t *__restrict__ block_sums, uint32_t *__restrict__ warp_sums, uint32_t *__restrict__ super_sums,
              OwnMask own, int sharded) {
+    pdl_enter();
     const uint32_t render_count = n_dev ? (uint32_t)*n_dev : render_count_host;
     __shared__ uint32_t s_w[kBinThreads / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -500,13 +484,13 @@ k_tile_count(const uint32_t *__restrict__ order, uint32_t render_count_host, con
 
 // pass 2: write (coarse tile id, {fine mask, splat id}) for every instance, in draw order.  One item at a time (rolled loop, no
 // per-thread arrays): the warp's base offset comes from pass 1's sums, the offsets inside an item from a warp scan.
-template <bool EXACT>
 __global__ void __launch_bounds__(kBinThreads)
 k_tile_emit(const uint32_t *__restrict__ order, uint32_t render_count_host, const unsigned long long *__restrict__ n_dev,
             const ushort4 *__restrict__ rects, const uint32_t *__restrict__ block_sums, const uint32_t *__restrict__ warp_sums,
             const uint32_t *__restrict__ super_sums, int coarse_x,
             uint16_t *__restrict__ keys, unsigned long long *__restrict__ vals, unsigned long long capacity, RasterControl *rctl, OwnMask own,
-            int sharded, const unsigned long long *__restrict__ fmask) {
+            int sharded) {
+    pdl_enter();
     const uint32_t render_count = n_dev ? (uint32_t)*n_dev : render_count_host;
     __shared__ unsigned long long s_prefix;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -534,8 +518,6 @@ k_tile_emit(const uint32_t *__restrict__ order, uint32_t render_count_host, cons
             r = rects[sid];
             cnt = coarse_instances(r, own, sharded != 0);
         }
-        unsigned long long fm = ~0ull;
-        if (EXACT && cnt) fm = fmask[sid];
         const uint32_t inc = warp_inclusive_scan(cnt);
         unsigned long long w = w0 + (inc - cnt);
         w0 += __shfl_sync(0xffffffffu, inc, 31);
@@ -544,8 +526,7 @@ k_tile_emit(const uint32_t *__restrict__ order, uint32_t render_count_host, cons
         if (cnt && single) {   // the common case: the splat sits inside one coarse tile
             const int fx0 = (int)r.x - cx0 * kCoarseW, fx1 = (int)r.z - cx0 * kCoarseW, fy0 = (int)r.y - cy0 * kCoarseH, fy1 = (int)r.w - cy0 * kCoarseH;
             const uint32_t rowsel = (0x01010101u >> (8 * (kCoarseH - 1 - (fy1 - fy0)))) << (8 * fy0);
-            uint32_t mask = (((1u << (fx1 - fx0 + 1)) - 1u) << fx0) * rowsel;
-            if (EXACT && fm != ~0ull) mask &= coarse_mask_from_bitmap((int)r.x, (int)r.y, (int)r.w, fm, cx0, cy0);
+            const uint32_t mask = (((1u << (fx1 - fx0 + 1)) - 1u) << fx0) * rowsel;
             if (w < capacity) {
                 keys[w] = (uint16_t)(cy0 * coarse_x + cx0);
                 vals[w] = ((unsigned long long)mask << 32) | sid;
@@ -563,8 +544,7 @@ k_tile_emit(const uint32_t *__restrict__ order, uint32_t render_count_host, cons
                 for (int cx = cx0; cx <= cx1; ++cx) {
                     if (sharded && !own_diag(own, cx + cy)) continue;
                     const int fx0 = max((int)r.x, cx * kCoarseW) - cx * kCoarseW, fx1 = min((int)r.z, cx * kCoarseW + kCoarseW - 1) - cx * kCoarseW;
-                    uint32_t mask = (((1u << (fx1 - fx0 + 1)) - 1u) << fx0) * rowsel;
-                    if (EXACT && fm != ~0ull) mask &= coarse_mask_from_bitmap((int)r.x, (int)r.y, (int)r.w, fm, cx, cy);
+                    const uint32_t mask = (((1u << (fx1 - fx0 + 1)) - 1u) << fx0) * rowsel;
                     if (w < capacity) {
                         keys[w] = (uint16_t)(cy * coarse_x + cx);
                         vals[w] = ((unsigned long long)mask << 32) | sid;
@@ -611,6 +591,211 @@ k_tile_emit(const uint32_t *__restrict__ order, uint32_t render_count_host, cons
     if (overflow) rctl->overflow = 1;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Binning v2: a COUNTING SORT of the coarse-tile instances straight from the draw order -- count, scan, place -- instead of
+// emit + a radix sort of the emitted (key, value) pairs.  One instance is written once (8 B) at its final slot of its coarse tile's
+// list.  Up to 1024 coarse tiles in ONE pass (3840x2160 has 1020), so the 4K frame no longer needs a second radix pass.
+//   k_bin_count : per chunk of draw ranks, instances per coarse tile            -> hist[tile][chunk], totals[tile]
+//   k_bin_scan  : per tile: exclusive scan over chunks + base of the tile's list -> hist becomes offsets, ranges[tile]
+//   k_bin_place : per chunk: stable rank of every instance inside the chunk (per-warp lane masks in shared memory: a splat touches a
+//                 coarse tile at most once, so the instances of one tile in one warp round ARE a 32-bit lane mask and the rank of lane l
+//                 is popc(mask & lanes_below(l))) + the chunk's offset -> list[slot] = {fine mask, splat id}
+// Rank order inside a chunk = (warp, round, lane) = draw-rank order (warp-striped, as in the radix kernels).
+constexpr int kBinTiles = 256;      // coarse tiles per frame in this path (8-bit bins)
+constexpr int kBinRanks = 2048;     // draw ranks per CTA = kWarps * 32 * kItems in every configuration
+template <int CFG> struct Bin2Cfg;
+template <> struct Bin2Cfg<0> { static constexpr int kWarps = 16, kItems = 4; };     // 32 KB shared in k_bin_place
+template <> struct Bin2Cfg<1> { static constexpr int kWarps = 8, kItems = 8; };      // 16 KB shared
+
+__device__ __forceinline__ uint32_t fine_mask_in_coarse(int rx0, int ry0, int rx1, int ry1, int cx, int cy) {
+    const int fx0 = max(rx0, cx * kCoarseW) - cx * kCoarseW, fx1 = min(rx1, cx * kCoarseW + kCoarseW - 1) - cx * kCoarseW;
+    const int fy0 = max(ry0, cy * kCoarseH) - cy * kCoarseH, fy1 = min(ry1, cy * kCoarseH + kCoarseH - 1) - cy * kCoarseH;
+    const uint32_t rowsel = (0x01010101u >> (8 * (kCoarseH - 1 - (fy1 - fy0)))) << (8 * fy0);
+    return (((1u << (fx1 - fx0 + 1)) - 1u) << fx0) * rowsel;
+}
+
+// Calls f(owner lane, owner's splat id, coarse tile id, fine mask) for every instance of this warp round.  Splats over a handful of
+// coarse tiles are walked by their own lane; the few huge ones (> 32 coarse tiles) by the whole warp, 32 tiles per step.
+// Must be called by all 32 lanes.  f must not contain warp-synchronous operations.
+template <typename F>
+__device__ __forceinline__ void round_instances(bool valid, uint32_t sid, ushort4 r, int coarse_x, const OwnMask &own, bool sharded, F f) {
+    const int lane = threadIdx.x & 31;
+    const bool nonempty = valid && r.z >= r.x && r.w >= r.y;
+    const int cx0 = r.x >> kCoarseShiftX, cx1 = r.z >> kCoarseShiftX, cy0 = r.y >> kCoarseShiftY, cy1 = r.w >> kCoarseShiftY;
+    const bool big = nonempty && (uint32_t)(cx1 - cx0 + 1) * (uint32_t)(cy1 - cy0 + 1) > 32u;
+    if (nonempty && !big) {
+#pragma unroll 1
+        for (int cy = cy0; cy <= cy1; ++cy)
+#pragma unroll 1
+            for (int cx = cx0; cx <= cx1; ++cx) {      // one iteration for most splats
+                if (sharded && !own_diag(own, cx + cy)) continue;
+                f(lane, sid, cy * coarse_x + cx, fine_mask_in_coarse((int)r.x, (int)r.y, (int)r.z, (int)r.w, cx, cy));
+            }
+    }
+    uint32_t multi = __ballot_sync(0xffffffffu, big);
+    while (multi) {
+        const int src = __ffs(multi) - 1;
+        multi &= multi - 1;
+        const uint32_t bsid = __shfl_sync(0xffffffffu, sid, src);
+        const int bx0 = __shfl_sync(0xffffffffu, (int)r.x, src), by0 = __shfl_sync(0xffffffffu, (int)r.y, src);
+        const int bx1 = __shfl_sync(0xffffffffu, (int)r.z, src), by1 = __shfl_sync(0xffffffffu, (int)r.w, src);
+        const int ccx0 = bx0 >> kCoarseShiftX, ccy0 = by0 >> kCoarseShiftY;
+        const int cw = (bx1 >> kCoarseShiftX) - ccx0 + 1, ntile = cw * ((by1 >> kCoarseShiftY) - ccy0 + 1);
+        for (int i = lane; i < ntile; i += 32) {
+            const int cy = ccy0 + i / cw, cx = ccx0 + i % cw;
+            if (sharded && !own_diag(own, cx + cy)) continue;
+            f(src, bsid, cy * coarse_x + cx, fine_mask_in_coarse(bx0, by0, bx1, by1, cx, cy));
+        }
+    }
+}
+
+template <int CFG>
+__global__ void __launch_bounds__(Bin2Cfg<CFG>::kWarps * 32)
+k_bin_count(const uint32_t *__restrict__ order, uint32_t render_count_host, const unsigned long long *__restrict__ n_dev, const ushort4 *__restrict__ rects,
+            int coarse_x, uint32_t nt, uint32_t *__restrict__ hist, uint32_t stride, uint32_t *__restrict__ totals, ushort4 *__restrict__ rect_by_rank,
+            OwnMask own, int sharded) {
+    pdl_enter();
+    constexpr int W = Bin2Cfg<CFG>::kWarps, ITEMS = Bin2Cfg<CFG>::kItems, NT = kBinTiles;
+    const uint32_t n = n_dev ? (uint32_t)*n_dev : render_count_host;
+    const uint32_t base = blockIdx.x * (uint32_t)(W * 32 * ITEMS);
+    if (base >= n) return;
+    __shared__ uint32_t s_hist[NT];
+    for (uint32_t t = threadIdx.x; t < nt; t += W * 32) s_hist[t] = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t run = base + (uint32_t)warp * (32 * ITEMS) + lane;
+    uint32_t sid[ITEMS];
+    ushort4 rc[ITEMS];
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        const uint32_t p = run + (uint32_t)k * 32;
+        sid[k] = p < n ? ld_nc_u32(order + (n - 1u - p)) : 0xffffffffu;
+    }
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) rc[k] = sid[k] != 0xffffffffu ? rects[sid[k]] : make_ushort4(1, 1, 0, 0);
+    // the gathered rects are left in DRAW-RANK order for k_bin_place: its reads are then streams, not a second random gather
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        const uint32_t p = run + (uint32_t)k * 32;
+        if (p < n) rect_by_rank[p] = rc[k];
+    }
+#pragma unroll 1
+    for (int k = 0; k < ITEMS; ++k) {
+        uint32_t id = 0; ushort4 r = make_ushort4(1, 1, 0, 0);
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) if (j == k) { id = sid[j]; r = rc[j]; }      // register select (no local-memory indexing)
+        round_instances(id != 0xffffffffu, id, r, coarse_x, own, sharded != 0, [&](int, uint32_t, int t, uint32_t) { atomicAdd(&s_hist[t], 1u); });
+    }
+    __syncthreads();
+    for (uint32_t t = threadIdx.x; t < nt; t += W * 32) {
+        const uint32_t v = s_hist[t];
+        hist[(size_t)t * stride + blockIdx.x] = v;
+        if (v) atomicAdd(&totals[t], v);
+    }
+}
+
+// One CTA per coarse tile: where its list starts (all smaller tiles' totals) and the running offset of every chunk inside it.
+__global__ void __launch_bounds__(1024)
+k_bin_scan(uint32_t *__restrict__ hist, uint32_t stride, uint32_t ranks_per_chunk, uint32_t render_count_host, const unsigned long long *__restrict__ n_dev,
+           const uint32_t *__restrict__ totals, uint32_t nt, uint2 *__restrict__ ranges, RasterControl *rctl) {
+    pdl_enter();
+    __shared__ uint32_t s_scan[40];
+    __shared__ uint32_t s_carry;
+    const uint32_t n = n_dev ? (uint32_t)*n_dev : render_count_host;
+    const uint32_t nchunks = (uint32_t)(((uint64_t)n + ranks_per_chunk - 1) / ranks_per_chunk);
+    const uint32_t d = blockIdx.x;
+    {
+        uint32_t total;
+        const uint32_t c = threadIdx.x < d ? totals[threadIdx.x] : 0u;
+        (void)block_exclusive_scan<1024>(c, s_scan, total);
+        if (threadIdx.x == 0) {
+            s_carry = total;
+            const uint32_t mine = totals[d];
+            ranges[d] = make_uint2(total, total + mine);
+            if (d == nt - 1) rctl->total_instances = (unsigned long long)total + mine;
+        }
+    }
+    __syncthreads();
+    uint32_t *col = hist + (size_t)d * stride;
+    for (uint32_t b = 0; b < nchunks; b += 1024) {
+        const uint32_t t = b + threadIdx.x;
+        const uint32_t v = t < nchunks ? col[t] : 0u;
+        uint32_t total;
+        const uint32_t ex = block_exclusive_scan<1024>(v, s_scan, total);
+        const uint32_t carry = s_carry;
+        if (t < nchunks) col[t] = ex + carry;
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry = carry + total;
+        __syncthreads();
+    }
+}
+
+template <int CFG>
+__global__ void __launch_bounds__(Bin2Cfg<CFG>::kWarps * 32)
+k_bin_place(const uint32_t *__restrict__ order, uint32_t render_count_host, const unsigned long long *__restrict__ n_dev, const ushort4 *__restrict__ rect_by_rank,
+            int coarse_x, uint32_t nt, const uint32_t *__restrict__ offsets, uint32_t stride, unsigned long long *__restrict__ list, unsigned long long capacity,
+            RasterControl *rctl, OwnMask own, int sharded) {
+    pdl_enter();
+    constexpr int W = Bin2Cfg<CFG>::kWarps, ITEMS = Bin2Cfg<CFG>::kItems, NT = kBinTiles;
+    const uint32_t n = n_dev ? (uint32_t)*n_dev : render_count_host;
+    const uint32_t base = blockIdx.x * (uint32_t)(W * 32 * ITEMS);
+    if (base >= n) return;
+    __shared__ uint32_t s_pre[W][NT];      // instances of this warp per tile, then: END of the slots this warp has handed out in the tile's list
+    __shared__ uint32_t s_mask[W][NT];     // lanes of the current round that touch the tile
+    for (uint32_t i = threadIdx.x; i < (uint32_t)(W * NT); i += W * 32) (&s_pre[0][0])[i] = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t run = base + (uint32_t)warp * (32 * ITEMS) + lane;
+    uint32_t sid[ITEMS];
+    ushort4 rc[ITEMS];
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        const uint32_t p = run + (uint32_t)k * 32;
+        sid[k] = p < n ? ld_nc_u32(order + (n - 1u - p)) : 0xffffffffu;
+        rc[k] = p < n ? rect_by_rank[p] : make_ushort4(1, 1, 0, 0);
+    }
+    uint32_t *my_pre = s_pre[warp], *my_mask = s_mask[warp];
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k)
+        round_instances(sid[k] != 0xffffffffu, sid[k], rc[k], coarse_x, own, sharded != 0, [&](int, uint32_t, int t, uint32_t) { atomicAdd(&my_pre[t], 1u); });
+    __syncthreads();
+    for (uint32_t t = threadIdx.x; t < nt; t += W * 32) {   // counts -> first slot of each warp (chunk offset + earlier warps)
+        uint32_t at = offsets[(size_t)t * stride + blockIdx.x];
+#pragma unroll
+        for (int w = 0; w < W; ++w) {
+            const uint32_t c = s_pre[w][t];
+            s_pre[w][t] = at;
+            at += c;
+        }
+    }
+    __syncthreads();
+    bool overflow = false;
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        const bool valid = sid[k] != 0xffffffffu;
+        // a round: (1) clear the warp's lane masks, (2) every instance sets its owner's bit in its tile's mask and takes one slot of the
+        // tile's list, (3) with all bits in place, the instance of lane l sits popc(mask & lanes below l) after the round's first slot,
+        // which is the tile's new end minus the round's population.
+#pragma unroll
+        for (int i = 0; i < NT / 32; ++i) my_mask[i * 32 + lane] = 0u;
+        __syncwarp();
+        round_instances(valid, sid[k], rc[k], coarse_x, own, sharded != 0, [&](int owner, uint32_t, int t, uint32_t) {
+            atomicOr(&my_mask[t], 1u << owner);
+            atomicAdd(&my_pre[t], 1u);
+        });
+        __syncwarp();
+        round_instances(valid, sid[k], rc[k], coarse_x, own, sharded != 0, [&](int owner, uint32_t sid_o, int t, uint32_t fmask) {
+            const uint32_t m = my_mask[t];
+            const unsigned long long at = (unsigned long long)(my_pre[t] - (uint32_t)__popc(m)) + __popc(m & ((1u << owner) - 1u));
+            if (at < capacity) list[at] = ((unsigned long long)fmask << 32) | sid_o;
+            else overflow = true;
+        });
+        __syncwarp();
+    }
+    if (overflow) rctl->overflow = 1;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // Sharded frames (world_size > 1): the depth sort of a rank covers only the splats whose screen rect touches one of ITS coarse tiles.
 // Any subset, bucketed with the GLOBAL min/max and kept in input order, sorts into exactly the global order restricted to that subset
@@ -619,6 +804,7 @@ k_tile_emit(const uint32_t *__restrict__ order, uint32_t render_count_host, cons
 __global__ void __launch_bounds__(kBinThreads)
 k_subset_count(const uint32_t *__restrict__ indexes, uint32_t count, const ushort4 *__restrict__ rects, OwnMask own,
                uint32_t *__restrict__ block_sums, uint32_t *__restrict__ warp_sums, uint32_t *__restrict__ super_sums) {
+    pdl_enter();
     __shared__ uint32_t s_w[kBinThreads / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t run = blockIdx.x * kBinTile + (uint32_t)warp * (32 * kBinItems) + lane;
@@ -644,6 +830,7 @@ __global__ void __launch_bounds__(kBinThreads)
 k_subset_emit(const uint32_t *__restrict__ indexes, uint32_t count, const ushort4 *__restrict__ rects, OwnMask own,
               const uint32_t *__restrict__ block_sums, const uint32_t *__restrict__ warp_sums, const uint32_t *__restrict__ super_sums,
               const int32_t *__restrict__ dist, uint32_t *__restrict__ sub_idx, int32_t *__restrict__ sub_dist, RasterControl *rctl) {
+    pdl_enter();
     __shared__ uint32_t s_prefix;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t before = (uint32_t)chunk_prefix(block_sums, super_sums);
@@ -676,7 +863,8 @@ k_subset_emit(const uint32_t *__restrict__ indexes, uint32_t count, const ushort
     }
 }
 
-__global__ void k_raster_init(RasterControl *rctl, SortControl *ctl, uint2 *ranges, uint32_t ntiles, uint32_t *super_sums, uint32_t nsuper) {
+__global__ void k_raster_init(RasterControl *rctl, SortControl *ctl, uint2 *ranges, uint32_t ntiles, uint32_t *super_sums, uint32_t nsuper, uint32_t *bin_totals) {
+    pdl_enter();
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     if (tid == 0) {
@@ -689,6 +877,7 @@ __global__ void k_raster_init(RasterControl *rctl, SortControl *ctl, uint2 *rang
     for (size_t i = tid; i < ntiles; i += stride) ranges[i] = make_uint2(0xffffffffu, 0u); // empty: first > last
     for (size_t i = tid; i < (size_t)kVisibleSlots * 8; i += stride) rctl->visible_slots[i] = 0;
     for (size_t i = tid; i < nsuper; i += stride) super_sums[i] = 0;
+    if (bin_totals) for (size_t i = tid; i < 1024; i += stride) bin_totals[i] = 0;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -710,6 +899,7 @@ template <int FORMAT>
 __global__ void __launch_bounds__(kBlendThreads)
 k_blend(const uint2 *__restrict__ ranges, const unsigned long long *__restrict__ list, const SplatRecord *__restrict__ rec, int tiles_x,
         int tiles_y, int coarse_x, uint32_t rank, uint32_t world, int width, int height, int flip_y, void *__restrict__ frame) {
+    pdl_enter();
     __shared__ float4 s_rec[kBlendThreads][3];
     __shared__ uint32_t s_ids[kBlendScan];
     __shared__ uint32_t s_cnt[2][4][2];
@@ -830,6 +1020,175 @@ k_blend(const uint2 *__restrict__ ranges, const unsigned long long *__restrict__
     if (world > 1) __threadfence_system();   // the frame may live in a peer GPU's memory (fused tile gather): publish before the signal
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Blend v2: one CTA per fine tile; warp w owns an 8x8-px BLOCK of it, a lane owns two vertically adjacent pixels.  The fine tile is
+// 16 px (S = 1: 4 warps) or 32 px (S = 2: 16 warps, frames beyond 256 coarse tiles of 128x64 px).  Differences from round 1's k_blend,
+// all aimed at issuing fewer instructions (the blend is FP32-issue bound, not HBM bound):
+//   * the thread that stages a splat record into shared memory also decides EXACTLY which of the tile's blocks the ellipse can
+//     reach (minimum of the quadratic over the block's rectangle of pixel centres, ellipse_mask.h) -- no AABB-corner work at all;
+//   * a warp then walks only the records that touch ITS block (one 32-bit word of touch bits per staging warp), ~45 instructions per
+//     record for its 64 pixels, and stops on its own as soon as its 64 pixels are saturated;
+//   * opacity is folded into the exponent (ex2(q * k + log2 a)), one multiply less per pixel.
+// Same arithmetic otherwise: q = u^2 + w^2 from the inverse quad map, alpha = exp(-4 q) a for q <= 1 (A = 8 q <= 8), front to back.
+
+// Which of a tile's 8x8-px blocks can hold a pixel the splat covers: exact minimum of q over each block's rectangle of pixel
+// centres (ellipse_mask.h), only for the blocks the ellipse's AABB reaches.  a0 = cx, cy, g1x, g1y; a1 = g2x, g2y, half2(hx, hy), alpha.
+// NB = blocks per tile row (2 or 4).  Not inlined: the caller's composite loop is register-bound and this runs once per staged record.
+template <int NB>
+__device__ __noinline__ uint32_t block_touch_mask(float4 a0, float4 a1, float tile_x0, float tile_y0) {
+    if (!(a1.w > 0.0f)) return 0u;
+    const uint32_t hb = __float_as_uint(a1.z);
+    const __half2 hh = *reinterpret_cast<const __half2 *>(&hb);
+    const float hx = __low2float(hh), hy = __high2float(hh);
+    const float qxx = a0.z * a0.z + a1.x * a1.x, qxy = a0.z * a0.w + a1.x * a1.y, qyy = a0.w * a0.w + a1.y * a1.y;
+    const float X0 = tile_x0 - a0.x, Y0 = tile_y0 - a0.y;      // first pixel centre of the tile, relative to the splat centre
+    // block i spans [X0 + 8 i, X0 + 8 i + 7]; it meets [-hx, hx] iff  (-hx - X0 - 7) / 8 <= i <= (hx - X0) / 8
+    const int ix0 = max(0, (int)ceilf((-hx - X0 - 7.0f) * 0.125f)), ix1 = min(NB - 1, (int)floorf((hx - X0) * 0.125f));
+    const int iy0 = max(0, (int)ceilf((-hy - Y0 - 7.0f) * 0.125f)), iy1 = min(NB - 1, (int)floorf((hy - Y0) * 0.125f));
+    uint32_t bm = 0;
+#pragma unroll 1
+    for (int iy = iy0; iy <= iy1; ++iy) {
+        const float by0 = Y0 + (float)(8 * iy), by1 = by0 + 7.0f;
+#pragma unroll 1
+        for (int ix = ix0; ix <= ix1; ++ix) {
+            const float bx0 = X0 + (float)(8 * ix), bx1 = bx0 + 7.0f;
+            if (ellipse_min_q(bx0, bx1, by0, by1, qxx, qxy, qyy) <= 1.0f + kEllipseSlack) bm |= 1u << (iy * NB + ix);
+        }
+    }
+    return bm;
+}
+
+template <int FORMAT, int S>
+__global__ void __launch_bounds__(128 * S * S, S == 1 ? 10 : 2)
+k_blend2(const uint2 *__restrict__ ranges, const unsigned long long *__restrict__ list, const SplatRecord *__restrict__ rec, int tiles_x,
+         int tiles_y, int coarse_x, uint32_t rank, uint32_t world, int width, int height, int flip_y, void *__restrict__ frame) {
+    pdl_enter();
+    constexpr int THREADS = 128 * S * S, WARPS = THREADS / 32, NB = 2 * S, TILE = 16 * S, BATCH = 4 * THREADS;
+    __shared__ float4 s_rec[THREADS][3];
+    __shared__ uint32_t s_ids[BATCH];
+    __shared__ uint32_t s_cnt[4 * WARPS + 1];   // [round][warp] survivors of the filter -> exclusive offsets; last = total
+    __shared__ uint32_t s_touch[WARPS][WARPS];  // [block][staging warp] staged records that reach the block
+    const uint32_t coarse = blockIdx.x / kFinePerCoarse, sub = blockIdx.x % kFinePerCoarse;
+    const int ccx = (int)(coarse % (uint32_t)coarse_x), ccy = (int)(coarse / (uint32_t)coarse_x);
+    const int tx = ccx * kCoarseW + (int)(sub & (kCoarseW - 1)), ty = ccy * kCoarseH + (int)(sub >> kCoarseShiftX);
+    if (tx >= tiles_x || ty >= tiles_y) return;
+    if (!owns_coarse(ccx, ccy, rank, world)) return;   // another GPU's tile
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int x = tx * TILE + (warp % NB) * 8 + (lane & 7), y0 = ty * TILE + (warp / NB) * 8 + (lane >> 3) * 2;
+    const float pxc = (float)x + 0.5f, pyc = (float)y0 + 0.5f;
+    const float tile_x0 = (float)(tx * TILE) + 0.5f, tile_y0 = (float)(ty * TILE) + 0.5f;    // first pixel centre of the tile
+    // pixels outside the frame start saturated so that they never keep a warp alive
+    float T0 = (x < width && y0 < height) ? 1.0f : 0.0f, T1 = (x < width && y0 + 1 < height) ? 1.0f : 0.0f;
+    float r0 = 0.f, g0 = 0.f, b0 = 0.f, r1 = 0.f, g1 = 0.f, b1 = 0.f;
+    bool wdone = !__any_sync(0xffffffffu, fmaxf(T0, T1) >= kTransmittanceCutoff);
+    const uint2 rg = ranges[coarse];
+    const uint32_t lt = lanemask_lt();
+    for (uint32_t base = rg.x; base < rg.y; base += BATCH) {
+        if (__syncthreads_and(wdone)) break;
+        // ---- filter 4 x THREADS list entries by this tile's mask bit; order-preserving compaction (order: round, warp, lane) ------
+        uint32_t ids[4], bal[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t i = base + (uint32_t)k * THREADS + threadIdx.x;
+            bool hit = false;
+            ids[k] = 0;
+            if (i < rg.y) {
+                const unsigned long long e = __ldg(list + i);
+                hit = ((uint32_t)(e >> 32) >> sub) & 1u;
+                ids[k] = (uint32_t)e;
+            }
+            bal[k] = __ballot_sync(0xffffffffu, hit);
+            if (lane == 0) s_cnt[k * WARPS + warp] = __popc(bal[k]);
+        }
+        __syncthreads();
+        if (warp == 0) {      // exclusive scan of the 4 * WARPS counts
+            uint32_t run = 0;
+#pragma unroll
+            for (int c = 0; c < 4 * WARPS; c += 32) {
+                const uint32_t v = (c + lane < 4 * WARPS) ? s_cnt[c + lane] : 0u;
+                const uint32_t inc = warp_inclusive_scan(v);
+                if (c + lane < 4 * WARPS) s_cnt[c + lane] = run + inc - v;
+                run += __shfl_sync(0xffffffffu, inc, 31);
+            }
+            if (lane == 0) s_cnt[4 * WARPS] = run;
+        }
+        __syncthreads();
+        const uint32_t nsurv = s_cnt[4 * WARPS];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if ((bal[k] >> lane) & 1u) s_ids[s_cnt[k * WARPS + warp] + __popc(bal[k] & lt)] = ids[k];
+        __syncthreads();
+        // ---- stage up to THREADS survivors at a time, then every warp composites the ones that reach its block -------------------
+        for (uint32_t c0 = 0; c0 < nsurv; c0 += THREADS) {
+            const uint32_t j = c0 + threadIdx.x;
+            uint32_t bm = 0;
+            if (j < nsurv) {
+                const float4 *src = reinterpret_cast<const float4 *>(rec + s_ids[j]);
+                float4 a0 = __ldg(src), a1 = __ldg(src + 1);
+                const float4 a2 = __ldg(src + 2);
+                // a0 = cx, cy, g1x, g1y ; a1 = g2x, g2y, half2(hx, hy), alpha ; a2 = r, g, b, ndc z
+                bm = block_touch_mask<NB>(a0, a1, tile_x0, tile_y0);
+                a1.z = a0.w * a0.w + a1.y * a1.y;     // h = |d(u,w)/dy|^2
+                a1.w = log2f(a1.w);                   // opacity folded into the exponent
+                s_rec[threadIdx.x][0] = a0;
+                s_rec[threadIdx.x][1] = a1;
+                s_rec[threadIdx.x][2] = a2;
+            }
+#pragma unroll
+            for (int b = 0; b < WARPS; ++b) {
+                const uint32_t v = __ballot_sync(0xffffffffu, (bm >> b) & 1u);
+                if (lane == 0) s_touch[b][warp] = v;
+            }
+            __syncthreads();
+            if (!wdone) {
+#pragma unroll 1
+                for (int sw = 0; sw < WARPS && !wdone; ++sw) {
+                    uint32_t bits = s_touch[warp][sw];
+                    while (bits) {
+                        const int jj = sw * 32 + __ffs(bits) - 1;
+                        bits &= bits - 1;
+                        const float4 A = s_rec[jj][0], B = s_rec[jj][1], C = s_rec[jj][2];
+                        const float dx = pxc - A.x, dy = pyc - A.y;
+                        const float u = fmaf(dy, A.w, dx * A.z), w = fmaf(dy, B.y, dx * B.x);
+                        const float q0 = fmaf(w, w, u * u);
+                        const float q1 = q0 + fmaf(2.0f, fmaf(u, A.w, w * B.y), B.z);        // one pixel up: (u + g1y)^2 + (w + g2y)^2
+                        // exp(-0.5 A) * vColor.a with A = 8 q, zero outside the quad's inscribed disc (branch-free)
+                        const float e0 = (q0 <= 1.0f) ? ex2_approx(fmaf(q0, -5.770780163555854f, B.w)) : 0.0f;
+                        const float e1 = (q1 <= 1.0f) ? ex2_approx(fmaf(q1, -5.770780163555854f, B.w)) : 0.0f;
+                        const float w0 = T0 * e0, w1 = T1 * e1;
+                        r0 = fmaf(w0, C.x, r0); g0 = fmaf(w0, C.y, g0); b0 = fmaf(w0, C.z, b0);
+                        r1 = fmaf(w1, C.x, r1); g1 = fmaf(w1, C.y, g1); b1 = fmaf(w1, C.z, b1);
+                        T0 -= w0; T1 -= w1;                                                // T *= (1 - alpha)
+                        if (!__any_sync(0xffffffffu, fmaxf(T0, T1) >= kTransmittanceCutoff)) { wdone = true; break; }
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    if (x < width) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int y = y0 + k;
+            if (y < height) {
+                const float Tk = k ? T1 : T0, Rk = k ? r1 : r0, Gk = k ? g1 : g0, Bk = k ? b1 : b0;
+                const float A = 1.0f - Tk;      // alpha accumulates as 1 - prod(1 - alpha_i)
+                const int out_row = flip_y ? (height - 1 - y) : y;   // every rank writes its tiles into a full-size frame
+                const size_t at = (size_t)out_row * width + x;
+                if (FORMAT == GS_FRAME_RGBA32F) {
+                    reinterpret_cast<float4 *>(frame)[at] = make_float4(Rk, Gk, Bk, A);
+                } else {
+                    const uint32_t r8 = (uint32_t)(__saturatef(Rk) * 255.0f + 0.5f), g8 = (uint32_t)(__saturatef(Gk) * 255.0f + 0.5f);
+                    const uint32_t b8 = (uint32_t)(__saturatef(Bk) * 255.0f + 0.5f), a8 = (uint32_t)(__saturatef(A) * 255.0f + 0.5f);
+                    reinterpret_cast<uint32_t *>(frame)[at] = r8 | (g8 << 8) | (b8 << 16) | (a8 << 24);
+                }
+            }
+        }
+    }
+    if (world > 1) __threadfence_system();   // the frame may live in a peer GPU's memory (fused tile gather): publish before the signal
+}
+
 // records -> the ABI's gs_projected_splat (basis vectors recovered from g = B/|B|^2)
 __global__ void k_export_projected(const SplatRecord *__restrict__ rec, const ushort4 *__restrict__ rects, uint32_t count, gs_projected_splat *out) {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -874,8 +1233,6 @@ struct RasterState {
     RBuf<ushort4> rects;
     RBuf<uint32_t> block_sums; // coarse instances per chunk of draw ranks
     RBuf<uint32_t> warp_sums;  // ... and per warp (256 draw ranks) inside the chunk
-    RBuf<unsigned long long> fmask;   // GS_EXACT_MASKS=1: per-splat bitmap of the tiles its ellipse reaches (k_fine_masks)
-    bool exact_masks = false;
     RBuf<uint32_t> super_sums; // ... and per group of kBinThreads chunks: [0, S) binning, [S, 2S) subset compaction
     uint32_t super_stride = 0;
     RBuf<uint16_t> ikeys[2];   // instance keys ping/pong (coarse tile ids)
@@ -885,9 +1242,17 @@ struct RasterState {
     RBuf<RasterControl> rctl;
     RBuf<SortControl> sctl;
     RBuf<uint32_t> tile_hist;   // radix tile histograms
+    RBuf<uint32_t> bin_hist;    // binning v2: [coarse tile][chunk] instance counts -> offsets
+    RBuf<ushort4> rect_by_rank; // binning v2: the rects gathered in draw-rank order by k_bin_count
+    RBuf<uint32_t> bin_totals;  // binning v2: instances per coarse tile (1024 words, zeroed by k_raster_init)
+    uint32_t bin_stride = 0;
+    int bin_cfg = 0;
+    int bin_version = 2, blend_version = 2;   // GS_BIN / GS_BLEND = 1 selects the round-1 kernels (A/B measurements)
     RBuf<DynamicUniforms> dyn;
     RBuf<ProjParams> projp;     // per-frame projection parameters (device copy read by k_project)
     RBuf<unsigned char> frame;
+    RBuf<unsigned char> frame_alt;   // second device frame: pipelined frames (gs_frame_begin) alternate so a D2H copy can overlap the next frame
+    int frame_parity = 0;
     RBuf<gs_projected_splat> exported;
     // fused tile gather over NVLink peer memory (world_size > 1)
     RBuf<PeerSync> peer_sync_local;      // rank 0 owns the block
@@ -925,8 +1290,6 @@ static int raster_init(RasterState &rs, const gs_config &c, int sm_count) {
         RCU(rs.warp_sums.ensure(((n + kBinTile - 1) / kBinTile + 1) * (kBinThreads / 32)));
         rs.super_stride = (uint32_t)(((n + kBinTile - 1) / kBinTile) / kBinThreads + 2);
         RCU(rs.super_sums.ensure(2 * (size_t)rs.super_stride));
-        if (const char *xm = getenv("GS_EXACT_MASKS")) rs.exact_masks = atoi(xm) != 0;
-        if (rs.exact_masks) RCU(rs.fmask.ensure(n));
         const char *f = getenv("GS_INSTANCE_FACTOR");
         const double factor = f ? atof(f) : 4.0;
         const size_t tiles = (size_t)((c.max_width + kTile - 1) / kTile) * ((c.max_height + kTile - 1) / kTile);
@@ -937,15 +1300,27 @@ static int raster_init(RasterState &rs, const gs_config &c, int sm_count) {
         RCU(rs.ranges.ensure(65536));
         RCU(rs.frame.ensure((size_t)c.max_width * (c.max_height + kTile) * 16));
         RCU(rs.tile_hist.ensure(radix_tile_hist_words(rs.instance_capacity, 2, &rs.hist_stride)));
+        if (const char *v = getenv("GS_BIN")) rs.bin_version = atoi(v);
+        if (const char *v = getenv("GS_BLEND")) rs.blend_version = atoi(v);
+        if (const char *v = getenv("GS_BINCFG")) rs.bin_cfg = atoi(v);
+        {   // binning v2: one column of chunk counts per coarse tile (2048 draw ranks per chunk in both configurations)
+            const size_t coarse = (size_t)((c.max_width + kTile * kCoarseW - 1) / (kTile * kCoarseW)) * ((c.max_height + kTile * kCoarseH - 1) / (kTile * kCoarseH));
+            const size_t chunks = (n + 2047) / 2048 + 1;
+            rs.bin_stride = (uint32_t)((chunks + 31) & ~(size_t)31);
+            RCU(rs.bin_hist.ensure(std::max<size_t>(coarse, 1) * rs.bin_stride));
+            RCU(rs.rect_by_rank.ensure(n));
+            RCU(rs.bin_totals.ensure(1024));
+            RCU(cudaMemset(rs.bin_totals.p, 0, 1024 * 4));
+        }
     }
     return GS_OK;
 }
 
 static void raster_release(RasterState &rs) {
     rs.cc.release(); rs.cov.release(); rs.sh.release(); rs.scene_idx.release(); rs.records.release(); rs.rects.release();
-    rs.block_sums.release(); rs.warp_sums.release(); rs.super_sums.release(); rs.fmask.release(); rs.ikeys[0].release(); rs.ikeys[1].release(); rs.ivals[0].release(); rs.ivals[1].release();
-    rs.list.release(); rs.ranges.release(); rs.rctl.release(); rs.sctl.release(); rs.tile_hist.release();
-    rs.dyn.release(); rs.projp.release(); rs.frame.release(); rs.peer_sync_local.release(); rs.exported.release();
+    rs.block_sums.release(); rs.warp_sums.release(); rs.super_sums.release(); rs.ikeys[0].release(); rs.ikeys[1].release(); rs.ivals[0].release(); rs.ivals[1].release();
+    rs.list.release(); rs.ranges.release(); rs.rctl.release(); rs.sctl.release(); rs.tile_hist.release(); rs.bin_hist.release(); rs.bin_totals.release(); rs.rect_by_rank.release();
+    rs.dyn.release(); rs.projp.release(); rs.frame.release(); rs.frame_alt.release(); rs.peer_sync_local.release(); rs.exported.release();
 }
 
 static int raster_upload(RasterState &rs, const gs_config &c, const gs_splat_data &d, cudaStream_t st) {
@@ -981,13 +1356,13 @@ static int raster_upload(RasterState &rs, const gs_config &c, const gs_splat_dat
     return GS_OK;
 }
 
-static void *raster_frame_ptr(RasterState &rs, int) { return rs.frame.p; }
+static void *raster_frame_ptr(RasterState &rs, int) { return (rs.frame_parity && rs.frame_alt.p) ? rs.frame_alt.p : rs.frame.p; }
 
 template <bool COVF16>
 static void launch_project(RasterState &rs, uint32_t count, cudaStream_t st) {
     const int blocks = (int)((count + kProjThreads - 1) / kProjThreads);
     const uint32_t *sc = rs.have_scene_idx ? rs.scene_idx.p : nullptr;
-#define GS_PROJ(FMT) k_project<COVF16, FMT><<<blocks, kProjThreads, 0, st>>>(rs.cc.p, rs.cov.p, rs.sh.p, (int)rs.sh_degree, sc, rs.dyn.p, rs.projp.p, count, rs.records.p, rs.rects.p, rs.rctl.p)
+#define GS_PROJ(FMT) gs_launch(k_project<COVF16, FMT>, blocks, kProjThreads, 0, st, rs.cc.p, rs.cov.p, rs.sh.p, (int)rs.sh_degree, sc, rs.dyn.p, rs.projp.p, count, rs.records.p, rs.rects.p, rs.rctl.p)
     switch (rs.sh_format) {
         case GS_SH_F16: GS_PROJ(GS_SH_F16); break;
         case GS_SH_U8: GS_PROJ(GS_SH_U8); break;
@@ -997,8 +1372,16 @@ static void launch_project(RasterState &rs, uint32_t count, cudaStream_t st) {
 #undef GS_PROJ
 }
 
+// Fine-tile edge for a frame: 16 px while that gives at most 256 coarse tiles (8 x 4 fine tiles each: one counting-sort pass with 8-bit
+// bins, 1920x1080 = 255), else 32 px (3840x2160 = 255 coarse tiles of 256 x 128 px).  Larger frames keep 32 px and the multi-pass path.
+static inline int frame_tile_shift(uint32_t width, uint32_t height) {
+    const uint32_t cx = (width + kTile * kCoarseW - 1) / (kTile * kCoarseW), cy = (height + kTile * kCoarseH - 1) / (kTile * kCoarseH);
+    return (cx * cy <= 256u) ? kTileShift : kTileShift + 1;
+}
+
 static int raster_upload_params(RasterState &rs, const gs_config &c, const gs_uniforms &u, const gs_render_params &p, cudaStream_t st) {
-    const int tiles_x = (p.width + kTile - 1) / kTile, tiles_y = (p.height + kTile - 1) / kTile;
+    const int tshift = frame_tile_shift(p.width, p.height), tpx = 1 << tshift;
+    const int tiles_x = (p.width + tpx - 1) / tpx, tiles_y = (p.height + tpx - 1) / tpx;
     const uint32_t world = c.world_size, rank = c.rank;
     const bool upload_params = true;
     ProjParams P{};
@@ -1011,6 +1394,7 @@ static int raster_upload_params(RasterState &rs, const gs_config &c, const gs_un
     memcpy(P.scene_center, u.scene_center, 12); P.fade_start = u.visible_region_fade_start_radius;
     P.dynamic = u.dynamic_mode; P.optional_effects = u.enable_optional_effects; P.scene_count = (int)u.scene_count;
     P.tiles_x = tiles_x; P.tiles_y = tiles_y; P.rank = rank; P.world = world; P.width = (int)p.width; P.height = (int)p.height;
+    P.tile_shift = tshift;
     if (upload_params) RCU(cudaMemcpyAsync(rs.projp.p, &P, sizeof(P), cudaMemcpyHostToDevice, st)); // pageable source: staged before return
     if (upload_params && (u.dynamic_mode || u.enable_optional_effects || rs.sh_format == GS_SH_U8)) {
         DynamicUniforms du;
@@ -1032,7 +1416,8 @@ static int raster_render(RasterState &rs, const gs_config &c, const gs_uniforms 
         snprintf(raster_err(), 512, "frame %ux%u outside the engine's %ux%u", p.width, p.height, c.max_width, c.max_height); return GS_ERR_BAD_ARG;
     }
     if (p.render_count > rs.uploaded) { snprintf(raster_err(), 512, "render_count %u > uploaded splats %u", p.render_count, rs.uploaded); return GS_ERR_CAPACITY; }
-    const int tiles_x = (p.width + kTile - 1) / kTile, tiles_y = (p.height + kTile - 1) / kTile;
+    const int tshift = frame_tile_shift(p.width, p.height), tpx = 1 << tshift;
+    const int tiles_x = (p.width + tpx - 1) / tpx, tiles_y = (p.height + tpx - 1) / tpx;
     const uint32_t world = c.world_size, rank = c.rank;
     const uint32_t local_tiles = (uint32_t)tiles_x * (uint32_t)tiles_y;
     uint32_t launches = 0;
@@ -1045,32 +1430,45 @@ static int raster_render(RasterState &rs, const gs_config &c, const gs_uniforms 
     while ((1u << tile_bits) < std::max(ncoarse, 2u)) ++tile_bits;
     const PassPlan pl = make_plan_bits(tile_bits);
     if (phases & 1) {
-        k_raster_init<<<8, 256, 0, st>>>(rs.rctl.p, rs.sctl.p, rs.ranges.p, ncoarse, rs.super_sums.p, 2 * rs.super_stride);
+        gs_launch(k_raster_init, 8, 256, 0, st, rs.rctl.p, rs.sctl.p, rs.ranges.p, ncoarse, rs.super_sums.p, 2 * rs.super_stride, rs.bin_totals.p);
         ++launches;
         prof.mark("k_raster_init", st);
+        // rank 0 frees its frame buffer for the peers' stores right at the START of the frame (everything that consumed the previous
+        // picture is earlier in stream order), so their blends never wait for rank 0's own sort + binning
+        if (world > 1 && rs.peer_root) { k_peer_release<<<1, 1, 0, st>>>(rs.peer_sync, rs.rctl.p); ++launches; }
         const uint32_t count = rs.uploaded;
         if (rs.cov_format == GS_COV_F16) launch_project<true>(rs, count, st); else launch_project<false>(rs, count, st);
         ++launches;
         prof.mark("k_project", st);
-        if (rs.exact_masks && count) {
-            k_fine_masks<<<(count + 255) / 256, 256, 0, st>>>(rs.records.p, rs.rects.p, count, rs.fmask.p);
-            ++launches;
-            prof.mark("k_fine_masks", st);
-        }
         if (record_events) RCU(cudaEventRecord(ev_project, st));
     }
     if (!(phases & 2)) { tm.kernel_launches = launches; return GS_OK; }
-    if (p.render_count && local_tiles) {
+    const bool bin2 = rs.bin_version >= 2 && ncoarse <= 256u;
+    if (p.render_count && local_tiles && bin2) {
+        const OwnMask own = make_own_mask(rank, world);
+        const int sharded = world > 1 ? 1 : 0;
+        const uint32_t chunks = (p.render_count + kBinRanks - 1u) / kBinRanks;
+#define GS_BIN_COUNT(C) gs_launch(k_bin_count<C>, chunks, Bin2Cfg<C>::kWarps * 32, 0, st, d_order, p.render_count, order_count_dev, rs.rects.p, coarse_x, ncoarse, rs.bin_hist.p, rs.bin_stride, rs.bin_totals.p, rs.rect_by_rank.p, own, sharded)
+#define GS_BIN_PLACE(C) gs_launch(k_bin_place<C>, chunks, Bin2Cfg<C>::kWarps * 32, 0, st, d_order, p.render_count, order_count_dev, rs.rect_by_rank.p, coarse_x, ncoarse, rs.bin_hist.p, rs.bin_stride, rs.list.p, rs.instance_capacity, rs.rctl.p, own, sharded)
+        if (rs.bin_cfg == 0) GS_BIN_COUNT(0); else GS_BIN_COUNT(1);
+        ++launches;
+        prof.mark("k_bin_count", st);
+        gs_launch(k_bin_scan, ncoarse, 1024, 0, st, rs.bin_hist.p, rs.bin_stride, (uint32_t)kBinRanks, p.render_count, order_count_dev, rs.bin_totals.p, ncoarse, rs.ranges.p, rs.rctl.p);
+        ++launches;
+        prof.mark("k_bin_scan", st);
+        if (rs.bin_cfg == 0) GS_BIN_PLACE(0); else GS_BIN_PLACE(1);
+#undef GS_BIN_COUNT
+#undef GS_BIN_PLACE
+        ++launches;
+        prof.mark("k_bin_place", st);
+    }
+    if (p.render_count && local_tiles && !bin2) {
         const uint32_t chunks = (p.render_count + kBinTile - 1) / kBinTile;
-        k_tile_count<<<chunks, kBinThreads, 0, st>>>(d_order, p.render_count, order_count_dev, rs.rects.p, rs.block_sums.p, rs.warp_sums.p, rs.super_sums.p, make_own_mask(rank, world), world > 1 ? 1 : 0);
+        gs_launch(k_tile_count, chunks, kBinThreads, 0, st, d_order, p.render_count, order_count_dev, rs.rects.p, rs.block_sums.p, rs.warp_sums.p, rs.super_sums.p, make_own_mask(rank, world), world > 1 ? 1 : 0);
         ++launches;
         prof.mark("k_tile_count", st);
-        if (rs.exact_masks)
-            k_tile_emit<true><<<chunks, kBinThreads, 0, st>>>(d_order, p.render_count, order_count_dev, rs.rects.p, rs.block_sums.p, rs.warp_sums.p, rs.super_sums.p, coarse_x, rs.ikeys[0].p,
-                                                             rs.ivals[0].p, rs.instance_capacity, rs.rctl.p, make_own_mask(rank, world), world > 1 ? 1 : 0, rs.fmask.p);
-        else
-            k_tile_emit<false><<<chunks, kBinThreads, 0, st>>>(d_order, p.render_count, order_count_dev, rs.rects.p, rs.block_sums.p, rs.warp_sums.p, rs.super_sums.p, coarse_x, rs.ikeys[0].p,
-                                                              rs.ivals[0].p, rs.instance_capacity, rs.rctl.p, make_own_mask(rank, world), world > 1 ? 1 : 0, nullptr);
+        gs_launch(k_tile_emit, chunks, kBinThreads, 0, st, d_order, p.render_count, order_count_dev, rs.rects.p, rs.block_sums.p, rs.warp_sums.p, rs.super_sums.p, coarse_x, rs.ikeys[0].p,
+                                                    rs.ivals[0].p, rs.instance_capacity, rs.rctl.p, make_own_mask(rank, world), world > 1 ? 1 : 0);
         ++launches;
         prof.mark("k_tile_emit", st);
         static const RadixNames names = {{"k_radix_hist[tile,0]", "k_radix_hist[tile,1]", "k_radix_hist[tile,2]", "k_radix_hist[tile,3]"},
@@ -1086,19 +1484,23 @@ static int raster_render(RasterState &rs, const gs_config &c, const gs_uniforms 
     if (local_tiles) {
         const bool peer_mode = world > 1 && (rs.peer_root || rs.peer_attached);
         // multi-GPU without the peer path: pixels of other ranks' tiles must be zero so that the frames can be summed (all-reduce)
-        if (world > 1 && !peer_mode) RCU(cudaMemsetAsync(rs.frame.p, 0, (size_t)p.width * p.height * (p.frame_format == GS_FRAME_RGBA8 ? 4 : 16), st));
-        void *target = rs.frame.p;
-        if (peer_mode && rs.peer_root) { k_peer_release<<<1, 1, 0, st>>>(rs.peer_sync, rs.rctl.p); ++launches; }
+        void *target = raster_frame_ptr(rs, p.frame_format);
+        if (world > 1 && !peer_mode) RCU(cudaMemsetAsync(target, 0, (size_t)p.width * p.height * (p.frame_format == GS_FRAME_RGBA8 ? 4 : 16), st));
         if (peer_mode && rs.peer_attached) {   // fused tile gather: blend straight into rank 0's frame over NVLink
             k_peer_wait_release<<<1, 1, 0, st>>>(rs.peer_sync, rs.rctl.p);
             ++launches;
             target = rs.peer_frame;
         }
         const uint32_t grid = ncoarse * kFinePerCoarse;
-        if (p.frame_format == GS_FRAME_RGBA8)
-            k_blend<GS_FRAME_RGBA8><<<grid, kBlendThreads, 0, st>>>(rs.ranges.p, rs.list.p, rs.records.p, tiles_x, tiles_y, coarse_x, rank, world, (int)p.width, (int)p.height, p.flip_y, target);
+        if (rs.blend_version >= 2 || tshift != kTileShift) {
+#define GS_BLEND2(FMT, SC) gs_launch(k_blend2<FMT, SC>, grid, 128 * SC * SC, 0, st, rs.ranges.p, rs.list.p, rs.records.p, tiles_x, tiles_y, coarse_x, rank, world, (int)p.width, (int)p.height, p.flip_y, target)
+            if (tshift == kTileShift) { if (p.frame_format == GS_FRAME_RGBA8) GS_BLEND2(GS_FRAME_RGBA8, 1); else GS_BLEND2(GS_FRAME_RGBA32F, 1); }
+            else { if (p.frame_format == GS_FRAME_RGBA8) GS_BLEND2(GS_FRAME_RGBA8, 2); else GS_BLEND2(GS_FRAME_RGBA32F, 2); }
+#undef GS_BLEND2
+        } else if (p.frame_format == GS_FRAME_RGBA8)
+            gs_launch(k_blend<GS_FRAME_RGBA8>, grid, kBlendThreads, 0, st, rs.ranges.p, rs.list.p, rs.records.p, tiles_x, tiles_y, coarse_x, rank, world, (int)p.width, (int)p.height, p.flip_y, target);
         else
-            k_blend<GS_FRAME_RGBA32F><<<grid, kBlendThreads, 0, st>>>(rs.ranges.p, rs.list.p, rs.records.p, tiles_x, tiles_y, coarse_x, rank, world, (int)p.width, (int)p.height, p.flip_y, target);
+            gs_launch(k_blend<GS_FRAME_RGBA32F>, grid, kBlendThreads, 0, st, rs.ranges.p, rs.list.p, rs.records.p, tiles_x, tiles_y, coarse_x, rank, world, (int)p.width, (int)p.height, p.flip_y, target);
         ++launches;
         prof.mark("k_blend", st);
         if (peer_mode && rs.peer_attached) { k_peer_signal<<<1, 1, 0, st>>>(rs.peer_sync); ++launches; }
@@ -1116,10 +1518,10 @@ static int raster_subset(RasterState &rs, const gs_config &c, const uint32_t *d_
                          int32_t *sub_dist, cudaStream_t st, Profiler &prof, uint32_t &launches) {
     const uint32_t chunks = (count + kBinTile - 1) / kBinTile;
     const OwnMask own = make_own_mask(c.rank, c.world_size);
-    k_subset_count<<<chunks, kBinThreads, 0, st>>>(d_indexes, count, rs.rects.p, own, rs.block_sums.p, rs.warp_sums.p, rs.super_sums.p + rs.super_stride);
+    gs_launch(k_subset_count, chunks, kBinThreads, 0, st, d_indexes, count, rs.rects.p, own, rs.block_sums.p, rs.warp_sums.p, rs.super_sums.p + rs.super_stride);
     ++launches;
     prof.mark("k_subset_count", st);
-    k_subset_emit<<<chunks, kBinThreads, 0, st>>>(d_indexes, count, rs.rects.p, own, rs.block_sums.p, rs.warp_sums.p, rs.super_sums.p + rs.super_stride, dist, sub_idx, sub_dist, rs.rctl.p);
+    gs_launch(k_subset_emit, chunks, kBinThreads, 0, st, d_indexes, count, rs.rects.p, own, rs.block_sums.p, rs.warp_sums.p, rs.super_sums.p + rs.super_stride, dist, sub_idx, sub_dist, rs.rctl.p);
     ++launches;
     prof.mark("k_subset_emit", st);
     return GS_OK;

@@ -26,6 +26,7 @@ struct DepthParams {
 
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void k_sort_init(SortControl *ctl) {
+    pdl_enter();
     const uint32_t tid = threadIdx.x;
     if (tid == 0) {
         ctl->dmin = 2147483640;
@@ -86,6 +87,7 @@ __global__ void __launch_bounds__(kDepthThreads)
 k_depth(const uint32_t *__restrict__ indexes, const void *__restrict__ centers, const void *__restrict__ pre,
         const uint32_t *__restrict__ scene_idx, const float *__restrict__ transforms, const DepthParams *__restrict__ Pp, uint32_t s0,
         uint32_t rc, int32_t *__restrict__ dist, SortControl *ctl) {
+    pdl_enter();
     // per-frame parameters live in device memory so that a captured CUDA graph of the frame can be replayed unchanged
     DepthParams P;
 #pragma unroll
@@ -193,6 +195,7 @@ __global__ void __launch_bounds__(kRadixThreads)
 k_bucket(int32_t *__restrict__ dist /* distances of the n sorted positions (dist + sortStart) */, KeyT *__restrict__ keys, uint32_t n_host,
          const unsigned long long *__restrict__ n_dev, uint32_t R, PassPlan plan, int write_buckets, SortControl *ctl,
          uint32_t *__restrict__ tile_hist, uint32_t stride) {
+    pdl_enter();
     __shared__ uint32_t s_hist[kRadix];
     if (threadIdx.x < kRadix) s_hist[threadIdx.x] = 0;
     __syncthreads();
@@ -242,6 +245,7 @@ template <typename KeyT>
 __global__ void __launch_bounds__(kRadixThreads)
 k_radix_hist(const KeyT *__restrict__ keys, uint32_t n_host, const unsigned long long *__restrict__ n_dev, unsigned long long n_cap,
              int shift, int bits, uint32_t *__restrict__ tile_hist, uint32_t stride, uint32_t *global_hist, int add_global) {
+    pdl_enter();
     const uint32_t n = n_dev ? (uint32_t)min(*n_dev, n_cap) : n_host;
     const uint64_t base = (uint64_t)blockIdx.x * kRadixTile;
     if (base >= n) return;
@@ -271,6 +275,7 @@ constexpr int kScanColThreads = 1024;
 __global__ void __launch_bounds__(kScanColThreads)
 k_radix_scan(uint32_t *__restrict__ tile_hist, uint32_t stride, uint32_t n_host, const unsigned long long *__restrict__ n_dev,
              unsigned long long n_cap, const uint32_t *__restrict__ global_hist) {
+    pdl_enter();
     __shared__ uint32_t s_scan[40];
     __shared__ uint32_t s_carry;
     const uint32_t n = n_dev ? (uint32_t)min(*n_dev, n_cap) : n_host;
@@ -405,6 +410,7 @@ k_radix_scatter(const KeyT *__restrict__ keys_in, const ValT *__restrict__ vals_
                 KeyT *__restrict__ keys_out, ValT *__restrict__ vals_out, uint32_t n_host,
                 const unsigned long long *__restrict__ n_dev, unsigned long long n_cap, int shift, int bits,
                 const uint32_t *__restrict__ tile_offsets, uint32_t stride, uint2 *ranges, uint32_t *clear_hist, SortControl *reset_ctl) {
+    pdl_enter();
     const uint32_t n = n_dev ? (uint32_t)min(*n_dev, n_cap) : n_host;
     const uint32_t tile = blockIdx.x;
     // self-cleaning control block (no init kernel on the frame's critical path): this pass's digit totals were consumed by the
@@ -434,6 +440,7 @@ k_radix_scatter(const KeyT *__restrict__ keys_in, const ValT *__restrict__ vals_
 
 // out[0..s0) = indexes[0..s0)   (sorter.cpp:158-160)
 __global__ void k_copy_head(const uint32_t *__restrict__ indexes, uint32_t *__restrict__ out, uint32_t s0) {
+    pdl_enter();
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < s0; i += (uint64_t)gridDim.x * blockDim.x)
         out[i] = indexes ? indexes[i] : (uint32_t)i;
 }
@@ -508,7 +515,7 @@ static void launch_radix_scatter(uint32_t grid, bool first, bool write_keys, boo
                                  uint32_t iota_top, KeyT *kout, ValT *vout, uint32_t n, const unsigned long long *n_dev, unsigned long long n_cap,
                                  int shift, int bits, const uint32_t *tile_offsets, uint32_t stride, uint2 *ranges, uint32_t *clear_hist, SortControl *reset_ctl,
                                  cudaStream_t st) {
-#define GS_PASS(VM, WK, RG) k_radix_scatter<KeyT, ValT, VM, WK, RG><<<grid, kRadixThreads, 0, st>>>(kin, vin, iota_top, kout, vout, n, n_dev, n_cap, shift, bits, tile_offsets, stride, ranges, clear_hist, reset_ctl)
+#define GS_PASS(VM, WK, RG) gs_launch(k_radix_scatter<KeyT, ValT, VM, WK, RG>, grid, kRadixThreads, 0, st, kin, vin, iota_top, kout, vout, n, n_dev, n_cap, shift, bits, tile_offsets, stride, ranges, clear_hist, reset_ctl)
     if (!first) valmode = kValArray;
     if (want_ranges && !write_keys) { GS_PASS(kValArray, false, true); }   // tile-instance sort (values always come from an array)
     else if (want_ranges) {                                                 // sharded depth sort: sorted keys AND per-key runs
@@ -546,11 +553,11 @@ static void radix_sort_pairs(KeyT *keys0, KeyT *keys1, const ValT *vals_src, uin
         ValT *vout = last ? vals_final : vt[p & 1];
         uint32_t *th = tile_hist + (size_t)p * kRadix * stride;
         if (!(p == 0 && hist0_done)) {
-            k_radix_hist<KeyT><<<tiles, kRadixThreads, 0, st>>>(kin, n, n_dev, n_cap, pl.shift[p], pl.bits[p], th, stride, &ctl->hist[p][0], 1);
+            gs_launch(k_radix_hist<KeyT>, tiles, kRadixThreads, 0, st, kin, n, n_dev, n_cap, pl.shift[p], pl.bits[p], th, stride, &ctl->hist[p][0], 1);
             ++launches;
             if (prof) prof->mark(names.hist[p], st);
         }
-        k_radix_scan<<<1u << pl.bits[p], kScanColThreads, 0, st>>>(th, stride, n, n_dev, n_cap, &ctl->hist[p][0]);
+        gs_launch(k_radix_scan, 1u << pl.bits[p], kScanColThreads, 0, st, th, stride, n, n_dev, n_cap, &ctl->hist[p][0]);
         ++launches;
         if (prof) prof->mark(names.scan[p], st);
         if (last && final_keys) *final_keys = kout;

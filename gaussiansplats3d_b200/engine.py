@@ -294,9 +294,9 @@ class Engine:
 
     def frame(self, mvp, uniforms: Uniforms, width: int, height: int, render_count: int, indexes=None, *,
               frame_format: int = N.GS_FRAME_RGBA8, flip_y: bool = True, frame_out: np.ndarray | None = None,
-              sorted_out: np.ndarray | None = None, download: bool = True):
-        """One viewer frame: full depth sort + render (Viewer.update + Viewer.render)."""
-        sp = self._sort_params(mvp, render_count, render_count, indexes, None, None)
+              sorted_out: np.ndarray | None = None, download: bool = True, transforms=None):
+        """One viewer frame: full depth sort + render (Viewer.update + Viewer.render).  `transforms`: per-scene matrices of a dynamic mesh."""
+        sp = self._sort_params(mvp, render_count, render_count, indexes, transforms, None)
         rp, _ = self._render_params(width, height, render_count, None, frame_format, flip_y)
         u = uniforms.to_c()
         shape, dt = self._frame_shape(width, height, frame_format)
@@ -323,6 +323,16 @@ class Engine:
         """gs_frame with pre-marshalled arguments (host buffers: frame_out / sorted_out may be pinned arrays)."""
         sp, u, rp = prepared
         N.check(self._lib.gs_frame(self._h, C.byref(sp), C.byref(u), C.byref(rp), N.ptr(sorted_out), N.ptr(frame_out)), "gs_frame")
+
+    def frame_begin(self, prepared, frame_out: np.ndarray | None) -> None:
+        """Pipelined frame (gs_frame_begin): enqueue the frame and the copy of its picture into `frame_out` (pinned host array);
+        at most two frames in flight.  `prepared` = prepare_frame(...)."""
+        sp, u, rp = prepared
+        N.check(self._lib.gs_frame_begin(self._h, C.byref(sp), C.byref(u), C.byref(rp), N.ptr(frame_out)), "gs_frame_begin")
+
+    def frame_end(self) -> None:
+        """Wait for the oldest pipelined frame: its frame_out is complete on return."""
+        N.check(self._lib.gs_frame_end(self._h), "gs_frame_end")
 
     def peer_export(self) -> tuple[bytes, bytes]:
         """Rank 0: CUDA-IPC handles (frame buffer, handshake block) for the fused tile gather."""

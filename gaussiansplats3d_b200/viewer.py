@@ -52,6 +52,9 @@ class SplatMesh:
         self.visibleRegionFadeStartRadius = 0.0
         self.fadeInComplete = True
         self.sceneCenter = (0.0, 0.0, 0.0)
+        # per-scene transforms of a dynamic mesh (SplatScene.transform, SplatScene.js:28-36; uploaded every frame by
+        # fillTransformsArray, SplatMesh.js:1660-1673): column-major f64, scene 0 = the one scene this mirror holds
+        self.sceneTransforms = np.tile(TM.identity(), (N.GS_MAX_SCENES, 1))
 
     def build(self, raw_scene: RawScene, *, sh_format: str = "f16", transform16=None) -> None:
         """Decode + pack the scene like refreshGPUDataFromSplatBuffers (SplatMesh.js:588-603) and keep it for upload.
@@ -59,6 +62,7 @@ class SplatMesh:
         the mesh is static (fillSplatDataArrays' applySceneTransform default, SplatMesh.js:1872-1883); a dynamic mesh keeps the
         data untouched and applies its transforms per frame in the sorter and the vertex stage."""
         if transform16 is not None and self.dynamicMode:
+            self.sceneTransforms[0] = np.asarray(transform16, np.float64).reshape(16)     # applied per frame, not baked
             transform16 = None
         if transform16 is not None:
             from .scenes import transform_scene
@@ -71,6 +75,10 @@ class SplatMesh:
             raw_scene = RawScene(raw_scene.centers, raw_scene.scales, raw_scene.rotations, raw_scene.colors,
                                  None if degree == 0 else raw_scene.sh[:, :ncoef], degree)
         self.packed = pack_scene(raw_scene, half_covariances=self.halfPrecisionCovariancesOnGPU, sh_format=sh_format, transform16=transform16)
+
+    def fillTransformsArray(self) -> np.ndarray:  # noqa: N802  SplatMesh.js:1660-1673
+        """f32[32 x 16] for the sorter ('transforms' of the sort message) and the vertex stage (`transforms` uniform)."""
+        return self.sceneTransforms.astype(np.float32)
 
     def getSplatCount(self) -> int:  # noqa: N802
         return 0 if self.packed is None else self.packed.count
@@ -168,7 +176,7 @@ class Viewer:
             start(self.sortWorker)
             self.sortWorker.postMessage({"centers": centers, "sceneIndexes": None, "range": {"from": 0, "to": n - 1, "count": n}})
         else:
-            self.engine.upload_centers(centers)
+            self.engine.upload_centers(centers, np.zeros(n, np.uint32) if self.dynamicScene else None)
         self.splatRenderCount = n
 
     def addSplatSceneFromKSplat(self, data: bytes, *, position=(0.0, 0.0, 0.0), rotation=(0.0, 0.0, 0.0, 1.0), scale=(1.0, 1.0, 1.0)) -> dict:  # noqa: N802
@@ -230,7 +238,10 @@ class Viewer:
         sm = self.splatMesh
         mv = TM.multiply(self.camera.matrixWorldInverse, sm.matrixWorld)
         u = sm.uniforms
-        return Uniforms(model_view=mv.astype(np.float32), projection=self.camera.projectionMatrix.astype(np.float32),
+        dyn = {}
+        if sm.dynamicMode:      # SplatMaterial.js:136-146: transformModelViewMatrix = viewMatrix * transforms[sceneIndex]
+            dyn = dict(dynamic_mode=1, scene_transforms=sm.fillTransformsArray(), view_matrix=self.camera.matrixWorldInverse.astype(np.float32), scene_count=1)
+        return Uniforms(**dyn, model_view=mv.astype(np.float32), projection=self.camera.projectionMatrix.astype(np.float32),
                         camera_position=np.asarray(self.camera.position, np.float32), focal=u["focal"], viewport=u["viewport"],
                         inverse_focal_adjustment=u["inverseFocalAdjustment"], ortho_zoom=u["orthoZoom"], orthographic_mode=u["orthographicMode"],
                         splat_scale=sm.splatScale, point_cloud_mode=1 if sm.pointCloudModeEnabled else 0,
@@ -259,10 +270,11 @@ class Viewer:
                    "splatSortCount": n, "usePrecomputedDistances": False}
             if not self.sharedMemoryForWorkers:
                 msg["indexesToSort"] = np.arange(n, dtype=np.uint32)
-                msg["transforms"] = None
+                msg["transforms"] = self.splatMesh.fillTransformsArray() if self.splatMesh.dynamicMode else None
             self.sortWorker.postMessage({"sort": msg})
         else:
-            _, ms = self.engine.sort(mvp.astype(np.float32), n, n, None, download=False)
+            _, ms = self.engine.sort(mvp.astype(np.float32), n, n, None, download=False,
+                                     transforms=self.splatMesh.fillTransformsArray() if self.splatMesh.dynamicMode else None)
             self.lastSortTime = ms
             self.splatMesh.updateRenderIndexes(None, n)
         return True
@@ -283,7 +295,8 @@ class Viewer:
         self.updateSplatMesh()
         n = self.splatMesh.getSplatCount()
         return self.engine.frame(self.mvp_matrix().astype(np.float32), self.uniforms(), self.renderWidth, self.renderHeight, n, None,
-                                 frame_format=frame_format, flip_y=flip_y, download=download, frame_out=frame_out)
+                                 frame_format=frame_format, flip_y=flip_y, download=download, frame_out=frame_out,
+                                 transforms=self.splatMesh.fillTransformsArray() if self.splatMesh.dynamicMode else None)
 
     def dispose(self) -> None:
         if self.sortWorker is not None:

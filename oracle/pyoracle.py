@@ -195,6 +195,18 @@ def blend(projected: np.ndarray, sorted_indexes: np.ndarray, width: int, height:
     return frame
 
 
+def blend_crop(projected: np.ndarray, sorted_indexes: np.ndarray, width: int, height: int, x0: int, y0: int, w: int, h: int, quantize8: bool = False) -> np.ndarray:
+    """The window [x0, x0+w) x [y0, y0+h) of the frame `blend` would produce (rows bottom-up), without restating the rest."""
+    lib = port_lib()
+    ps = np.ascontiguousarray(projected)
+    order = np.ascontiguousarray(sorted_indexes, dtype=np.uint32)
+    frame = np.empty((h, w, 4), np.float32)
+    lib.gso_blend_crop.restype = None
+    lib.gso_blend_crop.argtypes = [C.c_void_p, C.c_void_p] + [C.c_uint32] * 7 + [C.c_int, C.c_void_p]
+    lib.gso_blend_crop(ps.ctypes.data, order.ctypes.data, order.shape[0], width, height, x0, y0, w, h, int(quantize8), frame.ctypes.data)
+    return frame
+
+
 def render(uniforms, centers_colors, covariances, sorted_indexes, width, height, sh=None, sh_degree=0, scene_indexes=None, quantize8=False):
     ps = project(uniforms, centers_colors, covariances, sh, sh_degree, scene_indexes)
     return blend(ps, sorted_indexes, width, height, quantize8), ps

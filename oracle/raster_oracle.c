@@ -232,9 +232,25 @@ GS_ORACLE_API void gso_project(const gs_uniforms *u, const gs_splat_data *d, gs_
  * (GL window orientation: row 0 = bottom).  quantize8 != 0 models an RGBA8 render target: the destination is
  * rounded to 8 bits after every blend (informational second oracle).
  * Rows are distributed over threads; every pixel still sees the splats in exactly the draw order. */
+static void blend_region(const gs_projected_splat *ps, const uint32_t *sorted_indexes, uint32_t render_count, uint32_t width, uint32_t height,
+                         uint32_t cx0, uint32_t cy0, uint32_t cw, uint32_t chh, int quantize8, float *frame);
+
 GS_ORACLE_API void gso_blend(const gs_projected_splat *ps, const uint32_t *sorted_indexes, uint32_t render_count,
                              uint32_t width, uint32_t height, int quantize8, float *frame) {
-    memset(frame, 0, (size_t)width * height * 4 * sizeof(float));
+    blend_region(ps, sorted_indexes, render_count, width, height, 0, 0, width, height, quantize8, frame);
+}
+
+/* The same blend restricted to the window [cx0, cx0+cw) x [cy0, cy0+chh) of a width x height frame (GL window coordinates, row 0 =
+ * bottom); `frame` is cw x chh x 4.  Lets the tests check parts of frames that are too large to restate whole (16 M splats at 4K). */
+GS_ORACLE_API void gso_blend_crop(const gs_projected_splat *ps, const uint32_t *sorted_indexes, uint32_t render_count, uint32_t width,
+                                  uint32_t height, uint32_t cx0, uint32_t cy0, uint32_t cw, uint32_t chh, int quantize8, float *frame) {
+    blend_region(ps, sorted_indexes, render_count, width, height, cx0, cy0, cw, chh, quantize8, frame);
+}
+
+static void blend_region(const gs_projected_splat *ps, const uint32_t *sorted_indexes, uint32_t render_count, uint32_t width, uint32_t height,
+                         uint32_t cx0, uint32_t cy0, uint32_t cw, uint32_t chh, int quantize8, float *frame) {
+    (void)width; (void)height;
+    memset(frame, 0, (size_t)cw * chh * 4 * sizeof(float));
     /* per-splat row extents so each row band can skip quickly */
     int32_t *ylo = (int32_t *)malloc(sizeof(int32_t) * (size_t)render_count);
     int32_t *yhi = (int32_t *)malloc(sizeof(int32_t) * (size_t)render_count);
@@ -243,16 +259,16 @@ GS_ORACLE_API void gso_blend(const gs_projected_splat *ps, const uint32_t *sorte
         if (!p->valid) { ylo[i] = 1; yhi[i] = 0; continue; }
         const float ey = fabsf(p->b1y) + fabsf(p->b2y);
         float lo = floorf(p->cy - ey - 1.0f), hi = ceilf(p->cy + ey + 1.0f);
-        if (lo < 0.f) lo = 0.f;
-        if (hi > (float)height - 1.f) hi = (float)height - 1.f;
+        if (lo < (float)cy0) lo = (float)cy0;
+        if (hi > (float)(cy0 + chh) - 1.f) hi = (float)(cy0 + chh) - 1.f;
         if (!(lo <= hi)) { ylo[i] = 1; yhi[i] = 0; continue; }
         ylo[i] = (int32_t)lo; yhi[i] = (int32_t)hi;
     }
     const int band = 8;
-    const int nbands = ((int)height + band - 1) / band;
+    const int nbands = ((int)chh + band - 1) / band;
 #pragma omp parallel for schedule(dynamic, 1)
     for (int bi = 0; bi < nbands; ++bi) {
-        const int y0 = bi * band, y1 = (y0 + band < (int)height ? y0 + band : (int)height) - 1;
+        const int y0 = (int)cy0 + bi * band, y1 = (y0 + band < (int)(cy0 + chh) ? y0 + band : (int)(cy0 + chh)) - 1;
         for (uint32_t i = 0; i < render_count; ++i) {
             if (yhi[i] < y0 || ylo[i] > y1) continue;
             const gs_projected_splat *p = ps + sorted_indexes[i];
@@ -260,8 +276,8 @@ GS_ORACLE_API void gso_blend(const gs_projected_splat *ps, const uint32_t *sorte
             if (!(n1 > 0.f) || !(n2 > 0.f)) continue;
             const float ex = fabsf(p->b1x) + fabsf(p->b2x);
             float fx0 = floorf(p->cx - ex - 1.0f), fx1 = ceilf(p->cx + ex + 1.0f);
-            if (fx0 < 0.f) fx0 = 0.f;
-            if (fx1 > (float)width - 1.f) fx1 = (float)width - 1.f;
+            if (fx0 < (float)cx0) fx0 = (float)cx0;
+            if (fx1 > (float)(cx0 + cw) - 1.f) fx1 = (float)(cx0 + cw) - 1.f;
             if (!(fx0 <= fx1)) continue;
             const int x0 = (int)fx0, x1 = (int)fx1;
             const int ya = ylo[i] > y0 ? ylo[i] : y0, yb = yhi[i] < y1 ? yhi[i] : y1;
@@ -276,7 +292,7 @@ GS_ORACLE_API void gso_blend(const gs_projected_splat *ps, const uint32_t *sorte
                     const float A = 8.0f * (qu * qu + qw * qw);
                     if (A > 8.0f) continue;
                     const float alpha = expf(-0.5f * A) * p->a;
-                    float *px = frame + ((size_t)y * width + x) * 4;
+                    float *px = frame + ((size_t)(y - (int)cy0) * cw + (size_t)(x - (int)cx0)) * 4;
                     const float om = 1.0f - alpha;
                     px[0] = p->r * alpha + px[0] * om;
                     px[1] = p->g * alpha + px[1] * om;

@@ -304,3 +304,36 @@ def test_gpu_decodes_handmade_fixture(gs, name, half_cov):
         if sh is not None:
             got = e.read_buffer(N.GS_BUF_SH, sh.dtype, sh.size).reshape(sh.shape)
             assert np.array_equal(got, sh)
+
+
+@pytest.mark.gpu
+def test_malformed_ksplat_is_rejected_before_any_kernel_runs(gs):
+    """An untrusted file: section counts beyond the header's, zero bucket size, bucket tables that do not cover the splats, partial-bucket
+    lengths past the section, truncated data -- every one must come back as an error code, not as out-of-bounds device accesses."""
+    import struct
+    from gaussiansplats3d_b200 import _native as N
+    HM, data, exp = _handmade("l1_sh1")
+    n = exp["count"]
+
+    def patched(off, fmt, *vals):
+        b = bytearray(data)
+        struct.pack_into(fmt, b, off, *vals)
+        return bytes(b)
+
+    sec = 4096
+    bad = {
+        "section count > header": patched(sec + 4, "<I", n + 1000),
+        "zero bucket size": patched(sec + 8, "<I", 0),
+        "bucket storage": patched(sec + 20, "<H", 8),
+        "more buckets than centres": patched(sec + 32, "<I", 1000),
+        "partial length huge": patched(4096 + 1024, "<I", 1 << 30),
+        "buckets do not cover": patched(sec + 32, "<I", 0),
+        "truncated": data[:-40],
+        "header count small": patched(12, "<I", 3),
+    }
+    with gs.Engine(n + 8, max_width=64, max_height=64) as e:
+        for name, blob in bad.items():
+            with pytest.raises(RuntimeError):
+                e.upload_ksplat(blob)
+        info = e.upload_ksplat(data)            # the engine is still usable afterwards
+        assert info["splat_count"] == n

@@ -117,10 +117,10 @@ class gs_kernel_time(C.Structure):
 
 
 EXPORTED_SYMBOLS = [
-    "gs_abi_version", "gs_status_string", "gs_last_error_message", "gs_device_count", "gs_sort_indexes", "sortIndexes",
+    "gs_abi_version", "gs_status_string", "gs_last_error_message", "gs_device_count", "gs_sort_indexes", "sortIndexes", "gs_dropin_release",
     "gs_create", "gs_destroy", "gs_upload_centers", "gs_sort", "gs_compute_distances", "gs_upload_splat_data",
     "gs_render", "gs_frame", "gs_buffer_dev", "gs_stream", "gs_synchronize", "gs_host_alloc", "gs_host_free",
-    "gs_read_projected", "gs_last_timings", "gs_frame_async", "gs_frame_begin", "gs_frame_end", "gs_flush_l2", "gs_event_create", "gs_event_record",
+    "gs_read_projected", "gs_last_timings", "gs_frame_async", "gs_frame_begin", "gs_frame_end", "gs_upload_splat_tree", "gs_gather_for_sort", "gs_flush_l2", "gs_event_create", "gs_event_record",
     "gs_event_elapsed_ms", "gs_event_destroy", "gs_set_profiling", "gs_kernel_timings", "gs_set_graph_enabled", "gs_upload_ksplat", "gs_read_buffer", "gs_peer_export", "gs_peer_attach",
     "gs_shard_export", "gs_shard_attach", "gs_shard_attach_local", "gs_sort_sharded", "gs_sort_sharded_async", "gs_sort_sharded_finish",
 ]
@@ -181,6 +181,12 @@ def load() -> C.CDLL:
     lib.gs_read_projected.argtypes = [vp, vp, u32]
     lib.gs_last_timings.restype = C.c_int
     lib.gs_last_timings.argtypes = [vp, C.POINTER(gs_timings)]
+    lib.gs_upload_splat_tree.restype = C.c_int
+    lib.gs_upload_splat_tree.argtypes = [vp, vp, vp, vp, vp, vp, C.c_uint32]
+    lib.gs_gather_for_sort.restype = C.c_int
+    lib.gs_gather_for_sort.argtypes = [vp, vp, C.c_double, C.c_double, C.c_int, C.POINTER(C.c_uint32)]
+    lib.gs_dropin_release.restype = None
+    lib.gs_dropin_release.argtypes = []
     lib.gs_frame_begin.restype = C.c_int
     lib.gs_frame_begin.argtypes = [vp, C.POINTER(gs_sort_params), C.POINTER(gs_uniforms), C.POINTER(gs_render_params), vp]
     lib.gs_frame_end.restype = C.c_int

@@ -10,6 +10,7 @@
 #include "shard_kernels.cuh"
 #include "ksplat_transform.h"
 #include "ksplat_kernels.cuh"
+#include "cull_kernels.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -143,6 +144,13 @@ struct gs_engine {
     bool pending_async = false;
     gs_render_params pending_rp{};
     DevBuf<uint32_t> flush;          // L2 flush scratch (bench hygiene)
+    // SplatTree leaves (gs_upload_splat_tree) and the scratch of gs_gather_for_sort
+    struct Tree {
+        DevBuf<double> center, nmin, nmax;
+        DevBuf<uint32_t> offsets, indexes, start;
+        DevBuf<unsigned long long> key, total;
+        uint32_t count = 0, splats = 0;
+    } tree;
     // pipelined frames (gs_frame_begin / gs_frame_end): device frames alternate between two buffers, the D2H copy of frame i runs on
     // copy_stream while frame i+1 computes on `stream`
     cudaStream_t copy_stream = nullptr;
@@ -226,6 +234,7 @@ extern "C" int gs_create(const gs_config *cfg, gs_engine **out) {
         for (int s = 0; s < GS_MAX_SCENES; ++s) id[16 * s] = id[16 * s + 5] = id[16 * s + 10] = id[16 * s + 15] = 1.f;
         CUE(cudaMemcpy(e->transforms.p, id.data(), id.size() * 4, cudaMemcpyHostToDevice));
     }
+    CUE(cudaMemset(e->ctl.p, 0, sizeof(SortControl)));
     rc = raster_init(e->rs, c, e->sm_count);
     if (rc) { gs_destroy(e); return fail(rc, "raster_init failed: %s", g_err); }
     CUE(cudaStreamSynchronize(e->stream));
@@ -242,7 +251,8 @@ extern "C" void gs_destroy(gs_engine *e) {
     e->centers.release(); e->scene_idx.release(); e->indexes.release(); e->precomputed.release(); e->dist.release();
     e->keys[0].release(); e->keys[1].release(); e->vals[0].release(); e->vals[1].release(); e->sorted.release();
     e->transforms.release(); e->ctl.release(); e->depthp.release(); e->tile_hist.release(); e->freq.release(); e->dist_rows_i.release(); e->dist_rows_f.release(); e->sub_idx.release(); e->sub_dist.release();
-    e->h_indexes.release(); e->h_sorted.release(); e->h_ctl.release(); e->h_frame.release(); e->h_pipe.release(); e->flush.release(); e->prof.release();
+    e->h_indexes.release(); e->h_sorted.release(); e->h_ctl.release(); e->h_frame.release(); e->h_pipe.release();
+    e->tree.center.release(); e->tree.nmin.release(); e->tree.nmax.release(); e->tree.offsets.release(); e->tree.indexes.release(); e->tree.start.release(); e->tree.key.release(); e->tree.total.release(); e->flush.release(); e->prof.release();
     e->shard.block.release(); e->shard.total.release(); e->shard.ahead.release(); e->shard.block_total.release(); e->shard.delta.release(); e->shard.local_sorted.release();
     for (void *m : e->shard.opened) if (m) cudaIpcCloseMemHandle(m);
     if (e->rs.peer_attached) { if (e->rs.peer_frame) cudaIpcCloseMemHandle(e->rs.peer_frame); if (e->rs.peer_sync) cudaIpcCloseMemHandle(e->rs.peer_sync); }
@@ -719,6 +729,13 @@ extern "C" int gs_sort_sharded(gs_engine *e, const gs_sort_params *p, uint32_t *
 // calls do not re-allocate; inputs are uploaded on every call like a non-shared-memory worker copies them
 // (SortWorker.js:35-51).
 static gs_engine *g_dropin = nullptr;
+#include <mutex>
+static std::mutex g_dropin_mutex;   // the stateless entry shares one cached engine: calls are serialised, not rejected
+
+extern "C" void gs_dropin_release(void) {
+    std::lock_guard<std::mutex> lock(g_dropin_mutex);
+    if (g_dropin) { gs_destroy(g_dropin); g_dropin = nullptr; }
+}
 
 extern "C" int gs_sort_indexes(const uint32_t *indexes, const void *centers, const void *precomputedDistances, int32_t *mappedDistances,
                                uint32_t *frequencies, const float *modelViewProj, uint32_t *indexesOut, const uint32_t *sceneIndexes,
@@ -730,14 +747,17 @@ extern "C" int gs_sort_indexes(const uint32_t *indexes, const void *centers, con
     if (dynamicMode && !usePrecomputedDistances && (!sceneIndexes || !transforms)) return fail(GS_ERR_BAD_ARG, "gs_sort_indexes: dynamic mode needs sceneIndexes and transforms");
     if (sortCount > renderCount || renderCount > splatCount) return fail(GS_ERR_BAD_ARG, "need sortCount <= renderCount <= splatCount");
     if (distanceMapRange < 2 || distanceMapRange > (1u << 24)) return fail(GS_ERR_BAD_ARG, "distanceMapRange %u outside [2, 2^24]", distanceMapRange);
+    std::lock_guard<std::mutex> lock(g_dropin_mutex);
+    int cur_dev = 0;
+    if (cudaGetDevice(&cur_dev) != cudaSuccess) { cudaGetLastError(); cur_dev = 0; }     // the caller's current device, like any CUDA library
     gs_engine *e = g_dropin;
-    if (!e || e->cfg.max_splat_count < splatCount || e->cfg.distance_map_range != distanceMapRange ||
+    if (!e || e->cfg.device != cur_dev || e->cfg.max_splat_count < splatCount || e->cfg.distance_map_range != distanceMapRange ||
         (bool)e->cfg.integer_based_sort != useIntegerSort || (bool)e->cfg.dynamic_mode != dynamicMode) {
         if (e) gs_destroy(e);
         g_dropin = nullptr;
         gs_config c{};
         c.struct_size = sizeof(c);
-        c.device = 0;
+        c.device = cur_dev;
         c.max_splat_count = std::max(splatCount, 1u);
         c.distance_map_range = distanceMapRange;
         c.integer_based_sort = useIntegerSort;
@@ -1135,6 +1155,59 @@ extern "C" int gs_frame_end(gs_engine *e) {
     if (rctl.peer_timeout) return fail(GS_ERR_CUDA, "multi-GPU tile gather: a peer did not arrive within the time limit (ranks must render the same frames)");
     if (rctl.overflow) return fail(GS_ERR_CAPACITY, "tile-instance buffer overflow: %llu instances needed, capacity %llu (raise GS_INSTANCE_FACTOR)",
                                    (unsigned long long)rctl.total_instances, (unsigned long long)e->rs.instance_capacity);
+    return GS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// SplatTree leaves -> device, and the per-frame cull + index gather (cull_kernels.cuh).
+extern "C" int gs_upload_splat_tree(gs_engine *e, const double *node_center, const double *node_min, const double *node_max, const uint32_t *node_offsets,
+                                    const uint32_t *indexes, uint32_t node_count) {
+    int rc = check_engine(e);
+    if (rc) return rc;
+    if (node_count && (!node_center || !node_min || !node_max || !node_offsets || !indexes)) return fail(GS_ERR_BAD_ARG, "gs_upload_splat_tree: null argument");
+    const uint32_t total = node_count ? node_offsets[node_count] : 0;
+    if (total > e->cfg.max_splat_count) return fail(GS_ERR_CAPACITY, "the tree's leaves hold %u indexes, engine capacity %u", total, e->cfg.max_splat_count);
+    for (uint32_t i = 0; i < node_count; ++i)
+        if (node_offsets[i + 1] < node_offsets[i]) return fail(GS_ERR_BAD_ARG, "gs_upload_splat_tree: node_offsets must be non-decreasing");
+    auto &t = e->tree;
+    const size_t m = std::max<uint32_t>(node_count, 1);
+    if ((rc = t.center.ensure(3 * m)) || (rc = t.nmin.ensure(3 * m)) || (rc = t.nmax.ensure(3 * m)) || (rc = t.offsets.ensure(m + 1)) || (rc = t.indexes.ensure(std::max<uint32_t>(total, 1))) ||
+        (rc = t.start.ensure(m)) || (rc = t.key.ensure(m)) || (rc = t.total.ensure(1)))
+        return rc;
+    cudaStream_t st = e->stream;
+    if (node_count) {
+        CU(cudaMemcpyAsync(t.center.p, node_center, 24 * (size_t)node_count, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(t.nmin.p, node_min, 24 * (size_t)node_count, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(t.nmax.p, node_max, 24 * (size_t)node_count, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(t.offsets.p, node_offsets, 4 * ((size_t)node_count + 1), cudaMemcpyHostToDevice, st));
+        if (total) CU(cudaMemcpyAsync(t.indexes.p, indexes, 4 * (size_t)total, cudaMemcpyHostToDevice, st));
+    }
+    CU(cudaStreamSynchronize(st));
+    t.count = node_count; t.splats = total;
+    return GS_OK;
+}
+
+extern "C" int gs_gather_for_sort(gs_engine *e, const double *model_view, double cos_fov_x_over_2, double cos_fov_y_over_2, int gather_all_nodes,
+                                  uint32_t *render_count_out) {
+    int rc = check_engine(e);
+    if (rc) return rc;
+    if (!model_view || !render_count_out) return fail(GS_ERR_BAD_ARG, "gs_gather_for_sort: null argument");
+    auto &t = e->tree;
+    if (!t.count) { *render_count_out = 0; return GS_OK; }
+    CullParams P;
+    memcpy(P.mv, model_view, sizeof(P.mv));
+    P.cos_fov_x_over_2 = cos_fov_x_over_2; P.cos_fov_y_over_2 = cos_fov_y_over_2; P.gather_all = gather_all_nodes;
+    cudaStream_t st = e->stream;
+    k_tree_cull<<<(t.count + 127) / 128, 128, 0, st>>>(t.center.p, t.nmin.p, t.nmax.p, t.count, P, t.key.p);
+    k_tree_layout<<<(t.count + kLayoutThreads - 1) / kLayoutThreads, kLayoutThreads, 0, st>>>(t.key.p, t.offsets.p, t.count, t.start.p, t.total.p);
+    k_tree_copy<<<t.count, 128, 0, st>>>(t.start.p, t.offsets.p, t.indexes.p, e->indexes.p);
+    CU(cudaMemcpyAsync(e->h_ctl.p + 8, t.total.p, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    unsigned long long total;
+    memcpy(&total, e->h_ctl.p + 8, 8);
+    *render_count_out = (uint32_t)total;
+    e->tm.kernel_launches = 3;
     return GS_OK;
 }
 

@@ -1046,6 +1046,9 @@ __device__ __noinline__ uint32_t block_touch_mask(float4 a0, float4 a1, float ti
     // block i spans [X0 + 8 i, X0 + 8 i + 7]; it meets [-hx, hx] iff  (-hx - X0 - 7) / 8 <= i <= (hx - X0) / 8
     const int ix0 = max(0, (int)ceilf((-hx - X0 - 7.0f) * 0.125f)), ix1 = min(NB - 1, (int)floorf((hx - X0) * 0.125f));
     const int iy0 = max(0, (int)ceilf((-hy - Y0 - 7.0f) * 0.125f)), iy1 = min(NB - 1, (int)floorf((hy - Y0) * 0.125f));
+    // The AABB (exact extents of the ellipse) inside ONE block: that block holds the whole ellipse, nothing to decide.  (A block without
+    // a pixel centre inside the ellipse can still pass here; it costs one visit that adds nothing.)
+    if (ix0 == ix1 && iy0 == iy1) return 1u << (iy0 * NB + ix0);
     uint32_t bm = 0;
 #pragma unroll 1
     for (int iy = iy0; iy <= iy1; ++iy) {
@@ -1068,7 +1071,9 @@ k_blend2(const uint2 *__restrict__ ranges, const unsigned long long *__restrict_
     __shared__ float4 s_rec[THREADS][3];
     __shared__ uint32_t s_ids[BATCH];
     __shared__ uint32_t s_cnt[4 * WARPS + 1];   // [round][warp] survivors of the filter -> exclusive offsets; last = total
-    __shared__ uint32_t s_touch[WARPS][WARPS];  // [block][staging warp] staged records that reach the block
+    __shared__ uint8_t s_list[WARPS][THREADS];  // [block][staging warp * 32 + k] indices of the staged records that reach the block, in order
+    __shared__ uint8_t s_nlist[WARPS][WARPS];   // [block][staging warp] how many
+    static_assert(THREADS <= 256 || sizeof(uint8_t) == 1, "");
     const uint32_t coarse = blockIdx.x / kFinePerCoarse, sub = blockIdx.x % kFinePerCoarse;
     const int ccx = (int)(coarse % (uint32_t)coarse_x), ccy = (int)(coarse / (uint32_t)coarse_x);
     const int tx = ccx * kCoarseW + (int)(sub & (kCoarseW - 1)), ty = ccy * kCoarseH + (int)(sub >> kCoarseShiftX);
@@ -1129,28 +1134,33 @@ k_blend2(const uint2 *__restrict__ ranges, const unsigned long long *__restrict_
                 const float4 a2 = __ldg(src + 2);
                 // a0 = cx, cy, g1x, g1y ; a1 = g2x, g2y, half2(hx, hy), alpha ; a2 = r, g, b, ndc z
                 bm = block_touch_mask<NB>(a0, a1, tile_x0, tile_y0);
+                // staged form: u(p) = g1 . p + u0, w(p) = g2 . p + w0 at a pixel centre p (two FMAs each in the loop below)
+                const float u0 = -fmaf(a0.x, a0.z, a0.y * a0.w), w0 = -fmaf(a0.x, a1.x, a0.y * a1.y);
                 a1.z = a0.w * a0.w + a1.y * a1.y;     // h = |d(u,w)/dy|^2
                 a1.w = log2f(a1.w);                   // opacity folded into the exponent
-                s_rec[threadIdx.x][0] = a0;
-                s_rec[threadIdx.x][1] = a1;
+                a0.x = u0; a0.y = w0;
+                s_rec[threadIdx.x][0] = a0;           // u0, w0, g1x, g1y
+                s_rec[threadIdx.x][1] = a1;           // g2x, g2y, h, log2(alpha)
                 s_rec[threadIdx.x][2] = a2;
             }
+            // per block: the indices of this staging warp's records that reach it, compacted in order
 #pragma unroll
             for (int b = 0; b < WARPS; ++b) {
                 const uint32_t v = __ballot_sync(0xffffffffu, (bm >> b) & 1u);
-                if (lane == 0) s_touch[b][warp] = v;
+                if ((bm >> b) & 1u) s_list[b][warp * 32 + __popc(v & lt)] = (uint8_t)(threadIdx.x & 255);
+                if (lane == 0) s_nlist[b][warp] = (uint8_t)__popc(v);
             }
             __syncthreads();
             if (!wdone) {
 #pragma unroll 1
                 for (int sw = 0; sw < WARPS && !wdone; ++sw) {
-                    uint32_t bits = s_touch[warp][sw];
-                    while (bits) {
-                        const int jj = sw * 32 + __ffs(bits) - 1;
-                        bits &= bits - 1;
+                    const int cnt = s_nlist[warp][sw];
+                    const uint8_t *lst = &s_list[warp][sw * 32];
+#pragma unroll 1
+                    for (int k = 0; k < cnt; ++k) {
+                        const int jj = (THREADS > 256 ? (sw & ~7) * 32 : 0) + lst[k];      // 8-bit index inside the group of 8 staging warps
                         const float4 A = s_rec[jj][0], B = s_rec[jj][1], C = s_rec[jj][2];
-                        const float dx = pxc - A.x, dy = pyc - A.y;
-                        const float u = fmaf(dy, A.w, dx * A.z), w = fmaf(dy, B.y, dx * B.x);
+                        const float u = fmaf(pxc, A.z, fmaf(pyc, A.w, A.x)), w = fmaf(pxc, B.x, fmaf(pyc, B.y, A.y));
                         const float q0 = fmaf(w, w, u * u);
                         const float q1 = q0 + fmaf(2.0f, fmaf(u, A.w, w * B.y), B.z);        // one pixel up: (u + g1y)^2 + (w + g2y)^2
                         // exp(-0.5 A) * vColor.a with A = 8 q, zero outside the quad's inscribed disc (branch-free)

@@ -201,6 +201,33 @@ class Engine:
         self.sort_sharded_async(mvp, sort_count, render_count, indexes, transforms=transforms, precomputed=precomputed)
         return self.sort_sharded_finish(out)
 
+    # -- SplatTree cull -> indexesToSort (gs_upload_splat_tree / gs_gather_for_sort) --------------------------------------------
+    def upload_splat_tree(self, leaves) -> None:
+        """`leaves`: splat_tree.SplatTreeLeaves (nodesWithIndexes of the tree)."""
+        c = np.ascontiguousarray(leaves.node_center, dtype=np.float64)
+        mn = np.ascontiguousarray(leaves.node_min, dtype=np.float64)
+        mx = np.ascontiguousarray(leaves.node_max, dtype=np.float64)
+        off = np.ascontiguousarray(leaves.offsets, dtype=np.uint32)
+        idx = np.ascontiguousarray(leaves.indexes, dtype=np.uint32)
+        N.check(self._lib.gs_upload_splat_tree(self._h, N.ptr(c), N.ptr(mn), N.ptr(mx), N.ptr(off), N.ptr(idx) if idx.size else None, leaves.count), "gs_upload_splat_tree")
+
+    def gather_for_sort(self, model_view64, cos_fov_x_over_2: float, cos_fov_y_over_2: float, gather_all: bool = False) -> int:
+        """Viewer.gatherSceneNodesForSort on the GPU: fills the engine's indexesToSort, returns splatRenderCount."""
+        mv = np.ascontiguousarray(model_view64, dtype=np.float64).reshape(16)
+        rc = C.c_uint32(0)
+        N.check(self._lib.gs_gather_for_sort(self._h, N.ptr(mv), float(cos_fov_x_over_2), float(cos_fov_y_over_2), 1 if gather_all else 0, C.byref(rc)), "gs_gather_for_sort")
+        return int(rc.value)
+
+    def sort_gathered(self, mvp, sort_count: int, render_count: int, *, out: np.ndarray | None = None, download: bool = True, transforms=None):
+        """gs_sort over the index list gs_gather_for_sort left on the device."""
+        ptr, _ = self.buffer_dev(N.GS_BUF_INDEXES_TO_SORT)
+        p = self._sort_params(mvp, sort_count, render_count, None, transforms, None, indexes_dev=ptr)
+        if download and out is None:
+            out = np.empty(render_count, np.uint32)
+        ms = C.c_float(0)
+        N.check(self._lib.gs_sort(self._h, C.byref(p), N.ptr(out) if download else None, C.byref(ms)), "gs_sort")
+        return (out if download else None), ms.value
+
     def compute_distances(self, mvp64, count: int, scene_transforms64=None) -> np.ndarray:
         m = np.ascontiguousarray(mvp64, dtype=np.float64).reshape(16)
         st = None if scene_transforms64 is None else np.ascontiguousarray(scene_transforms64, dtype=np.float64).reshape(-1)

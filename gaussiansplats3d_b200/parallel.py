@@ -12,7 +12,14 @@ from __future__ import annotations
 import numpy as np
 
 TILE = 16
-COARSE_W, COARSE_H = 128, 64   # pixels (8 x 4 fine tiles), csrc/raster_kernels.cuh kCoarseW/kCoarseH
+COARSE_W, COARSE_H = 128, 64   # pixels (8 x 4 fine tiles of 16 px), csrc/raster_kernels.cuh kCoarseW/kCoarseH
+
+
+def tile_px(width: int, height: int) -> int:
+    """Fine-tile edge the engine uses for a frame (csrc/raster_kernels.cuh frame_tile_shift): 16 px while that gives at most 256 coarse
+    tiles, else 32 px (a coarse tile is always 8 x 4 fine tiles)."""
+    cx, cy = -(-width // COARSE_W), -(-height // COARSE_H)
+    return TILE if cx * cy <= 256 else 2 * TILE
 
 
 def owner_of_coarse(cx: int, cy: int, world: int) -> int:
@@ -21,8 +28,9 @@ def owner_of_coarse(cx: int, cy: int, world: int) -> int:
 
 def ownership_map(width: int, height: int, world: int) -> np.ndarray:
     """[height, width] array of the rank that rasterises each pixel (GL row order)."""
+    t = tile_px(width, height)
     ys, xs = np.mgrid[0:height, 0:width]
-    return ((xs // COARSE_W + ys // COARSE_H) % max(world, 1)).astype(np.int32)
+    return ((xs // (8 * t) + ys // (4 * t)) % max(world, 1)).astype(np.int32)
 
 
 def combine_frames(frames: list):

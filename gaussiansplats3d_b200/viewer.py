@@ -22,6 +22,7 @@ from . import three_math as TM
 from .engine import Engine, Uniforms
 from .scenes import PackedScene, RawScene, float_centers, integer_centers, pack_scene
 from .sort_worker import DefaultSplatSortDistanceMapPrecision, createSortWorker, start
+from .splat_tree import SplatTree, fov_cosines
 
 THREE_CAMERA_FOV = 50  # Viewer.js:30
 
@@ -55,6 +56,7 @@ class SplatMesh:
         # per-scene transforms of a dynamic mesh (SplatScene.transform, SplatScene.js:28-36; uploaded every frame by
         # fillTransformsArray, SplatMesh.js:1660-1673): column-major f64, scene 0 = the one scene this mirror holds
         self.sceneTransforms = np.tile(TM.identity(), (N.GS_MAX_SCENES, 1))
+        self.splatTree: SplatTree | None = None
 
     def build(self, raw_scene: RawScene, *, sh_format: str = "f16", transform16=None) -> None:
         """Decode + pack the scene like refreshGPUDataFromSplatBuffers (SplatMesh.js:588-603) and keep it for upload.
@@ -79,6 +81,16 @@ class SplatMesh:
     def fillTransformsArray(self) -> np.ndarray:  # noqa: N802  SplatMesh.js:1660-1673
         """f32[32 x 16] for the sorter ('transforms' of the sort message) and the vertex stage (`transforms` uniform)."""
         return self.sceneTransforms.astype(np.float32)
+
+    def buildSplatTree(self, minAlpha: int = 1) -> SplatTree:  # noqa: N802,N803  SplatMesh.js:231-279
+        """new SplatTree(8, 1000).processSplatMesh(this, alpha >= minAlpha): the octree over the (transformed) centres."""
+        tree = SplatTree(8, 1000)
+        tree.processSplatMesh(self.raw.centers, self.raw.colors[:, 3], minAlpha)
+        self.splatTree = tree
+        return tree
+
+    def getSplatTree(self):  # noqa: N802  SplatMesh.js:557-559
+        return self.splatTree
 
     def getSplatCount(self) -> int:  # noqa: N802
         return 0 if self.packed is None else self.packed.count
@@ -150,6 +162,12 @@ class Viewer:
         self.sortWorkerIndexesToSort: np.ndarray | None = None
         self.sortWorkerSortedIndexes: np.ndarray | None = None
         self._sorted_on_device = False
+        self.enableSplatTree = bool(o.get("splatTree", False))   # the reference always builds its tree; the benchmark configs sort all splats, so opt-in
+        # runSplatSort's closure state (Viewer.js:1835-1841)
+        self._lastSortViewDir = np.array([0.0, 0.0, -1.0])
+        self._lastSortViewPos = np.zeros(3)
+        self._queuedSorts: list[int] = []
+        self._gathered = False
 
     # -- scene set-up (addSplatBuffers / setupSortWorker, Viewer.js:1094-1300) ------------------------------------------------
     def addSplatScene(self, raw_scene: RawScene, *, separate_sort_worker: bool = False, position=(0.0, 0.0, 0.0),  # noqa: N802
@@ -178,6 +196,8 @@ class Viewer:
         else:
             self.engine.upload_centers(centers, np.zeros(n, np.uint32) if self.dynamicScene else None)
         self.splatRenderCount = n
+        if self.enableSplatTree:
+            self.engine.upload_splat_tree(self.splatMesh.buildSplatTree().leaves)
 
     def addSplatSceneFromKSplat(self, data: bytes, *, position=(0.0, 0.0, 0.0), rotation=(0.0, 0.0, 0.0, 1.0), scale=(1.0, 1.0, 1.0)) -> dict:  # noqa: N802
         """Viewer.addSplatScene for a `.ksplat` buffer (KSplatLoader.loadFromFileData -> new SplatBuffer -> SplatMesh.build ->
@@ -252,36 +272,77 @@ class Viewer:
                         scene_center=sm.sceneCenter, visible_region_fade_start_radius=sm.visibleRegionFadeStartRadius)
 
     # -- the per-frame path --------------------------------------------------------------------------------------------------------
-    def runSplatSort(self, force: bool = False, forceSortAll: bool = True) -> bool:  # noqa: N802,N803  Viewer.js:1833-1964
-        """Full sort of all splats (gatherSceneNodesForSort's shouldSortAll case, Viewer.js:2061-2074); the partial-sort
-        queue and the octree gather are out of scope."""
-        del force, forceSortAll
+    def gatherSceneNodesForSort(self, gatherAllNodes: bool = False) -> tuple[int, bool]:  # noqa: N802,N803  Viewer.js:1969-2077
+        """(splatRenderCount, shouldSortAll).  With a SplatTree: every leaf is culled against the frustum and the kept leaves' indexes are
+        laid out nearest-last in the sorter's indexesToSort -- on the GPU (gs_gather_for_sort); without one: identity, sort all."""
+        tree = self.splatMesh.getSplatTree()
+        if tree is None or tree.leaves is None:
+            self._gathered = False
+            return self.splatMesh.getSplatCount(), True
+        base = TM.invert(self.camera.matrixWorld)
+        if not self.splatMesh.dynamicMode:
+            base = TM.multiply(base, self.splatMesh.matrixWorld)
+        cx, cy = fov_cosines(self.renderWidth * self.devicePixelRatio, self.renderHeight * self.devicePixelRatio, self.camera.fov)
+        count = self.engine.gather_for_sort(base, cx, cy, gatherAllNodes)
+        self._gathered = True
+        return count, False
+
+    def runSplatSort(self, force: bool = False, forceSortAll: bool = False) -> bool:  # noqa: N802,N803  Viewer.js:1833-1964
+        """The reference's scheduling: skip while the view has barely changed, gather the visible leaves, and after a large rotation queue
+        partial sorts of the nearest 12.5 % / 33 % / 75 % ... before the full one (Viewer.js:1843-1856, 1899-1913)."""
         if self.sortRunning:
             return True
-        n = self.splatMesh.getSplatCount()
-        if n <= 0:
+        if self.splatMesh.getSplatCount() <= 0:
             self.splatRenderCount = 0
             return False
-        self.splatRenderCount = self.splatSortCount = n
+        view_dir = -np.asarray(self.camera.matrixWorld[8:11], np.float64)     # (0, 0, -1).applyQuaternion(camera.quaternion)
+        angle_diff = float(np.dot(view_dir, self._lastSortViewDir))
+        position_diff = float(np.linalg.norm(np.asarray(self.camera.position, np.float64) - self._lastSortViewPos))
+        if not force and not self.splatMesh.dynamicMode and not self._queuedSorts:
+            if not (angle_diff <= 0.99 or position_diff >= 1.0):
+                return False
+        render_count, should_sort_all = self.gatherSceneNodesForSort()
+        should_sort_all = should_sort_all or forceSortAll
+        self.splatRenderCount = render_count
         mvp = self.mvp_matrix()
+        if not self._queuedSorts:
+            if self.splatMesh.dynamicMode or should_sort_all:
+                self._queuedSorts.append(render_count)
+            else:
+                for threshold, fractions in ((0.55, (0.125, 0.33333, 0.75)), (0.65, (0.33333, 0.66667)), (0.8, (0.5,))):
+                    if angle_diff < threshold:
+                        self._queuedSorts.extend(int(np.floor(render_count * f)) for f in fractions)
+                        break
+                self._queuedSorts.append(render_count)
+        sort_count = min(self._queuedSorts.pop(0), render_count)
+        self.splatSortCount = sort_count
+        n = render_count
         if self.sortWorker is not None:
             self.sortRunning = True
             msg = {"modelViewProj": mvp.astype(np.float32), "cameraPosition": list(self.camera.position), "splatRenderCount": n,
-                   "splatSortCount": n, "usePrecomputedDistances": False}
+                   "splatSortCount": sort_count, "usePrecomputedDistances": False}
             if not self.sharedMemoryForWorkers:
                 msg["indexesToSort"] = np.arange(n, dtype=np.uint32)
                 msg["transforms"] = self.splatMesh.fillTransformsArray() if self.splatMesh.dynamicMode else None
             self.sortWorker.postMessage({"sort": msg})
         else:
-            _, ms = self.engine.sort(mvp.astype(np.float32), n, n, None, download=False,
-                                     transforms=self.splatMesh.fillTransformsArray() if self.splatMesh.dynamicMode else None)
+            tr = self.splatMesh.fillTransformsArray() if self.splatMesh.dynamicMode else None
+            if self._gathered:
+                _, ms = self.engine.sort_gathered(mvp.astype(np.float32), sort_count, n, download=False, transforms=tr)
+            else:
+                _, ms = self.engine.sort(mvp.astype(np.float32), sort_count, n, None, download=False, transforms=tr)
             self.lastSortTime = ms
             self.splatMesh.updateRenderIndexes(None, n)
+        if not self._queuedSorts:
+            self._lastSortViewPos = np.asarray(self.camera.position, np.float64).copy()
+            self._lastSortViewDir = view_dir.copy()
         return True
 
-    def update(self) -> None:  # Viewer.js:1625-1644
+    def update(self, force_sort: bool = True) -> None:  # Viewer.js:1625-1644
+        """force_sort=True sorts on every call (what the tests and the benchmark want); False applies the reference's view-change
+        thresholds like its frame loop does."""
         self.camera.update()
-        self.runSplatSort()
+        self.runSplatSort(force=force_sort, forceSortAll=force_sort and self.splatMesh.getSplatTree() is None)
         self.updateSplatMesh()
 
     def render(self, *, frame_format: int = N.GS_FRAME_RGBA8, flip_y: bool = True, download: bool = True):  # Viewer.js:1599-1623

@@ -10,7 +10,7 @@
  *
  * Threading: like the reference's worker (one sort in flight, SortWorker.js `sortRunning`), an engine handle is driven by one
  * thread at a time; different handles may be used from different threads.  The stateless drop-in (section 1) keeps one cached
- * private engine and is NOT re-entrant.  gs_last_error_message() is per thread.
+ * private engine; concurrent calls are serialised.  gs_last_error_message() is per thread.
  */
 #ifndef GSPLAT_B200_H
 #define GSPLAT_B200_H
@@ -58,6 +58,11 @@ GS_API int gs_sort_indexes(const uint32_t *indexes, const void *centers, const v
                            uint32_t *indexesOut, const uint32_t *sceneIndexes, const float *transforms,
                            uint32_t distanceMapRange, uint32_t sortCount, uint32_t renderCount, uint32_t splatCount,
                            bool usePrecomputedDistances, bool useIntegerSort, bool dynamicMode);
+
+/* The stateless entry keeps ONE private engine cached (sized for the largest call so far, on the caller's current CUDA device) so that
+ * repeated calls do not re-allocate; concurrent callers are serialised by a mutex.  gs_dropin_release() frees it (call it before
+ * unloading the library or tearing the CUDA context down; it is re-created on demand). */
+GS_API void gs_dropin_release(void);
 
 /* void twin with the reference's exact symbol name and signature; errors are swallowed like a wasm trap
  * would abort the call (indexesOut untouched on failure). */
@@ -113,6 +118,20 @@ typedef struct gs_sort_params {
  * device for gs_render.  sorted_out (HOST u32[render_count], may be NULL) receives 'sortedIndexes'
  * (SortWorker.js:68-75); sort_time_ms (may be NULL) the device time of the sort kernels.                       */
 GS_API int gs_sort(gs_engine *e, const gs_sort_params *p, uint32_t *sorted_out, float *sort_time_ms);
+
+/* The SplatTree's leaves (`nodesWithIndexes`, src/splattree/SplatTree.js:55-79; built at load on the host like the reference's tree worker)
+ * and the per-frame half of Viewer.gatherSceneNodesForSort (src/Viewer.js:1969-2077) on the GPU: every leaf is tested against the view
+ * frustum (the two angle tests and the `distance > nodeSize` exemption of Viewer.js:2013-2033, f64), the kept leaves are ordered by their
+ * distance to the camera and their index runs are written into the engine's indexesToSort (GS_BUF_INDEXES_TO_SORT) from the END of the
+ * window backwards -- nearest leaf last -- exactly the layout the reference builds (Viewer.js:2040-2055).  *render_count = splatRenderCount.
+ * Follow with gs_sort(indexes_to_sort_dev = GS_BUF_INDEXES_TO_SORT, render_count, sort_count <= render_count): a partial sort
+ * (Viewer.js:1843-1856) re-sorts the nearest sort_count splats and copies the rest through (sorter.cpp:158-160).
+ * node_center / node_min / node_max: f64[3 * node_count]; node_offsets: u32[node_count + 1]; indexes: u32[node_offsets[node_count]].
+ * model_view: f64[16] column-major = inverse(camera.matrixWorld) [* mesh.matrixWorld]; cos_fov_*: Viewer.js:1990-1995.                 */
+GS_API int gs_upload_splat_tree(gs_engine *e, const double *node_center, const double *node_min, const double *node_max,
+                                const uint32_t *node_offsets, const uint32_t *indexes, uint32_t node_count);
+GS_API int gs_gather_for_sort(gs_engine *e, const double *model_view, double cos_fov_x_over_2, double cos_fov_y_over_2, int gather_all_nodes,
+                              uint32_t *render_count);
 
 /* D1: the transform-feedback distance pre-pass, SplatMesh.computeDistancesOnGPU (SplatMesh.js:1701-1814): distances
  * in SPLAT order from the uploaded centres.  model_view_proj is f64 because three.js matrices are JS numbers and the

@@ -29,6 +29,17 @@ def build(quiet: bool = True) -> None:
         print(res.stdout)
 
 
+def set_threads(n: int) -> int:
+    """OpenMP threads of the CPU restatement (libgomp of this process).  Launchers such as torchrun export OMP_NUM_THREADS=1, which
+    would silently run the 'all host cores' baseline on one core: callers that time the oracle set the count explicitly."""
+    n = max(1, int(n))
+    try:
+        C.CDLL("libgomp.so.1").omp_set_num_threads(n)
+    except OSError:
+        pass
+    return n
+
+
 def have_ref() -> bool:
     return REF_LIB.exists()
 

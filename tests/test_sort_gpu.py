@@ -163,3 +163,69 @@ def test_engine_argument_errors_and_empty_work(gs):
             e.render(Uniforms(np.eye(4), np.eye(4), np.zeros(3), (1, 1), (8, 8)), 8, 8, 10)
     with pytest.raises(gs.GsError):
         gs.Engine(10, distance_map_range=1)                   # range < 2
+
+
+@pytest.mark.parametrize("integer,dynamic", [(True, False), (True, True), (False, False), (False, True)])
+def test_distance_prepass_all_four_shader_variants(gs, oracle_mod, integer, dynamic):
+    """D1: SplatMesh.computeDistancesOnGPU, the four transform-feedback vertex shaders (SplatMesh.js:1451-1502) with their host side
+    (:1722-1738, getIntegerMatrixArray :2057-2064 = Math.round(element * 1000)).  Integer variants are bit-exact (wrapping int32);
+    the float variants are GLSL f32 dot products whose summation order a driver may choose, so they are compared to 1 ulp of the
+    largest term.  The distances then drive the sorter's precomputed branch (sorter.cpp:31-38, 79-86) bit-exactly."""
+    n = 50_000
+    c = cases.sort_case(seed=6, n=n, integer=integer, dynamic=dynamic, index_kind="identity")
+    mvp64 = c["mvp"].astype(np.float64)
+    T64 = None
+    if dynamic:
+        T64 = np.zeros((32, 16), np.float64)
+        T64[:] = np.eye(4).T.reshape(16)
+        T64[: c["transforms"].shape[0]] = c["transforms"].astype(np.float64)
+    with gs.Engine(n, integer_based_sort=integer, dynamic_mode=dynamic) as e:
+        e.upload_centers(c["centers"], c["scene_indexes"])
+        d = e.compute_distances(mvp64, n, T64)
+        M = mvp64.reshape(4, 4).T
+        if dynamic:     # tempMatrix = mvp * transform_s (premultiply), row 2 of it: elements [2], [6], [10], [14]
+            rows = np.stack([(M @ T64[s].reshape(4, 4).T)[2] for s in range(32)])
+        else:
+            rows = np.tile(M[2], (32, 1))
+        scene = c["scene_indexes"].astype(np.int64) if dynamic else np.zeros(n, np.int64)
+        if integer:
+            ir = np.floor(rows * 1000.0 + 0.5).astype(np.int64)[scene]
+            cc = c["centers"].astype(np.int64)
+            want = cc[:, 0] * ir[:, 0] + cc[:, 1] * ir[:, 1] + cc[:, 2] * ir[:, 2] + (ir[:, 3] * cc[:, 3] if dynamic else 0)
+            want = ((want + 2**31) % 2**32 - 2**31).astype(np.int32)
+            assert d.dtype == np.int32 and np.array_equal(d, want)
+        else:
+            fr = rows.astype(np.float32)[scene]
+            cc = c["centers"].astype(np.float32)
+            terms = np.stack([cc[:, 0] * fr[:, 0], cc[:, 1] * fr[:, 1], cc[:, 2] * fr[:, 2]] + ([fr[:, 3]] if dynamic else []), 1)
+            want = terms.astype(np.float64).sum(1)
+            assert d.dtype == np.float32
+            assert np.all(np.abs(d.astype(np.float64) - want) <= 2.0 * np.spacing(np.abs(terms).max(1).astype(np.float32)).astype(np.float64) + 1e-30)
+        out, _ = e.sort(c["mvp"], n, n, None, precomputed=d, transforms=c["transforms"])
+        c3 = dict(c, precomputed=d, use_precomputed=True)
+        assert np.array_equal(out, _expect(oracle_mod, c3, 1 << 16))
+
+
+def test_void_twin_sortIndexes_has_the_reference_signature(gs, oracle_mod):
+    """`extern "C" void sortIndexes(...16 args...)` (sorter.cpp:17-22): the symbol a wasm-free host would bind in place of the reference's;
+    same arguments, no return value, indexesOut untouched on failure (like a trap that aborts the call)."""
+    import ctypes as C
+    lib = gs._native.load()
+    c = cases.sort_case(seed=3, n=30_000, index_kind="octree", sort_frac=0.6)
+    R = 1 << 16
+    out = np.full(c["render_count"], 0xFFFFFFFF, np.uint32)
+    mapped = np.zeros(c["render_count"], np.int32)
+    freq = np.zeros(2 * R, np.uint32)
+    idx = np.ascontiguousarray(c["indexes"], np.uint32); cen = np.ascontiguousarray(c["centers"]); mvp = np.ascontiguousarray(c["mvp"], np.float32)
+    lib.sortIndexes.restype = None
+    lib.sortIndexes.argtypes = [C.c_void_p] * 9 + [C.c_uint32] * 4 + [C.c_bool] * 3
+    p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)   # noqa: E731
+    lib.sortIndexes(p(idx), p(cen), None, p(mapped), p(freq), p(mvp), p(out), None, None, R, c["sort_count"], c["render_count"], c["splat_count"], False, True, False)
+    assert np.array_equal(out, _expect(oracle_mod, c, R))
+    # failure path: sortCount > renderCount is refused, the output buffer keeps its contents
+    sentinel = np.full(c["render_count"], 123456789, np.uint32)
+    lib.sortIndexes(p(idx), p(cen), None, None, None, p(mvp), p(sentinel), None, None, R, c["render_count"] + 1, c["render_count"], c["splat_count"], False, True, False)
+    assert (sentinel == 123456789).all()
+    lib.gs_dropin_release()          # the cached private engine of the stateless entry can be dropped explicitly
+    lib.sortIndexes(p(idx), p(cen), None, p(mapped), p(freq), p(mvp), p(out), None, None, R, c["sort_count"], c["render_count"], c["splat_count"], False, True, False)
+    assert np.array_equal(out, _expect(oracle_mod, c, R))

@@ -698,10 +698,18 @@ k_bin_count(const uint32_t *__restrict__ order, uint32_t render_count_host, cons
 // One CTA per coarse tile: where its list starts (all smaller tiles' totals) and the running offset of every chunk inside it.
 __global__ void __launch_bounds__(1024)
 k_bin_scan(uint32_t *__restrict__ hist, uint32_t stride, uint32_t ranks_per_chunk, uint32_t render_count_host, const unsigned long long *__restrict__ n_dev,
-           const uint32_t *__restrict__ totals, uint32_t nt, uint2 *__restrict__ ranges, RasterControl *rctl) {
+           const uint32_t *__restrict__ totals, uint32_t nt, uint2 *__restrict__ ranges, RasterControl *rctl, uint32_t *__restrict__ tile_order) {
     pdl_enter();
     __shared__ uint32_t s_scan[40];
     __shared__ uint32_t s_carry;
+    {   // longest list first: the blend's duration is bounded below by its densest tiles, so their CTAs must start first.
+        // rank of this tile among all tiles by list length, descending (ties: lower tile id first)
+        const uint32_t mine = totals[blockIdx.x];
+        bool ahead = false;
+        if (threadIdx.x < nt) { const uint32_t o = totals[threadIdx.x]; ahead = o > mine || (o == mine && threadIdx.x < blockIdx.x); }
+        const int rank = __syncthreads_count(ahead);
+        if (threadIdx.x == 0) tile_order[rank] = blockIdx.x;
+    }
     const uint32_t n = n_dev ? (uint32_t)*n_dev : render_count_host;
     const uint32_t nchunks = (uint32_t)(((uint64_t)n + ranks_per_chunk - 1) / ranks_per_chunk);
     const uint32_t d = blockIdx.x;
@@ -863,7 +871,7 @@ k_subset_emit(const uint32_t *__restrict__ indexes, uint32_t count, const ushort
     }
 }
 
-__global__ void k_raster_init(RasterControl *rctl, SortControl *ctl, uint2 *ranges, uint32_t ntiles, uint32_t *super_sums, uint32_t nsuper, uint32_t *bin_totals) {
+__global__ void k_raster_init(RasterControl *rctl, SortControl *ctl, uint2 *ranges, uint32_t ntiles, uint32_t *super_sums, uint32_t nsuper, uint32_t *bin_totals, uint32_t *tile_order) {
     pdl_enter();
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -878,6 +886,7 @@ __global__ void k_raster_init(RasterControl *rctl, SortControl *ctl, uint2 *rang
     for (size_t i = tid; i < (size_t)kVisibleSlots * 8; i += stride) rctl->visible_slots[i] = 0;
     for (size_t i = tid; i < nsuper; i += stride) super_sums[i] = 0;
     if (bin_totals) for (size_t i = tid; i < 1024; i += stride) bin_totals[i] = 0;
+    for (size_t i = tid; i < ntiles; i += stride) tile_order[i] = (uint32_t)i;     // blend schedule: identity unless the counting-sort binning ranks the tiles
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -898,12 +907,12 @@ __device__ __forceinline__ float ex2_approx(float x) {
 template <int FORMAT>
 __global__ void __launch_bounds__(kBlendThreads)
 k_blend(const uint2 *__restrict__ ranges, const unsigned long long *__restrict__ list, const SplatRecord *__restrict__ rec, int tiles_x,
-        int tiles_y, int coarse_x, uint32_t rank, uint32_t world, int width, int height, int flip_y, void *__restrict__ frame) {
+        int tiles_y, int coarse_x, uint32_t rank, uint32_t world, int width, int height, int flip_y, void *__restrict__ frame, const uint32_t *__restrict__ tile_order) {
     pdl_enter();
     __shared__ float4 s_rec[kBlendThreads][3];
     __shared__ uint32_t s_ids[kBlendScan];
     __shared__ uint32_t s_cnt[2][4][2];
-    const uint32_t coarse = blockIdx.x / kFinePerCoarse, sub = blockIdx.x % kFinePerCoarse;
+    const uint32_t coarse = tile_order[blockIdx.x / kFinePerCoarse], sub = blockIdx.x % kFinePerCoarse;
     const int tx = (int)(coarse % (uint32_t)coarse_x) * kCoarseW + (int)(sub & (kCoarseW - 1));
     const int ty = (int)(coarse / (uint32_t)coarse_x) * kCoarseH + (int)(sub >> kCoarseShiftX);
     if (tx >= tiles_x || ty >= tiles_y) return;
@@ -1063,18 +1072,18 @@ __device__ __noinline__ uint32_t block_touch_mask(float4 a0, float4 a1, float ti
 }
 
 template <int FORMAT, int S>
-__global__ void __launch_bounds__(128 * S * S, S == 1 ? 10 : 2)
+__global__ void __launch_bounds__(128 * S * S, S == 1 ? 8 : 2)
 k_blend2(const uint2 *__restrict__ ranges, const unsigned long long *__restrict__ list, const SplatRecord *__restrict__ rec, int tiles_x,
-         int tiles_y, int coarse_x, uint32_t rank, uint32_t world, int width, int height, int flip_y, void *__restrict__ frame) {
+         int tiles_y, int coarse_x, uint32_t rank, uint32_t world, int width, int height, int flip_y, void *__restrict__ frame, const uint32_t *__restrict__ tile_order) {
     pdl_enter();
     constexpr int THREADS = 128 * S * S, WARPS = THREADS / 32, NB = 2 * S, TILE = 16 * S, BATCH = 4 * THREADS;
-    __shared__ float4 s_rec[THREADS][3];
+    __shared__ float4 s_rec[THREADS + 1][3];    // [THREADS] = the null record (alpha 0) that pairs with an odd tail
     __shared__ uint32_t s_ids[BATCH];
     __shared__ uint32_t s_cnt[4 * WARPS + 1];   // [round][warp] survivors of the filter -> exclusive offsets; last = total
     __shared__ uint8_t s_list[WARPS][THREADS];  // [block][staging warp * 32 + k] indices of the staged records that reach the block, in order
     __shared__ uint8_t s_nlist[WARPS][WARPS];   // [block][staging warp] how many
     static_assert(THREADS <= 256 || sizeof(uint8_t) == 1, "");
-    const uint32_t coarse = blockIdx.x / kFinePerCoarse, sub = blockIdx.x % kFinePerCoarse;
+    const uint32_t coarse = tile_order[blockIdx.x / kFinePerCoarse], sub = blockIdx.x % kFinePerCoarse;
     const int ccx = (int)(coarse % (uint32_t)coarse_x), ccy = (int)(coarse / (uint32_t)coarse_x);
     const int tx = ccx * kCoarseW + (int)(sub & (kCoarseW - 1)), ty = ccy * kCoarseH + (int)(sub >> kCoarseShiftX);
     if (tx >= tiles_x || ty >= tiles_y) return;
@@ -1089,6 +1098,7 @@ k_blend2(const uint2 *__restrict__ ranges, const unsigned long long *__restrict_
     bool wdone = !__any_sync(0xffffffffu, fmaxf(T0, T1) >= kTransmittanceCutoff);
     const uint2 rg = ranges[coarse];
     const uint32_t lt = lanemask_lt();
+    if (threadIdx.x < 3) s_rec[THREADS][threadIdx.x] = (threadIdx.x == 1) ? make_float4(0.f, 0.f, 0.f, __int_as_float(0xff800000)) : make_float4(0.f, 0.f, 0.f, 0.f);   // log2(alpha) = -inf
     for (uint32_t base = rg.x; base < rg.y; base += BATCH) {
         if (__syncthreads_and(wdone)) break;
         // ---- filter 4 x THREADS list entries by this tile's mask bit; order-preserving compaction (order: round, warp, lane) ------
@@ -1156,20 +1166,34 @@ k_blend2(const uint2 *__restrict__ ranges, const unsigned long long *__restrict_
                 for (int sw = 0; sw < WARPS && !wdone; ++sw) {
                     const int cnt = s_nlist[warp][sw];
                     const uint8_t *lst = &s_list[warp][sw * 32];
+                    const int jbase = (THREADS > 256 ? (sw & ~7) * 32 : 0);      // 8-bit index inside the group of 8 staging warps
+                    // Two records per iteration: their quad coordinates and exponentials are independent, only the transmittance chain is
+                    // serial.  The blend's duration is set by the longest per-warp chain (the densest block), not by issue slots, so the
+                    // instruction-level parallelism matters more than the instruction count.  An odd tail pairs with the null record.
 #pragma unroll 1
-                    for (int k = 0; k < cnt; ++k) {
-                        const int jj = (THREADS > 256 ? (sw & ~7) * 32 : 0) + lst[k];      // 8-bit index inside the group of 8 staging warps
-                        const float4 A = s_rec[jj][0], B = s_rec[jj][1], C = s_rec[jj][2];
-                        const float u = fmaf(pxc, A.z, fmaf(pyc, A.w, A.x)), w = fmaf(pxc, B.x, fmaf(pyc, B.y, A.y));
-                        const float q0 = fmaf(w, w, u * u);
-                        const float q1 = q0 + fmaf(2.0f, fmaf(u, A.w, w * B.y), B.z);        // one pixel up: (u + g1y)^2 + (w + g2y)^2
+                    for (int k = 0; k < cnt; k += 2) {
+                        const int ja = jbase + lst[k];
+                        const int jb = (k + 1 < cnt) ? jbase + lst[k + 1] : THREADS;
+                        const float4 A = s_rec[ja][0], B = s_rec[ja][1], C = s_rec[ja][2];
+                        const float4 D = s_rec[jb][0], E = s_rec[jb][1], F = s_rec[jb][2];
+                        const float ua = fmaf(pxc, A.z, fmaf(pyc, A.w, A.x)), wa = fmaf(pxc, B.x, fmaf(pyc, B.y, A.y));
+                        const float ub = fmaf(pxc, D.z, fmaf(pyc, D.w, D.x)), wb = fmaf(pxc, E.x, fmaf(pyc, E.y, D.y));
+                        const float qa0 = fmaf(wa, wa, ua * ua), qb0 = fmaf(wb, wb, ub * ub);
+                        const float qa1 = qa0 + fmaf(2.0f, fmaf(ua, A.w, wa * B.y), B.z);      // one pixel up: (u + g1y)^2 + (w + g2y)^2
+                        const float qb1 = qb0 + fmaf(2.0f, fmaf(ub, D.w, wb * E.y), E.z);
                         // exp(-0.5 A) * vColor.a with A = 8 q, zero outside the quad's inscribed disc (branch-free)
-                        const float e0 = (q0 <= 1.0f) ? ex2_approx(fmaf(q0, -5.770780163555854f, B.w)) : 0.0f;
-                        const float e1 = (q1 <= 1.0f) ? ex2_approx(fmaf(q1, -5.770780163555854f, B.w)) : 0.0f;
-                        const float w0 = T0 * e0, w1 = T1 * e1;
+                        const float ea0 = (qa0 <= 1.0f) ? ex2_approx(fmaf(qa0, -5.770780163555854f, B.w)) : 0.0f;
+                        const float ea1 = (qa1 <= 1.0f) ? ex2_approx(fmaf(qa1, -5.770780163555854f, B.w)) : 0.0f;
+                        const float eb0 = (qb0 <= 1.0f) ? ex2_approx(fmaf(qb0, -5.770780163555854f, E.w)) : 0.0f;
+                        const float eb1 = (qb1 <= 1.0f) ? ex2_approx(fmaf(qb1, -5.770780163555854f, E.w)) : 0.0f;
+                        float w0 = T0 * ea0, w1 = T1 * ea1;
                         r0 = fmaf(w0, C.x, r0); g0 = fmaf(w0, C.y, g0); b0 = fmaf(w0, C.z, b0);
                         r1 = fmaf(w1, C.x, r1); g1 = fmaf(w1, C.y, g1); b1 = fmaf(w1, C.z, b1);
                         T0 -= w0; T1 -= w1;                                                // T *= (1 - alpha)
+                        w0 = T0 * eb0; w1 = T1 * eb1;
+                        r0 = fmaf(w0, F.x, r0); g0 = fmaf(w0, F.y, g0); b0 = fmaf(w0, F.z, b0);
+                        r1 = fmaf(w1, F.x, r1); g1 = fmaf(w1, F.y, g1); b1 = fmaf(w1, F.z, b1);
+                        T0 -= w0; T1 -= w1;
                         if (!__any_sync(0xffffffffu, fmaxf(T0, T1) >= kTransmittanceCutoff)) { wdone = true; break; }
                     }
                 }
@@ -1254,6 +1278,7 @@ struct RasterState {
     RBuf<uint32_t> tile_hist;   // radix tile histograms
     RBuf<uint32_t> bin_hist;    // binning v2: [coarse tile][chunk] instance counts -> offsets
     RBuf<ushort4> rect_by_rank; // binning v2: the rects gathered in draw-rank order by k_bin_count
+    RBuf<uint32_t> tile_order;  // blend schedule: coarse tiles by list length, longest first
     RBuf<uint32_t> bin_totals;  // binning v2: instances per coarse tile (1024 words, zeroed by k_raster_init)
     uint32_t bin_stride = 0;
     int bin_cfg = 0;
@@ -1308,6 +1333,7 @@ static int raster_init(RasterState &rs, const gs_config &c, int sm_count) {
         for (int i = 0; i < 2; ++i) { RCU(rs.ikeys[i].ensure(rs.instance_capacity)); RCU(rs.ivals[i].ensure(rs.instance_capacity)); }
         RCU(rs.list.ensure(rs.instance_capacity));
         RCU(rs.ranges.ensure(65536));
+        RCU(rs.tile_order.ensure(65536));
         RCU(rs.frame.ensure((size_t)c.max_width * (c.max_height + kTile) * 16));
         RCU(rs.tile_hist.ensure(radix_tile_hist_words(rs.instance_capacity, 2, &rs.hist_stride)));
         if (const char *v = getenv("GS_BIN")) rs.bin_version = atoi(v);
@@ -1329,7 +1355,7 @@ static int raster_init(RasterState &rs, const gs_config &c, int sm_count) {
 static void raster_release(RasterState &rs) {
     rs.cc.release(); rs.cov.release(); rs.sh.release(); rs.scene_idx.release(); rs.records.release(); rs.rects.release();
     rs.block_sums.release(); rs.warp_sums.release(); rs.super_sums.release(); rs.ikeys[0].release(); rs.ikeys[1].release(); rs.ivals[0].release(); rs.ivals[1].release();
-    rs.list.release(); rs.ranges.release(); rs.rctl.release(); rs.sctl.release(); rs.tile_hist.release(); rs.bin_hist.release(); rs.bin_totals.release(); rs.rect_by_rank.release();
+    rs.list.release(); rs.ranges.release(); rs.rctl.release(); rs.sctl.release(); rs.tile_hist.release(); rs.bin_hist.release(); rs.bin_totals.release(); rs.rect_by_rank.release(); rs.tile_order.release();
     rs.dyn.release(); rs.projp.release(); rs.frame.release(); rs.frame_alt.release(); rs.peer_sync_local.release(); rs.exported.release();
 }
 
@@ -1440,7 +1466,7 @@ static int raster_render(RasterState &rs, const gs_config &c, const gs_uniforms 
     while ((1u << tile_bits) < std::max(ncoarse, 2u)) ++tile_bits;
     const PassPlan pl = make_plan_bits(tile_bits);
     if (phases & 1) {
-        gs_launch(k_raster_init, 8, 256, 0, st, rs.rctl.p, rs.sctl.p, rs.ranges.p, ncoarse, rs.super_sums.p, 2 * rs.super_stride, rs.bin_totals.p);
+        gs_launch(k_raster_init, 8, 256, 0, st, rs.rctl.p, rs.sctl.p, rs.ranges.p, ncoarse, rs.super_sums.p, 2 * rs.super_stride, rs.bin_totals.p, rs.tile_order.p);
         ++launches;
         prof.mark("k_raster_init", st);
         // rank 0 frees its frame buffer for the peers' stores right at the START of the frame (everything that consumed the previous
@@ -1463,7 +1489,7 @@ static int raster_render(RasterState &rs, const gs_config &c, const gs_uniforms 
         if (rs.bin_cfg == 0) GS_BIN_COUNT(0); else GS_BIN_COUNT(1);
         ++launches;
         prof.mark("k_bin_count", st);
-        gs_launch(k_bin_scan, ncoarse, 1024, 0, st, rs.bin_hist.p, rs.bin_stride, (uint32_t)kBinRanks, p.render_count, order_count_dev, rs.bin_totals.p, ncoarse, rs.ranges.p, rs.rctl.p);
+        gs_launch(k_bin_scan, ncoarse, 1024, 0, st, rs.bin_hist.p, rs.bin_stride, (uint32_t)kBinRanks, p.render_count, order_count_dev, rs.bin_totals.p, ncoarse, rs.ranges.p, rs.rctl.p, rs.tile_order.p);
         ++launches;
         prof.mark("k_bin_scan", st);
         if (rs.bin_cfg == 0) GS_BIN_PLACE(0); else GS_BIN_PLACE(1);
@@ -1503,14 +1529,14 @@ static int raster_render(RasterState &rs, const gs_config &c, const gs_uniforms 
         }
         const uint32_t grid = ncoarse * kFinePerCoarse;
         if (rs.blend_version >= 2 || tshift != kTileShift) {
-#define GS_BLEND2(FMT, SC) gs_launch(k_blend2<FMT, SC>, grid, 128 * SC * SC, 0, st, rs.ranges.p, rs.list.p, rs.records.p, tiles_x, tiles_y, coarse_x, rank, world, (int)p.width, (int)p.height, p.flip_y, target)
+#define GS_BLEND2(FMT, SC) gs_launch(k_blend2<FMT, SC>, grid, 128 * SC * SC, 0, st, rs.ranges.p, rs.list.p, rs.records.p, tiles_x, tiles_y, coarse_x, rank, world, (int)p.width, (int)p.height, p.flip_y, target, rs.tile_order.p)
             if (tshift == kTileShift) { if (p.frame_format == GS_FRAME_RGBA8) GS_BLEND2(GS_FRAME_RGBA8, 1); else GS_BLEND2(GS_FRAME_RGBA32F, 1); }
             else { if (p.frame_format == GS_FRAME_RGBA8) GS_BLEND2(GS_FRAME_RGBA8, 2); else GS_BLEND2(GS_FRAME_RGBA32F, 2); }
 #undef GS_BLEND2
         } else if (p.frame_format == GS_FRAME_RGBA8)
-            gs_launch(k_blend<GS_FRAME_RGBA8>, grid, kBlendThreads, 0, st, rs.ranges.p, rs.list.p, rs.records.p, tiles_x, tiles_y, coarse_x, rank, world, (int)p.width, (int)p.height, p.flip_y, target);
+            gs_launch(k_blend<GS_FRAME_RGBA8>, grid, kBlendThreads, 0, st, rs.ranges.p, rs.list.p, rs.records.p, tiles_x, tiles_y, coarse_x, rank, world, (int)p.width, (int)p.height, p.flip_y, target, rs.tile_order.p);
         else
-            gs_launch(k_blend<GS_FRAME_RGBA32F>, grid, kBlendThreads, 0, st, rs.ranges.p, rs.list.p, rs.records.p, tiles_x, tiles_y, coarse_x, rank, world, (int)p.width, (int)p.height, p.flip_y, target);
+            gs_launch(k_blend<GS_FRAME_RGBA32F>, grid, kBlendThreads, 0, st, rs.ranges.p, rs.list.p, rs.records.p, tiles_x, tiles_y, coarse_x, rank, world, (int)p.width, (int)p.height, p.flip_y, target, rs.tile_order.p);
         ++launches;
         prof.mark("k_blend", st);
         if (peer_mode && rs.peer_attached) { k_peer_signal<<<1, 1, 0, st>>>(rs.peer_sync); ++launches; }

@@ -437,6 +437,14 @@ __device__ __forceinline__ uint32_t coarse_instances(ushort4 r, const OwnMask &o
     return n;
 }
 
+// Does a fine-tile rect reach a coarse tile of this rank?  The coarse tiles of a rect cover EVERY diagonal index cx + cy in
+// [cx0 + cy0, cx1 + cy1], and ownership depends on the diagonal only: one window of the 128-bit ownership mask, no loop.
+__device__ __forceinline__ bool rect_touches_owned(ushort4 r, const OwnMask &own) {
+    if (r.z < r.x || r.w < r.y) return false;
+    const int d0 = (r.x >> kCoarseShiftX) + (r.y >> kCoarseShiftY), d1 = (r.z >> kCoarseShiftX) + (r.w >> kCoarseShiftY);
+    return own_count_range(own, d0, min(d1, 127)) != 0u;
+}
+
 constexpr int kBinThreads = 256;
 constexpr int kBinItems = 2;
 constexpr int kBinTile = kBinThreads * kBinItems;   // draw ranks per CTA
@@ -820,7 +828,7 @@ k_subset_count(const uint32_t *__restrict__ indexes, uint32_t count, const ushor
 #pragma unroll
     for (int k = 0; k < kBinItems; ++k) {
         const uint32_t i = run + (uint32_t)k * 32;
-        if (i < count) mine += coarse_instances(rects[indexes ? ld_nc_u32(indexes + i) : i], own, true) ? 1u : 0u;
+        if (i < count) mine += rect_touches_owned(rects[indexes ? ld_nc_u32(indexes + i) : i], own) ? 1u : 0u;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
@@ -859,7 +867,7 @@ k_subset_emit(const uint32_t *__restrict__ indexes, uint32_t count, const ushort
         bool keep = false;
         if (i < count) {
             g = indexes ? ld_nc_u32(indexes + i) : i;
-            keep = coarse_instances(rects[g], own, true) != 0u;
+            keep = rect_touches_owned(rects[g], own);
         }
         const uint32_t bal = __ballot_sync(0xffffffffu, keep);
         if (keep) {

@@ -71,3 +71,26 @@ def test_product_does_not_import_oracle():
         if p.suffix in (".py", ".cu", ".cuh", ".h") and p.is_file():
             t = p.read_text()
             assert "import oracle" not in t and "from oracle" not in t and "oracle/" not in t.replace("oracle/_ref", ""), p
+
+
+def test_napi_addon_type_checks_and_binds_every_entry_point():
+    """js/gsplat_b200_addon.cc (the Node.js side of the drop-in; Node itself is absent from this image): compiles cleanly against the
+    declarations of the Node-API it uses (js/test/node_api_stub.h) with -Wall -Wextra, calls every GS_API symbol of the header, and
+    exports one JS function per symbol; the JS shims only call functions the addon exports."""
+    import subprocess
+    res = subprocess.run(["/usr/bin/g++", "-std=c++17", "-fsyntax-only", "-Wall", "-Wextra", "-Werror", "-DGS_NAPI_STUB", str(ROOT / "js" / "gsplat_b200_addon.cc")],
+                         capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    src = (ROOT / "js" / "gsplat_b200_addon.cc").read_text()
+    for sym in declared_symbols():
+        assert re.search(r"\b" + sym + r"\s*\(", src), f"{sym} is not called by the addon"
+    exported = set(re.findall(r'EXPORT\("(\w+)"', src))
+    assert len(exported) >= len(declared_symbols())
+    for shim in ("SortWorkerB200.js", "SplatMeshB200.js"):
+        used = set(re.findall(r"\baddon\.(\w+)\(", (ROOT / "js" / shim).read_text()))
+        assert used and used <= exported, (shim, used - exported)
+    # the worker shim speaks the whole protocol of src/worker/SortWorker.js
+    w = (ROOT / "js" / "SortWorkerB200.js").read_text()
+    for key in ("sortSetupPhase1Complete", "indexesToSortBuffer", "sortedIndexesBuffer", "precomputedDistancesBuffer", "transformsBuffer", "sortDone",
+                "sortCanceled", "splatSortCount", "splatRenderCount", "usePrecomputedDistances", "precomputedDistances", "transforms", "sceneIndexes"):
+        assert key in w, key

@@ -1049,6 +1049,40 @@ k_blend(const uint2 *__restrict__ ranges, const unsigned long long *__restrict__
 //   * opacity is folded into the exponent (ex2(q * k + log2 a)), one multiply less per pixel.
 // Same arithmetic otherwise: q = u^2 + w^2 from the inverse quad map, alpha = exp(-4 q) a for q <= 1 (A = 8 q <= 8), front to back.
 
+// ---- 1-D bulk async copy (TMA unit) global -> shared with an mbarrier, used to prefetch the next batch of a coarse-tile list while the
+// current batch is being composited (cp.async.bulk needs 16-byte aligned source / destination / size).
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// bounded wait: a protocol error must show up as a wrong picture in a test, never as a hung GPU
+__device__ __forceinline__ bool mbar_wait(unsigned long long *bar, uint32_t parity) {
+    for (int spin = 0; spin < (1 << 22); ++spin) {
+        uint32_t done;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (done) return true;
+    }
+    return false;
+}
+
+// ---- packed 2 x f32 arithmetic (sm_100: FFMA2 / FMUL2, one issue slot for two IEEE fp32 results; scalar operands broadcast for free)
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ f32x2 bcast2(float v) { return pack2(v, v); }
+__device__ __forceinline__ float lo2(f32x2 v) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return a; }
+__device__ __forceinline__ float hi2(f32x2 v) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return b; }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+
 // Which of a tile's 8x8-px blocks can hold a pixel the splat covers: exact minimum of q over each block's rectangle of pixel
 // centres (ellipse_mask.h), only for the blocks the ellipse's AABB reaches.  a0 = cx, cy, g1x, g1y; a1 = g2x, g2y, half2(hx, hy), alpha.
 // NB = blocks per tile row (2 or 4).  Not inlined: the caller's composite loop is register-bound and this runs once per staged record.
@@ -1079,15 +1113,18 @@ __device__ __noinline__ uint32_t block_touch_mask(float4 a0, float4 a1, float ti
     return bm;
 }
 
-template <int FORMAT, int S>
+template <int FORMAT, int S, int ROUNDS, bool TMA>
 __global__ void __launch_bounds__(128 * S * S, S == 1 ? 8 : 2)
 k_blend2(const uint2 *__restrict__ ranges, const unsigned long long *__restrict__ list, const SplatRecord *__restrict__ rec, int tiles_x,
          int tiles_y, int coarse_x, uint32_t rank, uint32_t world, int width, int height, int flip_y, void *__restrict__ frame, const uint32_t *__restrict__ tile_order) {
     pdl_enter();
-    constexpr int THREADS = 128 * S * S, WARPS = THREADS / 32, NB = 2 * S, TILE = 16 * S, BATCH = 4 * THREADS;
+    constexpr int THREADS = 128 * S * S, WARPS = THREADS / 32, NB = 2 * S, TILE = 16 * S;
+    constexpr int BATCH = ROUNDS * THREADS;      // list entries per batch
     __shared__ float4 s_rec[THREADS + 1][3];    // [THREADS] = the null record (alpha 0) that pairs with an odd tail
     __shared__ uint32_t s_ids[BATCH];
-    __shared__ uint32_t s_cnt[4 * WARPS + 1];   // [round][warp] survivors of the filter -> exclusive offsets; last = total
+    __shared__ uint32_t s_cnt[ROUNDS * WARPS + 1];   // [round][warp] survivors of the filter -> exclusive offsets; last = total
+    __shared__ __align__(16) unsigned long long s_chunk[TMA ? 2 : 1][TMA ? BATCH + 2 : 2];   // list batches, double buffered, filled by bulk async copies (TMA)
+    __shared__ __align__(8) unsigned long long s_mbar[2];
     __shared__ uint8_t s_list[WARPS][THREADS];  // [block][staging warp * 32 + k] indices of the staged records that reach the block, in order
     __shared__ uint8_t s_nlist[WARPS][WARPS];   // [block][staging warp] how many
     static_assert(THREADS <= 256 || sizeof(uint8_t) == 1, "");
@@ -1101,23 +1138,48 @@ k_blend2(const uint2 *__restrict__ ranges, const unsigned long long *__restrict_
     const float pxc = (float)x + 0.5f, pyc = (float)y0 + 0.5f;
     const float tile_x0 = (float)(tx * TILE) + 0.5f, tile_y0 = (float)(ty * TILE) + 0.5f;    // first pixel centre of the tile
     // pixels outside the frame start saturated so that they never keep a warp alive
-    float T0 = (x < width && y0 < height) ? 1.0f : 0.0f, T1 = (x < width && y0 + 1 < height) ? 1.0f : 0.0f;
-    float r0 = 0.f, g0 = 0.f, b0 = 0.f, r1 = 0.f, g1 = 0.f, b1 = 0.f;
-    bool wdone = !__any_sync(0xffffffffu, fmaxf(T0, T1) >= kTransmittanceCutoff);
+    f32x2 T = pack2((x < width && y0 < height) ? 1.0f : 0.0f, (x < width && y0 + 1 < height) ? 1.0f : 0.0f);
+    f32x2 Rr = pack2(0.f, 0.f), Gg = Rr, Bb = Rr;
+    const f32x2 PY = pack2(pyc, pyc + 1.0f);
+    bool wdone = !__any_sync(0xffffffffu, fmaxf(lo2(T), hi2(T)) >= kTransmittanceCutoff);
     const uint2 rg = ranges[coarse];
     const uint32_t lt = lanemask_lt();
     if (threadIdx.x < 3) s_rec[THREADS][threadIdx.x] = (threadIdx.x == 1) ? make_float4(0.f, 0.f, 0.f, __int_as_float(0xff800000)) : make_float4(0.f, 0.f, 0.f, 0.f);   // log2(alpha) = -inf
-    for (uint32_t base = rg.x; base < rg.y; base += BATCH) {
+    // The tile's list is consumed in batches of BATCH entries.  Batch b+1 is fetched into the other half of s_chunk by ONE bulk async
+    // copy (the TMA unit; completion on an mbarrier) while batch b is filtered, staged and composited, so a dense tile's critical path
+    // never waits for list loads.  Copies start at an even entry (16-byte alignment): `skip` = 0 or 1 leading entry to ignore.
+    auto issue = [&](uint32_t b) {        // thread 0 only
+        const uint32_t start = rg.x + b * (uint32_t)BATCH, cnt = min((uint32_t)BATCH, rg.y - start);
+        const uint32_t a0 = start & ~1u, a1 = (start + cnt + 1u) & ~1u, bytes = (a1 - a0) * 8u;
+        fence_proxy_async_smem();
+        mbar_expect_tx(&s_mbar[b & 1u], bytes);
+        bulk_g2s(&s_chunk[b & 1u][0], list + a0, bytes, &s_mbar[b & 1u]);
+    };
+    const uint32_t nbatch = (rg.y - rg.x + BATCH - 1) / BATCH;
+    if (TMA && threadIdx.x == 0) { mbar_init(&s_mbar[0], 1); mbar_init(&s_mbar[1], 1); mbar_fence_init(); }
+    __syncthreads();
+    if (TMA && threadIdx.x == 0 && nbatch) issue(0);
+    uint32_t pending = (TMA && nbatch) ? 1u : 0u;      // batches issued so far (uniform)
+    bool copy_ok = true;
+    for (uint32_t b = 0; b < nbatch; ++b) {
+        const uint32_t base = rg.x + b * (uint32_t)BATCH;
         if (__syncthreads_and(wdone)) break;
+        const unsigned long long *chunk = list + base;
+        if (TMA) {
+            if (threadIdx.x == 0 && b + 1 < nbatch) issue(b + 1);      // its buffer was last read two barriers ago
+            if (b + 1 < nbatch) pending = b + 2;
+            copy_ok = mbar_wait(&s_mbar[b & 1u], (b >> 1) & 1u) && copy_ok;
+            chunk = &s_chunk[b & 1u][base & 1u];
+        }
         // ---- filter 4 x THREADS list entries by this tile's mask bit; order-preserving compaction (order: round, warp, lane) ------
-        uint32_t ids[4], bal[4];
+        uint32_t ids[ROUNDS], bal[ROUNDS];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < ROUNDS; ++k) {
             const uint32_t i = base + (uint32_t)k * THREADS + threadIdx.x;
             bool hit = false;
             ids[k] = 0;
             if (i < rg.y) {
-                const unsigned long long e = __ldg(list + i);
+                const unsigned long long e = TMA ? chunk[(uint32_t)k * THREADS + threadIdx.x] : __ldg(chunk + (uint32_t)k * THREADS + threadIdx.x);
                 hit = ((uint32_t)(e >> 32) >> sub) & 1u;
                 ids[k] = (uint32_t)e;
             }
@@ -1128,18 +1190,18 @@ k_blend2(const uint2 *__restrict__ ranges, const unsigned long long *__restrict_
         if (warp == 0) {      // exclusive scan of the 4 * WARPS counts
             uint32_t run = 0;
 #pragma unroll
-            for (int c = 0; c < 4 * WARPS; c += 32) {
-                const uint32_t v = (c + lane < 4 * WARPS) ? s_cnt[c + lane] : 0u;
+            for (int c = 0; c < ROUNDS * WARPS; c += 32) {
+                const uint32_t v = (c + lane < ROUNDS * WARPS) ? s_cnt[c + lane] : 0u;
                 const uint32_t inc = warp_inclusive_scan(v);
-                if (c + lane < 4 * WARPS) s_cnt[c + lane] = run + inc - v;
+                if (c + lane < ROUNDS * WARPS) s_cnt[c + lane] = run + inc - v;
                 run += __shfl_sync(0xffffffffu, inc, 31);
             }
-            if (lane == 0) s_cnt[4 * WARPS] = run;
+            if (lane == 0) s_cnt[ROUNDS * WARPS] = run;
         }
         __syncthreads();
-        const uint32_t nsurv = s_cnt[4 * WARPS];
+        const uint32_t nsurv = s_cnt[ROUNDS * WARPS];
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
+        for (int k = 0; k < ROUNDS; ++k)
             if ((bal[k] >> lane) & 1u) s_ids[s_cnt[k * WARPS + warp] + __popc(bal[k] & lt)] = ids[k];
         __syncthreads();
         // ---- stage up to THREADS survivors at a time, then every warp composites the ones that reach its block -------------------
@@ -1184,31 +1246,39 @@ k_blend2(const uint2 *__restrict__ ranges, const unsigned long long *__restrict_
                         const int jb = (k + 1 < cnt) ? jbase + lst[k + 1] : THREADS;
                         const float4 A = s_rec[ja][0], B = s_rec[ja][1], C = s_rec[ja][2];
                         const float4 D = s_rec[jb][0], E = s_rec[jb][1], F = s_rec[jb][2];
-                        const float ua = fmaf(pxc, A.z, fmaf(pyc, A.w, A.x)), wa = fmaf(pxc, B.x, fmaf(pyc, B.y, A.y));
-                        const float ub = fmaf(pxc, D.z, fmaf(pyc, D.w, D.x)), wb = fmaf(pxc, E.x, fmaf(pyc, E.y, D.y));
-                        const float qa0 = fmaf(wa, wa, ua * ua), qb0 = fmaf(wb, wb, ub * ub);
-                        const float qa1 = qa0 + fmaf(2.0f, fmaf(ua, A.w, wa * B.y), B.z);      // one pixel up: (u + g1y)^2 + (w + g2y)^2
-                        const float qb1 = qb0 + fmaf(2.0f, fmaf(ub, D.w, wb * E.y), E.z);
-                        // exp(-0.5 A) * vColor.a with A = 8 q, zero outside the quad's inscribed disc (branch-free)
-                        const float ea0 = (qa0 <= 1.0f) ? ex2_approx(fmaf(qa0, -5.770780163555854f, B.w)) : 0.0f;
-                        const float ea1 = (qa1 <= 1.0f) ? ex2_approx(fmaf(qa1, -5.770780163555854f, B.w)) : 0.0f;
-                        const float eb0 = (qb0 <= 1.0f) ? ex2_approx(fmaf(qb0, -5.770780163555854f, E.w)) : 0.0f;
-                        const float eb1 = (qb1 <= 1.0f) ? ex2_approx(fmaf(qb1, -5.770780163555854f, E.w)) : 0.0f;
-                        float w0 = T0 * ea0, w1 = T1 * ea1;
-                        r0 = fmaf(w0, C.x, r0); g0 = fmaf(w0, C.y, g0); b0 = fmaf(w0, C.z, b0);
-                        r1 = fmaf(w1, C.x, r1); g1 = fmaf(w1, C.y, g1); b1 = fmaf(w1, C.z, b1);
-                        T0 -= w0; T1 -= w1;                                                // T *= (1 - alpha)
-                        w0 = T0 * eb0; w1 = T1 * eb1;
-                        r0 = fmaf(w0, F.x, r0); g0 = fmaf(w0, F.y, g0); b0 = fmaf(w0, F.z, b0);
-                        r1 = fmaf(w1, F.x, r1); g1 = fmaf(w1, F.y, g1); b1 = fmaf(w1, F.z, b1);
-                        T0 -= w0; T1 -= w1;
-                        if (!__any_sync(0xffffffffu, fmaxf(T0, T1) >= kTransmittanceCutoff)) { wdone = true; break; }
+                        // the lane's two pixels ride in the halves of packed f32x2 registers (FFMA2 / FMUL2: one issue slot for both);
+                        // per-record scalars enter as broadcast operands
+                        const float tua = fmaf(pxc, A.z, A.x), twa = fmaf(pxc, B.x, A.y);
+                        const float tub = fmaf(pxc, D.z, D.x), twb = fmaf(pxc, E.x, D.y);
+                        const f32x2 Ua = fma2(PY, bcast2(A.w), bcast2(tua)), Wa = fma2(PY, bcast2(B.y), bcast2(twa));
+                        const f32x2 Ub = fma2(PY, bcast2(D.w), bcast2(tub)), Wb = fma2(PY, bcast2(E.y), bcast2(twb));
+                        const f32x2 Qa = fma2(Wa, Wa, mul2(Ua, Ua)), Qb = fma2(Wb, Wb, mul2(Ub, Ub));
+                        // exp(-0.5 A) * vColor.a with A = 8 q, zero outside the quad's inscribed disc
+                        const f32x2 Xa = fma2(Qa, bcast2(-5.770780163555854f), bcast2(B.w)), Xb = fma2(Qb, bcast2(-5.770780163555854f), bcast2(E.w));
+                        const float ea0 = (lo2(Qa) <= 1.0f) ? ex2_approx(lo2(Xa)) : 0.0f, ea1 = (hi2(Qa) <= 1.0f) ? ex2_approx(hi2(Xa)) : 0.0f;
+                        const float eb0 = (lo2(Qb) <= 1.0f) ? ex2_approx(lo2(Xb)) : 0.0f, eb1 = (hi2(Qb) <= 1.0f) ? ex2_approx(hi2(Xb)) : 0.0f;
+                        f32x2 wgt = mul2(T, pack2(ea0, ea1));
+                        Rr = fma2(wgt, bcast2(C.x), Rr); Gg = fma2(wgt, bcast2(C.y), Gg); Bb = fma2(wgt, bcast2(C.z), Bb);
+                        T = fma2(wgt, bcast2(-1.0f), T);                                   // T *= (1 - alpha)
+                        wgt = mul2(T, pack2(eb0, eb1));
+                        Rr = fma2(wgt, bcast2(F.x), Rr); Gg = fma2(wgt, bcast2(F.y), Gg); Bb = fma2(wgt, bcast2(F.z), Bb);
+                        T = fma2(wgt, bcast2(-1.0f), T);
+                        if (!__any_sync(0xffffffffu, fmaxf(lo2(T), hi2(T)) >= kTransmittanceCutoff)) { wdone = true; break; }
                     }
                 }
             }
-            __syncthreads();
+            if (__syncthreads_and(wdone)) break;      // every pixel of the tile is saturated: the rest of the batch cannot change it
         }
     }
+    // a CTA must not retire while a bulk copy into its shared memory is in flight: wait for the last batch issued (if it was not consumed)
+    if (TMA) {
+        __syncthreads();
+        const uint32_t last = pending ? pending - 1u : 0u;
+        if (pending && threadIdx.x == 0) copy_ok = mbar_wait(&s_mbar[last & 1u], (last >> 1) & 1u) && copy_ok;
+        // (a batch that WAS consumed has completed its phase already: the wait returns at once)
+    }
+    float T0 = lo2(T), T1 = hi2(T), r0 = lo2(Rr), r1 = hi2(Rr), g0 = lo2(Gg), g1 = hi2(Gg), b0 = lo2(Bb), b1 = hi2(Bb);
+    if (!copy_ok) { T0 = T1 = 0.5f; r0 = r1 = 1.0f; g0 = g1 = 0.0f; b0 = b1 = 1.0f; }      // protocol failure: paint the pixels magenta so that every comparison fails
     if (x < width) {
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
@@ -1291,6 +1361,7 @@ struct RasterState {
     uint32_t bin_stride = 0;
     int bin_cfg = 0;
     int bin_version = 2, blend_version = 2;   // GS_BIN / GS_BLEND = 1 selects the round-1 kernels (A/B measurements)
+    int blend_tma = 0, blend_rounds = 4;      // GS_BLEND_TMA = 1: bulk-async list prefetch; GS_BLEND_ROUNDS = 2 / 4 (16-px tiles)
     RBuf<DynamicUniforms> dyn;
     RBuf<ProjParams> projp;     // per-frame projection parameters (device copy read by k_project)
     RBuf<unsigned char> frame;
@@ -1346,6 +1417,8 @@ static int raster_init(RasterState &rs, const gs_config &c, int sm_count) {
         RCU(rs.tile_hist.ensure(radix_tile_hist_words(rs.instance_capacity, 2, &rs.hist_stride)));
         if (const char *v = getenv("GS_BIN")) rs.bin_version = atoi(v);
         if (const char *v = getenv("GS_BLEND")) rs.blend_version = atoi(v);
+        if (const char *v = getenv("GS_BLEND_TMA")) rs.blend_tma = atoi(v);
+        if (const char *v = getenv("GS_BLEND_ROUNDS")) rs.blend_rounds = atoi(v);
         if (const char *v = getenv("GS_BINCFG")) rs.bin_cfg = atoi(v);
         {   // binning v2: one column of chunk counts per coarse tile (2048 draw ranks per chunk in both configurations)
             const size_t coarse = (size_t)((c.max_width + kTile * kCoarseW - 1) / (kTile * kCoarseW)) * ((c.max_height + kTile * kCoarseH - 1) / (kTile * kCoarseH));
@@ -1537,9 +1610,15 @@ static int raster_render(RasterState &rs, const gs_config &c, const gs_uniforms 
         }
         const uint32_t grid = ncoarse * kFinePerCoarse;
         if (rs.blend_version >= 2 || tshift != kTileShift) {
-#define GS_BLEND2(FMT, SC) gs_launch(k_blend2<FMT, SC>, grid, 128 * SC * SC, 0, st, rs.ranges.p, rs.list.p, rs.records.p, tiles_x, tiles_y, coarse_x, rank, world, (int)p.width, (int)p.height, p.flip_y, target, rs.tile_order.p)
-            if (tshift == kTileShift) { if (p.frame_format == GS_FRAME_RGBA8) GS_BLEND2(GS_FRAME_RGBA8, 1); else GS_BLEND2(GS_FRAME_RGBA32F, 1); }
-            else { if (p.frame_format == GS_FRAME_RGBA8) GS_BLEND2(GS_FRAME_RGBA8, 2); else GS_BLEND2(GS_FRAME_RGBA32F, 2); }
+#define GS_BLEND2(FMT, SC, RD, TM) gs_launch(k_blend2<FMT, SC, RD, TM>, grid, 128 * SC * SC, 0, st, rs.ranges.p, rs.list.p, rs.records.p, tiles_x, tiles_y, coarse_x, rank, world, (int)p.width, (int)p.height, p.flip_y, target, rs.tile_order.p)
+#define GS_BLEND2F(SC, RD, TM) do { if (p.frame_format == GS_FRAME_RGBA8) GS_BLEND2(GS_FRAME_RGBA8, SC, RD, TM); else GS_BLEND2(GS_FRAME_RGBA32F, SC, RD, TM); } while (0)
+            // list batches: plain loads; GS_BLEND_TMA=1 prefetches them with bulk async copies instead (measured: no gain)
+            const bool tma = rs.blend_tma > 0;
+            if (tshift == kTileShift) {
+                if (rs.blend_rounds == 2) { if (tma) GS_BLEND2F(1, 2, true); else GS_BLEND2F(1, 2, false); }
+                else { if (tma) GS_BLEND2F(1, 4, true); else GS_BLEND2F(1, 4, false); }
+            } else { if (tma) GS_BLEND2F(2, 1, true); else GS_BLEND2F(2, 1, false); }
+#undef GS_BLEND2F
 #undef GS_BLEND2
         } else if (p.frame_format == GS_FRAME_RGBA8)
             gs_launch(k_blend<GS_FRAME_RGBA8>, grid, kBlendThreads, 0, st, rs.ranges.p, rs.list.p, rs.records.p, tiles_x, tiles_y, coarse_x, rank, world, (int)p.width, (int)p.height, p.flip_y, target, rs.tile_order.p);

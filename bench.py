@@ -11,7 +11,7 @@ RGBA8 frame (Viewer.update + Viewer.render of the reference).  Prints ONE JSON l
 value   device-timed (CUDA events on the engine's stream), scene resident in HBM, L2 flushed between steps.
 e2e     the same frames through the C ABI with HOST buffers: every frame's camera (mvp + uniforms) goes host->device and its RGBA8
         picture comes back into pinned host memory inside the timed region.  `value` is the throughput of the pipelined entry
-        (gs_frame_begin / gs_frame_end, two frames in flight); `latency_ms` is one blocking gs_frame.
+        (gs_frame_begin / gs_frame_end, up to three frames in flight); `latency_ms` is one blocking gs_frame.
 N > 1   strong scaling of ONE frame: rank r rasterises the coarse tiles with (cx + cy) % N == r; the ranks' blend kernels store
         their pixels straight into rank 0's frame over NVLink (CUDA IPC); rank 0's assembled picture is compared with a
         single-GPU render of the same frame after the timed loops (`frame_check`).
@@ -373,33 +373,39 @@ def run_ours(args):
             dt = float(tt.item())
         if i >= W:
             t_lat.append(dt)
-    # (b) throughput: gs_frame_begin / gs_frame_end, two frames in flight: frame i+1 is sorted and rendered while frame i's picture
+    # (b) throughput: gs_frame_begin / gs_frame_end, frames in flight: frame i+1 is sorted and rendered while frame i's picture
     # crosses PCIe on the copy stream.  No L2 flush inside this loop (it would sit in the timed stream): the frame's working set
     # (centres, splat data, records, sort scratch, lists: > 180 MB at 1.2 M splats) exceeds the 126 MB L2 and every frame's picture leaves
     # through PCIe.  N > 1 with the NCCL fallback keeps the blocking loop.
+    depth = 3 if world == 1 else 2      # frames in flight (N > 1: rank 0 holds ONE frame buffer, the peers store into it)
+    while len(frames_host) < depth:
+        frames_host.append(N.pinned_empty((height, width, 4), np.uint8))
+
+    def pipelined(count):
+        for j in range(min(depth - 1, count)):
+            e.frame_begin(prep(j), frames_host[j % depth])
+        for i in range(count):
+            if i + depth - 1 < count:
+                e.frame_begin(prep(i + depth - 1), frames_host[(i + depth - 1) % depth])
+            e.frame_end()
+
     if world == 1 or peer:       # warm-up of the pipelined entry (its second frame buffer has its own captured graph)
         if rank == 0:
-            for i in range(4):
-                e.frame_begin(prep(i), frames_host[i & 1])
-                e.frame_end()
+            pipelined(6)
         else:
-            for i in range(4):
+            for i in range(6):
                 step_async(i)
             e.synchronize()
     barrier()
     t0 = time.perf_counter()
     if world == 1 or peer:
         if rank == 0:
-            e.frame_begin(prep(0), frames_host[0])
-            for i in range(K):
-                if i + 1 < K:
-                    e.frame_begin(prep(i + 1), frames_host[(i + 1) & 1])
-                e.frame_end()
+            pipelined(K)
         else:
             for i in range(K):
                 step_async(i)
             e.synchronize()
-        e2e_mode = "pipelined gs_frame_begin/gs_frame_end on rank 0, 2 frames in flight, pinned host frames"
+        e2e_mode = f"pipelined gs_frame_begin/gs_frame_end on rank 0, {depth} frames in flight over {2 if world == 1 else 1} device frame buffer(s), pinned host frames"
     else:
         for i in range(K):
             step_async(i)

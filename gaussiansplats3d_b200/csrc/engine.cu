@@ -91,6 +91,8 @@ template <typename T> struct PinBuf {
 
 enum { EV_SORT0, EV_DEPTH, EV_BUCKET, EV_SORT1, EV_R0, EV_PROJECT, EV_BIN, EV_R1, EV_H2D0, EV_H2D1, EV_D2H0, EV_D2H1, EV_COUNT };
 
+// one status slot of a pipelined frame: SortControl head (3 words, padded to 4) + RasterControl + slack
+constexpr size_t kPipeSlotWords = 4 + (sizeof(RasterControl) + 3) / 4 + 12;   // SortControl head (3 words) + RasterControl
 struct gs_engine {
     gs_config cfg{};
     cudaStream_t stream = nullptr;
@@ -154,12 +156,22 @@ struct gs_engine {
     // pipelined frames (gs_frame_begin / gs_frame_end): device frames alternate between two buffers, the D2H copy of frame i runs on
     // copy_stream while frame i+1 computes on `stream`
     cudaStream_t copy_stream = nullptr;
-    cudaEvent_t ev_frame_done[2] = {nullptr, nullptr}, ev_copy_done[2] = {nullptr, nullptr};
+    // ring of per-frame events / host status slots (more entries than frames in flight); the DEVICE frame buffers stay two
+    static constexpr int kPipeRing = 4, kPipeMaxInflight = 3;
+    cudaEvent_t ev_frame_done[kPipeRing] = {nullptr}, ev_copy_done[kPipeRing] = {nullptr};
+    // per-frame parameter blocks are double buffered by frame-buffer parity and uploaded on their own stream, and the frame's status words
+    // are snapshotted by the blend kernel into a per-parity device slot that the copy stream reads: a pipelined frame then puts NO copy
+    // operation on the compute stream (each small copy there costs a few microseconds of serialisation between two frame graphs)
+    cudaStream_t param_stream = nullptr;
+    cudaEvent_t ev_params[2] = {nullptr, nullptr};
+    bool param_side = false;                       // upload_frame_params goes through param_stream (set by gs_frame_begin)
+    bool graph_snapshot[2] = {false, false};       // the captured frame graph of this parity ends in a blend that writes the status snapshot
+    DevBuf<uint32_t> status_dev;                   // 2 x kPipeSlotWords
     cudaGraphExec_t graph_exec_alt = nullptr;     // the same frame graph with the alternate frame buffer as target
     unsigned long long graph_key_alt[8] = {0};
-    PinBuf<uint32_t> h_pipe;                       // 2 slots x (SortControl head + RasterControl) read back per pipelined frame
-    struct PipeSlot { bool busy = false; gs_render_params rp{}; bool copied = false; } pipe[2];
-    uint32_t pipe_next = 0, pipe_oldest = 0, pipe_inflight = 0;
+    PinBuf<uint32_t> h_pipe;                       // kPipeRing slots x (SortControl head + RasterControl) read back per pipelined frame
+    uint64_t pipe_begun = 0, pipe_ended = 0;       // frames begun / ended; in flight = the difference
+    uint32_t pipe_inflight() const { return (uint32_t)(pipe_begun - pipe_ended); }
 
     // --- sort-only sharding by input position (shard_kernels.cuh) ---
     struct Shard {
@@ -223,7 +235,7 @@ extern "C" int gs_create(const gs_config *cfg, gs_engine **out) {
     const size_t n = std::max<uint32_t>(c.max_splat_count, 1);
     if ((rc = e->centers.ensure(n)) || (rc = e->indexes.ensure(n)) || (rc = e->dist.ensure(n)) || (rc = e->sorted.ensure(n)) ||
         (rc = e->vals[0].ensure(n)) || (rc = e->vals[1].ensure(n)) || (rc = e->keys[0].ensure(n)) || (rc = e->keys[1].ensure(n)) ||
-        (rc = e->ctl.ensure(1)) || (rc = e->depthp.ensure(1)) || (rc = e->transforms.ensure(16 * GS_MAX_SCENES)) || (rc = e->h_ctl.ensure(sizeof(SortControl) / 4 + 64 + sizeof(RasterControl) / 4 + sizeof(ShardHeader) / 4))) {
+        (rc = e->ctl.ensure(1)) || (rc = e->depthp.ensure(2)) || (rc = e->transforms.ensure(16 * GS_MAX_SCENES)) || (rc = e->h_ctl.ensure(sizeof(SortControl) / 4 + 64 + sizeof(RasterControl) / 4 + sizeof(ShardHeader) / 4))) {
         gs_destroy(e);
         return rc;
     }
@@ -237,6 +249,11 @@ extern "C" int gs_create(const gs_config *cfg, gs_engine **out) {
     CUE(cudaMemset(e->ctl.p, 0, sizeof(SortControl)));
     rc = raster_init(e->rs, c, e->sm_count);
     if (rc) { gs_destroy(e); return fail(rc, "raster_init failed: %s", g_err); }
+    if ((rc = e->status_dev.ensure(2 * kPipeSlotWords))) { gs_destroy(e); return rc; }
+    CUE(cudaMemset(e->status_dev.p, 0, 2 * kPipeSlotWords * 4));
+    e->rs.snap_base = e->status_dev.p;
+    e->rs.snap_stride = (uint32_t)kPipeSlotWords;
+    e->rs.snap_sort_ctl = reinterpret_cast<const uint32_t *>(e->ctl.p);
     CUE(cudaStreamSynchronize(e->stream));
     *out = e;
     return GS_OK;
@@ -261,7 +278,10 @@ extern "C" void gs_destroy(gs_engine *e) {
     if (e->stream) cudaStreamDestroy(e->stream);
     if (e->stream2) cudaStreamDestroy(e->stream2);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
-    for (int i = 0; i < 2; ++i) { if (e->ev_frame_done[i]) cudaEventDestroy(e->ev_frame_done[i]); if (e->ev_copy_done[i]) cudaEventDestroy(e->ev_copy_done[i]); }
+    for (int i = 0; i < gs_engine::kPipeRing; ++i) { if (e->ev_frame_done[i]) cudaEventDestroy(e->ev_frame_done[i]); if (e->ev_copy_done[i]) cudaEventDestroy(e->ev_copy_done[i]); }
+    for (int i = 0; i < 2; ++i) if (e->ev_params[i]) cudaEventDestroy(e->ev_params[i]);
+    if (e->param_stream) cudaStreamDestroy(e->param_stream);
+    e->status_dev.release();
     if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
     if (e->graph_exec_alt) cudaGraphExecDestroy(e->graph_exec_alt);
     if (e->ev_fork) cudaEventDestroy(e->ev_fork);
@@ -301,7 +321,7 @@ static int enqueue_depth(gs_engine *e, const uint32_t *d_indexes, const float *m
     P.irow[2] = (int32_t)((double)mvp[10] * 1000.0);
     P.irow[3] = 1;
     P.frow[0] = mvp[2]; P.frow[1] = mvp[6]; P.frow[2] = mvp[10]; P.frow[3] = 0.f;
-    if (!capturing) CU(cudaMemcpyAsync(e->depthp.p, &P, sizeof(P), cudaMemcpyHostToDevice, st)); // pageable source: staged before return
+    if (!capturing) CU(cudaMemcpyAsync(e->depthp.p + e->rs.frame_parity, &P, sizeof(P), cudaMemcpyHostToDevice, st)); // pageable source: staged before return
     const bool integer = e->cfg.integer_based_sort, dyn = e->cfg.dynamic_mode;
     const int mode = use_pre ? (integer ? kIntPrecomputed : kFloatPrecomputed)
                              : (integer ? (dyn ? kIntDynamic : kIntStatic) : (dyn ? kFloatDynamic : kFloatStatic));
@@ -309,12 +329,12 @@ static int enqueue_depth(gs_engine *e, const uint32_t *d_indexes, const float *m
     const bool identity = (d_indexes == nullptr);
     const void *pre = e->precomputed.p;
     switch (mode) {
-        case kIntStatic: launch_depth<kIntStatic>(identity, dblocks, st, d_indexes, e->centers.p, pre, e->scene_idx.p, e->transforms.p, e->depthp.p, lo, hi, e->dist.p, e->ctl.p); break;
-        case kIntDynamic: launch_depth<kIntDynamic>(identity, dblocks, st, d_indexes, e->centers.p, pre, e->scene_idx.p, e->transforms.p, e->depthp.p, lo, hi, e->dist.p, e->ctl.p); break;
-        case kIntPrecomputed: launch_depth<kIntPrecomputed>(identity, dblocks, st, d_indexes, e->centers.p, pre, e->scene_idx.p, e->transforms.p, e->depthp.p, lo, hi, e->dist.p, e->ctl.p); break;
-        case kFloatStatic: launch_depth<kFloatStatic>(identity, dblocks, st, d_indexes, e->centers.p, pre, e->scene_idx.p, e->transforms.p, e->depthp.p, lo, hi, e->dist.p, e->ctl.p); break;
-        case kFloatDynamic: launch_depth<kFloatDynamic>(identity, dblocks, st, d_indexes, e->centers.p, pre, e->scene_idx.p, e->transforms.p, e->depthp.p, lo, hi, e->dist.p, e->ctl.p); break;
-        default: launch_depth<kFloatPrecomputed>(identity, dblocks, st, d_indexes, e->centers.p, pre, e->scene_idx.p, e->transforms.p, e->depthp.p, lo, hi, e->dist.p, e->ctl.p); break;
+        case kIntStatic: launch_depth<kIntStatic>(identity, dblocks, st, d_indexes, e->centers.p, pre, e->scene_idx.p, e->transforms.p, e->depthp.p + e->rs.frame_parity, lo, hi, e->dist.p, e->ctl.p); break;
+        case kIntDynamic: launch_depth<kIntDynamic>(identity, dblocks, st, d_indexes, e->centers.p, pre, e->scene_idx.p, e->transforms.p, e->depthp.p + e->rs.frame_parity, lo, hi, e->dist.p, e->ctl.p); break;
+        case kIntPrecomputed: launch_depth<kIntPrecomputed>(identity, dblocks, st, d_indexes, e->centers.p, pre, e->scene_idx.p, e->transforms.p, e->depthp.p + e->rs.frame_parity, lo, hi, e->dist.p, e->ctl.p); break;
+        case kFloatStatic: launch_depth<kFloatStatic>(identity, dblocks, st, d_indexes, e->centers.p, pre, e->scene_idx.p, e->transforms.p, e->depthp.p + e->rs.frame_parity, lo, hi, e->dist.p, e->ctl.p); break;
+        case kFloatDynamic: launch_depth<kFloatDynamic>(identity, dblocks, st, d_indexes, e->centers.p, pre, e->scene_idx.p, e->transforms.p, e->depthp.p + e->rs.frame_parity, lo, hi, e->dist.p, e->ctl.p); break;
+        default: launch_depth<kFloatPrecomputed>(identity, dblocks, st, d_indexes, e->centers.p, pre, e->scene_idx.p, e->transforms.p, e->depthp.p + e->rs.frame_parity, lo, hi, e->dist.p, e->ctl.p); break;
     }
     return GS_OK;
 }
@@ -940,9 +960,15 @@ static int upload_frame_params(gs_engine *e, const float *mvp, const gs_uniforms
     P.irow[2] = (int32_t)((double)mvp[10] * 1000.0);
     P.irow[3] = 1;
     P.frow[0] = mvp[2]; P.frow[1] = mvp[6]; P.frow[2] = mvp[10]; P.frow[3] = 0.f;
-    CU(cudaMemcpyAsync(e->depthp.p, &P, sizeof(P), cudaMemcpyHostToDevice, e->stream));
-    int rc = raster_upload_params(e->rs, e->cfg, u, p, e->stream);
-    return rc;
+    cudaStream_t st = e->param_side ? e->param_stream : e->stream;
+    CU(cudaMemcpyAsync(e->depthp.p + e->rs.frame_parity, &P, sizeof(P), cudaMemcpyHostToDevice, st));
+    int rc = raster_upload_params(e->rs, e->cfg, u, p, st);
+    if (rc) return rc;
+    if (e->param_side) {      // the frame graph (and nothing else on the compute stream) waits for the side upload
+        CU(cudaEventRecord(e->ev_params[e->rs.frame_parity], st));
+        CU(cudaStreamWaitEvent(e->stream, e->ev_params[e->rs.frame_parity], 0));
+    }
+    return GS_OK;
 }
 
 static int enqueue_frame(gs_engine *e, const gs_sort_params *s, const gs_uniforms *u, const gs_render_params *p, gs_sort_params &q, gs_render_params &rp) {
@@ -1013,6 +1039,7 @@ static int enqueue_frame(gs_engine *e, const gs_sort_params *s, const gs_uniform
             cudaGraphDestroy(g);
             if (ce != cudaSuccess) { gexec = nullptr; return fail(GS_ERR_CUDA, "cudaGraphInstantiate -> %s", cudaGetErrorString(ce)); }
             memcpy(gkey, key, sizeof(key));
+            e->graph_snapshot[e->rs.frame_parity ? 1 : 0] = e->rs.snapshot_taken;
         }
         if (e->ctl_dirty) gs_launch(k_sort_init, 1, 256, 0, st, e->ctl.p);   // the captured sort assumes (and leaves) a clean control block
         e->ctl_dirty = true;
@@ -1054,7 +1081,7 @@ extern "C" int gs_frame(gs_engine *e, const gs_sort_params *s, const gs_uniforms
     int rc = check_engine(e);
     if (rc) return rc;
     if (!s || !u || !p) return fail(GS_ERR_BAD_ARG, "gs_frame: null argument");
-    if (e->pipe_inflight) return fail(GS_ERR_NOT_READY, "gs_frame: pipelined frames are in flight (gs_frame_end first)");
+    if (e->pipe_inflight()) return fail(GS_ERR_NOT_READY, "gs_frame: pipelined frames are in flight (gs_frame_end first)");
     e->rs.frame_parity = 0;
     gs_sort_params q; gs_render_params rp;
     e->no_subset = (sorted_out != nullptr);
@@ -1083,19 +1110,24 @@ extern "C" int gs_frame_async(gs_engine *e, const gs_sort_params *s, const gs_un
 
 // ---------------------------------------------------------------------------------------------------------------
 // Pipelined frames: gs_frame_begin enqueues frame i (camera H2D, sort, render) and a D2H copy of its picture on a separate copy
-// stream; gs_frame_end waits for the OLDEST frame in flight and reports its errors.  Up to two frames are in flight: the device
-// frames alternate between two buffers, so frame i+1 renders while frame i's picture crosses PCIe (begin(0); loop { begin(i+1);
-// end(i); }).  Per-frame latency is that of gs_frame; throughput approaches max(compute, copy).  Multi-GPU engines that gather
-// tiles into rank 0's exported frame keep ONE buffer (the peers store into it), so there the copy only overlaps the host side.
-constexpr size_t kPipeSlotWords = 4 + (sizeof(RasterControl) + 3) / 4 + 12;   // SortControl head (3 words) + RasterControl
+// stream; gs_frame_end waits for the OLDEST frame in flight and reports its errors.  Up to three frames may be in flight over TWO
+// device frame buffers: frame i+1 renders while frame i's picture crosses PCIe, and frame i+2 is already queued behind it (it
+// starts only when frame i's copy has left its buffer), so the GPU never waits for the host between frames
+// (begin(0); begin(1); loop { begin(i+2); end(i); }).  Every frame in flight needs its own `frame_out`.  Per-frame latency is that of
+// gs_frame; throughput approaches max(compute, copy).  With two buffers a frame graph is the ONLY thing a frame puts on the compute
+// stream: the parameter blocks go up on `param_stream` into the block of the frame buffer's parity, and the status words are
+// snapshotted by the blend kernel and read back on the copy stream.  Multi-GPU engines that gather tiles into rank 0's exported
+// frame keep ONE buffer (the peers store into it), so there the copy only overlaps the host side.
 static int pipe_init(gs_engine *e) {
     if (e->copy_stream) return GS_OK;
     CU(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; ++i) {
+    CU(cudaStreamCreateWithFlags(&e->param_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < gs_engine::kPipeRing; ++i) {
         CU(cudaEventCreateWithFlags(&e->ev_frame_done[i], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&e->ev_copy_done[i], cudaEventDisableTiming));
     }
-    int rc = e->h_pipe.ensure(2 * kPipeSlotWords);
+    for (int i = 0; i < 2; ++i) CU(cudaEventCreateWithFlags(&e->ev_params[i], cudaEventDisableTiming));
+    int rc = e->h_pipe.ensure(gs_engine::kPipeRing * kPipeSlotWords);
     if (rc) return rc;
     const bool single = e->cfg.world_size > 1;
     if (!single && !e->rs.frame_alt.p) {
@@ -1109,42 +1141,49 @@ extern "C" int gs_frame_begin(gs_engine *e, const gs_sort_params *s, const gs_un
     int rc = check_engine(e);
     if (rc) return rc;
     if (!s || !u || !p) return fail(GS_ERR_BAD_ARG, "gs_frame_begin: null argument");
-    if (e->pipe_inflight >= 2) return fail(GS_ERR_NOT_READY, "gs_frame_begin: two frames already in flight (call gs_frame_end)");
+    if (e->pipe_inflight() >= (uint32_t)gs_engine::kPipeMaxInflight) return fail(GS_ERR_NOT_READY, "gs_frame_begin: %d frames already in flight (call gs_frame_end)", gs_engine::kPipeMaxInflight);
     if (e->pending_async) return fail(GS_ERR_NOT_READY, "gs_frame_begin: an asynchronous frame is pending (gs_synchronize first)");
     if ((rc = pipe_init(e))) return rc;
-    const uint32_t slot = e->pipe_next;
-    // the buffer this frame renders into must have been copied out (frame i-2, or i-1 with a single buffer)
-    CU(cudaStreamWaitEvent(e->stream, e->ev_copy_done[slot], 0));
-    if (e->cfg.world_size > 1) CU(cudaStreamWaitEvent(e->stream, e->ev_copy_done[slot ^ 1], 0));
-    e->rs.frame_parity = (e->rs.frame_alt.p && slot) ? 1 : 0;
+    constexpr uint64_t R = gs_engine::kPipeRing;
+    const uint64_t seq = e->pipe_begun;
+    const uint32_t ring = (uint32_t)(seq % R);
+    const bool two = e->rs.frame_alt.p != nullptr;
+    // the buffer this frame renders into must have been copied out: frame seq-2 with two buffers, seq-1 with one
+    if (two) { if (seq >= 2) CU(cudaStreamWaitEvent(e->stream, e->ev_copy_done[(seq - 2) % R], 0)); }
+    else if (seq >= 1) CU(cudaStreamWaitEvent(e->stream, e->ev_copy_done[(seq - 1) % R], 0));
+    e->rs.frame_parity = two ? (int)(seq & 1) : 0;
+    // parameter blocks of this parity were last read by frame seq-2: its graph must have finished before they are overwritten
+    e->param_side = two;
+    if (two && seq >= 2) CU(cudaStreamWaitEvent(e->param_stream, e->ev_frame_done[(seq - 2) % R], 0));
     gs_sort_params q; gs_render_params rp;
     rc = enqueue_frame(e, s, u, p, q, rp);
+    e->param_side = false;
     if (rc) { e->rs.frame_parity = 0; return rc; }
     cudaStream_t st = e->stream;
-    uint32_t *hs = e->h_pipe.p + slot * kPipeSlotWords;
-    CU(cudaMemcpyAsync(hs, e->ctl.p, 12, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(hs + 4, e->rs.rctl.p, sizeof(RasterControl), cudaMemcpyDeviceToHost, st));
-    CU(cudaEventRecord(e->ev_frame_done[slot], st));
-    CU(cudaStreamWaitEvent(e->copy_stream, e->ev_frame_done[slot], 0));
+    uint32_t *hs = e->h_pipe.p + ring * kPipeSlotWords;
+    const bool snapshot = two && e->last_frame_was_graph && e->graph_snapshot[e->rs.frame_parity];
+    if (!snapshot) {      // status read-back in stream order (frames outside a graph, blend generations without the snapshot, one buffer)
+        CU(cudaMemcpyAsync(hs, e->ctl.p, 12, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(hs + 4, e->rs.rctl.p, sizeof(RasterControl), cudaMemcpyDeviceToHost, st));
+    }
+    CU(cudaEventRecord(e->ev_frame_done[ring], st));
+    CU(cudaStreamWaitEvent(e->copy_stream, e->ev_frame_done[ring], 0));
+    if (snapshot)
+        CU(cudaMemcpyAsync(hs, e->status_dev.p + (size_t)e->rs.frame_parity * kPipeSlotWords, (4 + sizeof(RasterControl) / 4) * 4, cudaMemcpyDeviceToHost, e->copy_stream));
     if (frame_out) CU(cudaMemcpyAsync(frame_out, raster_frame_ptr(e->rs, rp.frame_format), frame_bytes(&rp), cudaMemcpyDeviceToHost, e->copy_stream));
-    CU(cudaEventRecord(e->ev_copy_done[slot], e->copy_stream));
-    e->pipe[slot].busy = true;
-    e->pipe[slot].rp = rp;
-    e->pipe_next = slot ^ 1;
-    if (e->pipe_inflight++ == 0) e->pipe_oldest = slot;
+    CU(cudaEventRecord(e->ev_copy_done[ring], e->copy_stream));
+    ++e->pipe_begun;
     return GS_OK;
 }
 
 extern "C" int gs_frame_end(gs_engine *e) {
     int rc = check_engine(e);
     if (rc) return rc;
-    if (e->pipe_inflight == 0) return fail(GS_ERR_NOT_READY, "gs_frame_end: no frame in flight");
-    const uint32_t slot = e->pipe_oldest;
-    CU(cudaEventSynchronize(e->ev_copy_done[slot]));
-    e->pipe[slot].busy = false;
-    e->pipe_oldest = slot ^ 1;
-    --e->pipe_inflight;
-    const uint32_t *hs = e->h_pipe.p + slot * kPipeSlotWords;
+    if (e->pipe_inflight() == 0) return fail(GS_ERR_NOT_READY, "gs_frame_end: no frame in flight");
+    const uint32_t ring = (uint32_t)(e->pipe_ended % (uint64_t)gs_engine::kPipeRing);
+    CU(cudaEventSynchronize(e->ev_copy_done[ring]));
+    ++e->pipe_ended;
+    const uint32_t *hs = e->h_pipe.p + ring * kPipeSlotWords;
     RasterControl rctl;
     memcpy(&rctl, hs + 4, sizeof(rctl));
     e->tm.tile_instances = rctl.total_instances;

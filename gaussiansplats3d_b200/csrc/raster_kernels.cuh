@@ -1085,8 +1085,8 @@ __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f
 
 // Which of a tile's 8x8-px blocks can hold a pixel the splat covers: exact minimum of q over each block's rectangle of pixel
 // centres (ellipse_mask.h), only for the blocks the ellipse's AABB reaches.  a0 = cx, cy, g1x, g1y; a1 = g2x, g2y, half2(hx, hy), alpha.
-// NB = blocks per tile row (2 or 4).  Not inlined: the caller's composite loop is register-bound and this runs once per staged record.
-template <int NB>
+// NBX x NBY = blocks per tile row / column.  Not inlined: the caller's composite loop is register-bound and this runs once per staged record.
+template <int NBX, int NBY>
 __device__ __noinline__ uint32_t block_touch_mask(float4 a0, float4 a1, float tile_x0, float tile_y0) {
     if (!(a1.w > 0.0f)) return 0u;
     const uint32_t hb = __float_as_uint(a1.z);
@@ -1095,11 +1095,11 @@ __device__ __noinline__ uint32_t block_touch_mask(float4 a0, float4 a1, float ti
     const float qxx = a0.z * a0.z + a1.x * a1.x, qxy = a0.z * a0.w + a1.x * a1.y, qyy = a0.w * a0.w + a1.y * a1.y;
     const float X0 = tile_x0 - a0.x, Y0 = tile_y0 - a0.y;      // first pixel centre of the tile, relative to the splat centre
     // block i spans [X0 + 8 i, X0 + 8 i + 7]; it meets [-hx, hx] iff  (-hx - X0 - 7) / 8 <= i <= (hx - X0) / 8
-    const int ix0 = max(0, (int)ceilf((-hx - X0 - 7.0f) * 0.125f)), ix1 = min(NB - 1, (int)floorf((hx - X0) * 0.125f));
-    const int iy0 = max(0, (int)ceilf((-hy - Y0 - 7.0f) * 0.125f)), iy1 = min(NB - 1, (int)floorf((hy - Y0) * 0.125f));
+    const int ix0 = max(0, (int)ceilf((-hx - X0 - 7.0f) * 0.125f)), ix1 = min(NBX - 1, (int)floorf((hx - X0) * 0.125f));
+    const int iy0 = max(0, (int)ceilf((-hy - Y0 - 7.0f) * 0.125f)), iy1 = min(NBY - 1, (int)floorf((hy - Y0) * 0.125f));
     // The AABB (exact extents of the ellipse) inside ONE block: that block holds the whole ellipse, nothing to decide.  (A block without
     // a pixel centre inside the ellipse can still pass here; it costs one visit that adds nothing.)
-    if (ix0 == ix1 && iy0 == iy1) return 1u << (iy0 * NB + ix0);
+    if (ix0 == ix1 && iy0 == iy1) return 1u << (iy0 * NBX + ix0);
     uint32_t bm = 0;
 #pragma unroll 1
     for (int iy = iy0; iy <= iy1; ++iy) {
@@ -1107,18 +1107,33 @@ __device__ __noinline__ uint32_t block_touch_mask(float4 a0, float4 a1, float ti
 #pragma unroll 1
         for (int ix = ix0; ix <= ix1; ++ix) {
             const float bx0 = X0 + (float)(8 * ix), bx1 = bx0 + 7.0f;
-            if (ellipse_min_q(bx0, bx1, by0, by1, qxx, qxy, qyy) <= 1.0f + kEllipseSlack) bm |= 1u << (iy * NB + ix);
+            if (ellipse_min_q(bx0, bx1, by0, by1, qxx, qxy, qyy) <= 1.0f + kEllipseSlack) bm |= 1u << (iy * NBX + ix);
         }
     }
     return bm;
 }
 
+struct StatusSnapshot {
+    const uint32_t *sort_ctl;     // SortControl head: 3 words (dmin, dmax, error)
+    const uint32_t *raster_ctl;   // RasterControl
+    uint32_t *dst;                // [0, 3) sort head, [4, 4 + sizeof(RasterControl) / 4) raster control; nullptr = no snapshot
+};
+
 template <int FORMAT, int S, int ROUNDS, bool TMA>
 __global__ void __launch_bounds__(128 * S * S, S == 1 ? 8 : 2)
 k_blend2(const uint2 *__restrict__ ranges, const unsigned long long *__restrict__ list, const SplatRecord *__restrict__ rec, int tiles_x,
-         int tiles_y, int coarse_x, uint32_t rank, uint32_t world, int width, int height, int flip_y, void *__restrict__ frame, const uint32_t *__restrict__ tile_order) {
+         int tiles_y, int coarse_x, uint32_t rank, uint32_t world, int width, int height, int flip_y, void *__restrict__ frame, const uint32_t *__restrict__ tile_order,
+         StatusSnapshot snap) {
     pdl_enter();
-    constexpr int THREADS = 128 * S * S, WARPS = THREADS / 32, NB = 2 * S, TILE = 16 * S;
+    // Everything the host reads back about a frame (sort error bits, instance / visibility counters, overflow flag) is final before the
+    // blend starts; CTA 0 copies it into a per-frame-buffer slot so that the read-back can run on the copy stream, off this stream.
+    if (snap.dst && blockIdx.x == 0) {
+        if (threadIdx.x < 3) snap.dst[threadIdx.x] = snap.sort_ctl[threadIdx.x];
+        for (uint32_t i = threadIdx.x; i < (uint32_t)(sizeof(RasterControl) / 4); i += blockDim.x) snap.dst[4 + i] = snap.raster_ctl[i];
+    }
+    // (A CTA covering TWO fine tiles side by side -- one scan of the coarse list for 32x16 px -- was measured: fewer instructions, but
+    // the per-round barrier then waits for the densest of 8 blocks instead of 4 and the blend got 5-18 % slower.  Not kept.)
+    constexpr int THREADS = 128 * S * S, WARPS = THREADS / 32, NBX = 2 * S, NBY = 2 * S, TILE = 16 * S;
     constexpr int BATCH = ROUNDS * THREADS;      // list entries per batch
     __shared__ float4 s_rec[THREADS + 1][3];    // [THREADS] = the null record (alpha 0) that pairs with an odd tail
     __shared__ uint32_t s_ids[BATCH];
@@ -1134,7 +1149,7 @@ k_blend2(const uint2 *__restrict__ ranges, const unsigned long long *__restrict_
     if (tx >= tiles_x || ty >= tiles_y) return;
     if (!owns_coarse(ccx, ccy, rank, world)) return;   // another GPU's tile
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int x = tx * TILE + (warp % NB) * 8 + (lane & 7), y0 = ty * TILE + (warp / NB) * 8 + (lane >> 3) * 2;
+    const int x = tx * TILE + (warp % NBX) * 8 + (lane & 7), y0 = ty * TILE + (warp / NBX) * 8 + (lane >> 3) * 2;
     const float pxc = (float)x + 0.5f, pyc = (float)y0 + 0.5f;
     const float tile_x0 = (float)(tx * TILE) + 0.5f, tile_y0 = (float)(ty * TILE) + 0.5f;    // first pixel centre of the tile
     // pixels outside the frame start saturated so that they never keep a warp alive
@@ -1213,7 +1228,7 @@ k_blend2(const uint2 *__restrict__ ranges, const unsigned long long *__restrict_
                 float4 a0 = __ldg(src), a1 = __ldg(src + 1);
                 const float4 a2 = __ldg(src + 2);
                 // a0 = cx, cy, g1x, g1y ; a1 = g2x, g2y, half2(hx, hy), alpha ; a2 = r, g, b, ndc z
-                bm = block_touch_mask<NB>(a0, a1, tile_x0, tile_y0);
+                bm = block_touch_mask<NBX, NBY>(a0, a1, tile_x0, tile_y0);
                 // staged form: u(p) = g1 . p + u0, w(p) = g2 . p + w0 at a pixel centre p (two FMAs each in the loop below)
                 const float u0 = -fmaf(a0.x, a0.z, a0.y * a0.w), w0 = -fmaf(a0.x, a1.x, a0.y * a1.y);
                 a1.z = a0.w * a0.w + a1.y * a1.y;     // h = |d(u,w)/dy|^2
@@ -1367,6 +1382,11 @@ struct RasterState {
     RBuf<unsigned char> frame;
     RBuf<unsigned char> frame_alt;   // second device frame: pipelined frames (gs_frame_begin) alternate so a D2H copy can overlap the next frame
     int frame_parity = 0;
+    // status snapshot taken by the blend kernel (see StatusSnapshot): destination slots [parity * snap_stride], source sort control
+    uint32_t *snap_base = nullptr;
+    uint32_t snap_stride = 0;
+    const uint32_t *snap_sort_ctl = nullptr;
+    bool snapshot_taken = false;   // the last raster_render launched a blend that wrote the snapshot
     RBuf<gs_projected_splat> exported;
     // fused tile gather over NVLink peer memory (world_size > 1)
     RBuf<PeerSync> peer_sync_local;      // rank 0 owns the block
@@ -1393,9 +1413,9 @@ static int raster_init(RasterState &rs, const gs_config &c, int sm_count) {
     const size_t n = c.max_splat_count ? c.max_splat_count : 1;
     RCU(rs.rctl.ensure(1));
     RCU(rs.sctl.ensure(1));
-    RCU(rs.dyn.ensure(1));
-    RCU(rs.projp.ensure(1));
-    RCU(cudaMemset(rs.dyn.p, 0, sizeof(DynamicUniforms)));
+    RCU(rs.dyn.ensure(2));          // per-frame parameter blocks: one per frame-buffer parity (pipelined frames upload them off-stream)
+    RCU(rs.projp.ensure(2));
+    RCU(cudaMemset(rs.dyn.p, 0, 2 * sizeof(DynamicUniforms)));
     if (c.max_width && c.max_height) {
         RCU(rs.cc.ensure(n));
         RCU(rs.records.ensure(n));
@@ -1479,7 +1499,7 @@ template <bool COVF16>
 static void launch_project(RasterState &rs, uint32_t count, cudaStream_t st) {
     const int blocks = (int)((count + kProjThreads - 1) / kProjThreads);
     const uint32_t *sc = rs.have_scene_idx ? rs.scene_idx.p : nullptr;
-#define GS_PROJ(FMT) gs_launch(k_project<COVF16, FMT>, blocks, kProjThreads, 0, st, rs.cc.p, rs.cov.p, rs.sh.p, (int)rs.sh_degree, sc, rs.dyn.p, rs.projp.p, count, rs.records.p, rs.rects.p, rs.rctl.p)
+#define GS_PROJ(FMT) gs_launch(k_project<COVF16, FMT>, blocks, kProjThreads, 0, st, rs.cc.p, rs.cov.p, rs.sh.p, (int)rs.sh_degree, sc, rs.dyn.p + rs.frame_parity, rs.projp.p + rs.frame_parity, count, rs.records.p, rs.rects.p, rs.rctl.p)
     switch (rs.sh_format) {
         case GS_SH_F16: GS_PROJ(GS_SH_F16); break;
         case GS_SH_U8: GS_PROJ(GS_SH_U8); break;
@@ -1512,14 +1532,14 @@ static int raster_upload_params(RasterState &rs, const gs_config &c, const gs_un
     P.dynamic = u.dynamic_mode; P.optional_effects = u.enable_optional_effects; P.scene_count = (int)u.scene_count;
     P.tiles_x = tiles_x; P.tiles_y = tiles_y; P.rank = rank; P.world = world; P.width = (int)p.width; P.height = (int)p.height;
     P.tile_shift = tshift;
-    if (upload_params) RCU(cudaMemcpyAsync(rs.projp.p, &P, sizeof(P), cudaMemcpyHostToDevice, st)); // pageable source: staged before return
+    if (upload_params) RCU(cudaMemcpyAsync(rs.projp.p + rs.frame_parity, &P, sizeof(P), cudaMemcpyHostToDevice, st)); // pageable source: staged before return
     if (upload_params && (u.dynamic_mode || u.enable_optional_effects || rs.sh_format == GS_SH_U8)) {
         DynamicUniforms du;
         memcpy(du.view, u.view_matrix, 64);
         memcpy(du.transforms, u.scene_transforms, sizeof(du.transforms));
         memcpy(du.sh8_min, u.sh8_min, sizeof(du.sh8_min)); memcpy(du.sh8_max, u.sh8_max, sizeof(du.sh8_max));
         memcpy(du.opacity, u.scene_opacity, sizeof(du.opacity)); memcpy(du.visibility, u.scene_visibility, sizeof(du.visibility));
-        RCU(cudaMemcpyAsync(rs.dyn.p, &du, sizeof(du), cudaMemcpyHostToDevice, st)); // pageable source: staged before return
+        RCU(cudaMemcpyAsync(rs.dyn.p + rs.frame_parity, &du, sizeof(du), cudaMemcpyHostToDevice, st)); // pageable source: staged before return
     }
 
     return GS_OK;
@@ -1560,6 +1580,7 @@ static int raster_render(RasterState &rs, const gs_config &c, const gs_uniforms 
         if (record_events) RCU(cudaEventRecord(ev_project, st));
     }
     if (!(phases & 2)) { tm.kernel_launches = launches; return GS_OK; }
+    rs.snapshot_taken = false;
     const bool bin2 = rs.bin_version >= 2 && ncoarse <= 256u;
     if (p.render_count && local_tiles && bin2) {
         const OwnMask own = make_own_mask(rank, world);
@@ -1610,7 +1631,10 @@ static int raster_render(RasterState &rs, const gs_config &c, const gs_uniforms 
         }
         const uint32_t grid = ncoarse * kFinePerCoarse;
         if (rs.blend_version >= 2 || tshift != kTileShift) {
-#define GS_BLEND2(FMT, SC, RD, TM) gs_launch(k_blend2<FMT, SC, RD, TM>, grid, 128 * SC * SC, 0, st, rs.ranges.p, rs.list.p, rs.records.p, tiles_x, tiles_y, coarse_x, rank, world, (int)p.width, (int)p.height, p.flip_y, target, rs.tile_order.p)
+            const StatusSnapshot snap{rs.snap_sort_ctl, reinterpret_cast<const uint32_t *>(rs.rctl.p),
+                                      (rs.snap_base && rs.snap_sort_ctl) ? rs.snap_base + (size_t)rs.frame_parity * rs.snap_stride : nullptr};
+            rs.snapshot_taken = snap.dst != nullptr;
+#define GS_BLEND2(FMT, SC, RD, TM) gs_launch(k_blend2<FMT, SC, RD, TM>, grid, 128 * SC * SC, 0, st, rs.ranges.p, rs.list.p, rs.records.p, tiles_x, tiles_y, coarse_x, rank, world, (int)p.width, (int)p.height, p.flip_y, target, rs.tile_order.p, snap)
 #define GS_BLEND2F(SC, RD, TM) do { if (p.frame_format == GS_FRAME_RGBA8) GS_BLEND2(GS_FRAME_RGBA8, SC, RD, TM); else GS_BLEND2(GS_FRAME_RGBA32F, SC, RD, TM); } while (0)
             // list batches: plain loads; GS_BLEND_TMA=1 prefetches them with bulk async copies instead (measured: no gain)
             const bool tma = rs.blend_tma > 0;

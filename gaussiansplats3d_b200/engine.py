@@ -353,7 +353,7 @@ class Engine:
 
     def frame_begin(self, prepared, frame_out: np.ndarray | None) -> None:
         """Pipelined frame (gs_frame_begin): enqueue the frame and the copy of its picture into `frame_out` (pinned host array);
-        at most two frames in flight.  `prepared` = prepare_frame(...)."""
+        at most three frames in flight, each with its own `frame_out`.  `prepared` = prepare_frame(...)."""
         sp, u, rp = prepared
         N.check(self._lib.gs_frame_begin(self._h, C.byref(sp), C.byref(u), C.byref(rp), N.ptr(frame_out)), "gs_frame_begin")
 

@@ -245,11 +245,13 @@ GS_API int gs_frame(gs_engine *e, const gs_sort_params *s, const gs_uniforms *u,
  * (gs_buffer_dev(GS_BUF_FRAME)); device-side errors and timings are collected by the next gs_synchronize().         */
 GS_API int gs_frame_async(gs_engine *e, const gs_sort_params *s, const gs_uniforms *u, const gs_render_params *p);
 
-/* Pipelined frames: the frame loop of Viewer.selfDrivenUpdate (Viewer.js:1543-1555) with up to two frames in flight.  gs_frame_begin
+/* Pipelined frames: the frame loop of Viewer.selfDrivenUpdate (Viewer.js:1543-1555) with up to three frames in flight.  gs_frame_begin
  * enqueues one frame exactly like gs_frame (camera host -> device, full sort, render) plus the copy of its picture into frame_out (HOST,
- * ideally page-locked: gs_host_alloc) on a separate copy stream, and returns at once; gs_frame_end waits for the OLDEST frame in
- * flight, after which its frame_out is complete, and returns that frame's status.  Device frames alternate between two buffers, so
- * frame i+1 is computed while frame i crosses PCIe:   begin(0); for (i...) { begin(i+1); end(i); }                                  */
+ * ideally page-locked: gs_host_alloc; every frame in flight needs its own) on a separate copy stream, and returns at once; gs_frame_end
+ * waits for the OLDEST frame in flight, after which its frame_out is complete, and returns that frame's status.  Device frames alternate
+ * between two buffers, so frame i+1 is computed while frame i crosses PCIe and frame i+2 is already queued behind it:
+ *   begin(0); begin(1); for (i...) { begin(i+2); end(i); }       (begin(0); for (i...) { begin(i+1); end(i); } also works)
+ * A fourth gs_frame_begin without a gs_frame_end returns GS_ERR_NOT_READY.                                                            */
 GS_API int gs_frame_begin(gs_engine *e, const gs_sort_params *s, const gs_uniforms *u, const gs_render_params *p, void *frame_out);
 GS_API int gs_frame_end(gs_engine *e);
 

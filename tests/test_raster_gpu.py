@@ -253,6 +253,34 @@ def test_blend_and_binning_generations_agree(gs, oracle_mod, monkeypatch, w, h):
     assert d.max() <= 4.0 / 255 and (d <= 1.0 / 255).mean() >= 0.9995, (d.max() * 255, (d <= 1.0 / 255).mean())
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("w,h", [(1280, 720), (3840, 2160)])
+def test_blend_list_prefetch_variants_are_bit_identical(gs, monkeypatch, w, h):
+    """GS_BLEND_TMA=1 fetches the coarse-tile list batches with bulk asynchronous copies (cp.async.bulk + mbarrier, double buffered)
+    instead of plain loads: same batches, same arithmetic, so the frame must be bit-identical (a protocol error paints magenta).
+    GS_BLEND_ROUNDS=2 halves the batch; that shifts which records share a loop iteration, and a warp stops at the first ITERATION after
+    which all of its pixels are below the 1/512 transmittance cutoff, so it may composite one more (invisible) record: <= 1/255.
+    16-px tiles (720p) and 32-px tiles (4K)."""
+    from gaussiansplats3d_b200.scenes import synthetic_scene
+    n = 150_000
+    raw = synthetic_scene(n, seed=11, kind="bonsai", sh_degree=0)
+    frames = {}
+    for name, env in (("plain", {}), ("tma", {"GS_BLEND_TMA": "1"}), ("rounds2", {"GS_BLEND_ROUNDS": "2"}), ("tma_rounds2", {"GS_BLEND_TMA": "1", "GS_BLEND_ROUNDS": "2"})):
+        for k in ("GS_BLEND_TMA", "GS_BLEND_ROUNDS"):
+            monkeypatch.delenv(k, raising=False)
+        for k, val in env.items():
+            monkeypatch.setenv(k, val)
+        v = _viewer(gs, raw, w, h)
+        v.update()
+        frames[name] = v.render(frame_format=gs._native.GS_FRAME_RGBA8, flip_y=True).copy()
+        v.dispose()
+    assert frames["plain"][..., 3].max() > 0
+    assert np.array_equal(frames["tma"], frames["plain"])
+    assert np.array_equal(frames["tma_rounds2"], frames["rounds2"])
+    d = np.abs(frames["rounds2"].astype(np.int16) - frames["plain"].astype(np.int16))
+    assert d.max() <= 1 and (d != 0).mean() < 1e-3, (d.max(), (d != 0).mean())
+
+
 def test_dynamic_scene_applies_its_transform(gs, oracle_mod):
     """Viewer(dynamicScene=True).addSplatScene(position, rotation, scale): the transform is NOT baked; the sorter (sorter.cpp:44-50) and the
     vertex stage (SplatMaterial.js:136-146) apply it every frame.  The picture must match (a) the restatement driven with the same
@@ -291,7 +319,7 @@ def test_dynamic_scene_applies_its_transform(gs, oracle_mod):
 
 
 def test_pipelined_frames_equal_blocking_frames(gs):
-    """gs_frame_begin / gs_frame_end (two frames in flight, alternating device frame buffers, copies on a second stream) must deliver
+    """gs_frame_begin / gs_frame_end (two or three frames in flight, alternating device frame buffers, copies on a second stream) must deliver
     exactly the pictures gs_frame delivers, in order, for a moving camera."""
     from gaussiansplats3d_b200 import _native as N
     from gaussiansplats3d_b200.scenes import synthetic_scene
@@ -323,4 +351,23 @@ def test_pipelined_frames_equal_blocking_frames(gs):
     assert not np.array_equal(want[0], want[-1])
     with pytest.raises(RuntimeError):
         e.frame_end()                                   # nothing in flight any more
+    # three frames in flight over the two device buffers (begin(i+2) before end(i)); each needs its own host buffer; statistics of the
+    # frame that ended come from the blend kernel's status snapshot
+    bufs = [N.pinned_empty((h, w, 4), np.uint8) for _ in range(3)]
+    got = []
+    e.frame_begin(cams[0], bufs[0])
+    e.frame_begin(cams[1], bufs[1])
+    for i in range(len(cams)):
+        if i + 2 < len(cams):
+            e.frame_begin(cams[i + 2], bufs[(i + 2) % 3])
+        e.frame_end()
+        assert e.timings()["visible_splats"] > 0 and e.timings()["tile_instances"] > 0
+        got.append(bufs[i % 3].copy())
+    for i, (a, b) in enumerate(zip(got, want)):
+        assert np.array_equal(a, b), f"3-deep pipelined frame {i} differs"
+    e.frame_begin(cams[0], bufs[0]); e.frame_begin(cams[1], bufs[1]); e.frame_begin(cams[2], bufs[2])
+    with pytest.raises(RuntimeError):
+        e.frame_begin(cams[3], bufs[0])                 # a fourth frame in flight is refused
+    for _ in range(3):
+        e.frame_end()
     v.dispose()

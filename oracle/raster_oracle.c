@@ -9,9 +9,13 @@
  *   fragment     : SplatMaterial3D.js:234-252
  *   blend state  : SplatMaterial3D.js:65-75 (NormalBlending), clear (0,0,0,0) Viewer.js:353-360
  *
- * PARITY UNPINNED: the reference has no golden frames and its WebGL/three.js output cannot be produced in this
- * environment (no browser, three@0.160.0 not vendored).  This file is pinned only by reading the GLSL; the
- * blend-function mapping of THREE.NormalBlending is three.js behaviour restated from knowledge of
+ * PINNING: the reference has no golden frames and its WebGL/three.js output cannot be produced in this environment (no
+ * browser, three@0.160.0 not vendored), so no reference-made artefact pins this file ("parity unpinned" in that strict sense).
+ * It is pinned by an INDEPENDENT FORMULATION instead -- oracle/raster_independent.py, checked in
+ * tests/test_oracle_raster_independent.py -- that shares no code or algebra with this file or with the CUDA kernels:
+ * finite-difference Jacobian of the actual projection, conic exp(-1/2 d^T Sigma'^-1 d) where the shader's clamps are inactive,
+ * scipy's real spherical harmonics, and a triangle rasteriser of the 4-vertex quad with interpolated vPosition.
+ * The blend-function mapping of THREE.NormalBlending is three.js behaviour restated from knowledge of
  * WebGLState.setBlending (SRC_ALPHA, ONE_MINUS_SRC_ALPHA, ONE, ONE_MINUS_SRC_ALPHA).
  *
  * All arithmetic is f32, unfused, in GLSL expression order (-ffp-contract=off).  Coverage: a fragment exists for

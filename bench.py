@@ -377,7 +377,7 @@ def run_ours(args):
     # crosses PCIe on the copy stream.  No L2 flush inside this loop (it would sit in the timed stream): the frame's working set
     # (centres, splat data, records, sort scratch, lists: > 180 MB at 1.2 M splats) exceeds the 126 MB L2 and every frame's picture leaves
     # through PCIe.  N > 1 with the NCCL fallback keeps the blocking loop.
-    depth = 3 if world == 1 else 2      # frames in flight (N > 1: rank 0 holds ONE frame buffer, the peers store into it)
+    depth = 3      # frames in flight (N > 1 with the peer gather: rank 0's exported allocation holds two frames, the peers alternate)
     while len(frames_host) < depth:
         frames_host.append(N.pinned_empty((height, width, 4), np.uint8))
 
@@ -405,7 +405,7 @@ def run_ours(args):
             for i in range(K):
                 step_async(i)
             e.synchronize()
-        e2e_mode = f"pipelined gs_frame_begin/gs_frame_end on rank 0, {depth} frames in flight over {2 if world == 1 else 1} device frame buffer(s), pinned host frames"
+        e2e_mode = f"pipelined gs_frame_begin/gs_frame_end on rank 0, {depth} frames in flight over 2 device frame buffers, pinned host frames"
     else:
         for i in range(K):
             step_async(i)

@@ -1129,7 +1129,7 @@ static int pipe_init(gs_engine *e) {
     for (int i = 0; i < 2; ++i) CU(cudaEventCreateWithFlags(&e->ev_params[i], cudaEventDisableTiming));
     int rc = e->h_pipe.ensure(gs_engine::kPipeRing * kPipeSlotWords);
     if (rc) return rc;
-    const bool single = e->cfg.world_size > 1;
+    const bool single = e->cfg.world_size > 1;      // (rank 0 of a peer group may hold a double allocation instead: rs.frame_half2)
     if (!single && !e->rs.frame_alt.p) {
         cudaError_t ce = e->rs.frame_alt.ensure(e->rs.frame.n);
         if (ce != cudaSuccess) return fail(GS_ERR_CUDA, "cudaMalloc(second frame buffer) -> %s", cudaGetErrorString(ce));
@@ -1147,7 +1147,7 @@ extern "C" int gs_frame_begin(gs_engine *e, const gs_sort_params *s, const gs_un
     constexpr uint64_t R = gs_engine::kPipeRing;
     const uint64_t seq = e->pipe_begun;
     const uint32_t ring = (uint32_t)(seq % R);
-    const bool two = e->rs.frame_alt.p != nullptr;
+    const bool two = raster_second_frame(e->rs) != nullptr;
     // the buffer this frame renders into must have been copied out: frame seq-2 with two buffers, seq-1 with one
     if (two) { if (seq >= 2) CU(cudaStreamWaitEvent(e->stream, e->ev_copy_done[(seq - 2) % R], 0)); }
     else if (seq >= 1) CU(cudaStreamWaitEvent(e->stream, e->ev_copy_done[(seq - 1) % R], 0));
@@ -1161,7 +1161,8 @@ extern "C" int gs_frame_begin(gs_engine *e, const gs_sort_params *s, const gs_un
     if (rc) { e->rs.frame_parity = 0; return rc; }
     cudaStream_t st = e->stream;
     uint32_t *hs = e->h_pipe.p + ring * kPipeSlotWords;
-    const bool snapshot = two && e->last_frame_was_graph && e->graph_snapshot[e->rs.frame_parity];
+    // (multi-GPU: rank 0's peer_timeout flag is raised AFTER the blend, by k_peer_wait_arrived -- the snapshot would miss it)
+    const bool snapshot = two && e->cfg.world_size == 1 && e->last_frame_was_graph && e->graph_snapshot[e->rs.frame_parity];
     if (!snapshot) {      // status read-back in stream order (frames outside a graph, blend generations without the snapshot, one buffer)
         CU(cudaMemcpyAsync(hs, e->ctl.p, 12, cudaMemcpyDeviceToHost, st));
         CU(cudaMemcpyAsync(hs + 4, e->rs.rctl.p, sizeof(RasterControl), cudaMemcpyDeviceToHost, st));
@@ -1459,6 +1460,21 @@ extern "C" int gs_peer_export(gs_engine *e, void *frame_handle, void *sync_handl
     cudaError_t ce = e->rs.peer_sync_local.ensure(1);
     if (ce != cudaSuccess) return fail(GS_ERR_CUDA, "cudaMalloc -> %s", cudaGetErrorString(ce));
     CU(cudaMemset(e->rs.peer_sync_local.p, 0, sizeof(PeerSync)));
+    // Double the exported allocation: pipelined frames (gs_frame_begin) then alternate between its halves, so the picture of frame f
+    // leaves over PCIe while the peers already store frame f+1 into the other half.  Which half a frame uses travels in the release
+    // word.  Every rank sizes its own frame buffer from the same gs_config, so the peers know where the second half starts.
+    // GS_PEER_DOUBLE=0 keeps one buffer.
+    const char *pd = getenv("GS_PEER_DOUBLE");
+    if (!(pd && pd[0] == '0') && e->rs.blend_version >= 2 && !e->rs.frame_half2 && !e->pipe_inflight()) {
+        CU(cudaStreamSynchronize(e->stream));
+        const size_t half = e->rs.frame.n;
+        e->rs.frame.release();
+        ce = e->rs.frame.ensure(2 * half);
+        if (ce != cudaSuccess) return fail(GS_ERR_CUDA, "cudaMalloc(double frame buffer) -> %s", cudaGetErrorString(ce));
+        CU(cudaMemset(e->rs.frame.p, 0, 2 * half));
+        e->rs.frame_half2 = e->rs.frame.p + half;
+        e->rs.frame_half_bytes = half;
+    }
     static_assert(sizeof(cudaIpcMemHandle_t) == GS_IPC_HANDLE_BYTES, "IPC handle size");
     cudaIpcMemHandle_t h;
     CU(cudaIpcGetMemHandle(&h, e->rs.frame.p));

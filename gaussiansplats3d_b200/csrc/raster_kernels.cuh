@@ -37,7 +37,7 @@ struct RasterControl {
     uint32_t reserved0;
     uint32_t frame_seq;      // frames rendered so far (never reset): the peer-gather handshake counts in frames
     uint32_t peer_timeout;   // a peer handshake gave up waiting
-    uint32_t pad[1];
+    uint32_t peer_parity;    // ranks > 0: which half of rank 0's (double) frame buffer this frame's tiles go to (from the release word)
     unsigned long long subset_count;   // sharded frames: splats whose rect touches one of this rank's coarse tiles
     // visible-splat statistic, spread over 64 counters 32 B apart: one counter took ~1.6 ns per same-address atomic, which at one atomic
     // per warp WAS the duration of k_project (16 M splats: 500 K atomics = 0.79 ms; 1.2 M: 26 K = 41 us of a 37 us kernel)
@@ -45,7 +45,8 @@ struct RasterControl {
 };
 
 // Block in rank 0's memory that the other ranks map through CUDA IPC: the fused tile gather's handshake.
-//   released = f : rank 0 has finished with frame f-1's picture; peers may write frame f's tiles into rank 0's frame buffer
+//   released = 2 f + b : rank 0 has finished with the picture that last occupied half b of its frame allocation; peers may write
+//                  frame f's tiles into that half (b = 0 always unless rank 0 pipelines its frames over two halves)
 //   arrived      : += 1 by every peer once its tiles of the current frame are in rank 0's buffer
 struct PeerSync { uint32_t released; uint32_t arrived; uint32_t pad[2]; };
 
@@ -57,18 +58,22 @@ __device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t *p) {
 constexpr long long kPeerTimeoutCycles = 4000000000ll;   // ~2 s: a missing peer must never hang the GPU
 
 // rank 0, start of frame f: the picture of frame f-1 has been consumed (stream order) -> peers may overwrite the buffer
-__global__ void k_peer_release(PeerSync *sync, const RasterControl *rctl) {
+__global__ void k_peer_release(PeerSync *sync, const RasterControl *rctl, uint32_t half) {
     __threadfence_system();
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(&sync->released), "r"(rctl->frame_seq) : "memory");
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(&sync->released), "r"(rctl->frame_seq * 2u + (half & 1u)) : "memory");
 }
 // rank r > 0, before its blend of frame f: wait until rank 0 released frame f
 __global__ void k_peer_wait_release(const PeerSync *sync, RasterControl *rctl) {
+    // rank 0 cannot release frame f+1 before every peer has signalled frame f, so the word read here is frame f's
     const uint32_t f = rctl->frame_seq;
     const long long t0 = clock64();
-    while ((int32_t)(ld_acquire_sys_u32(&sync->released) - f) < 0) {
-        if (clock64() - t0 > kPeerTimeoutCycles) { rctl->peer_timeout = 1; break; }
+    uint32_t v = ld_acquire_sys_u32(&sync->released);
+    while ((int32_t)((v >> 1) - f) < 0) {
+        if (clock64() - t0 > kPeerTimeoutCycles) { rctl->peer_timeout = 1; v = 0; break; }
         __nanosleep(200);
+        v = ld_acquire_sys_u32(&sync->released);
     }
+    rctl->peer_parity = v & 1u;
 }
 // rank r > 0, after its blend: tiles are in rank 0's frame
 __global__ void k_peer_signal(PeerSync *sync) {
@@ -1117,14 +1122,18 @@ struct StatusSnapshot {
     const uint32_t *sort_ctl;     // SortControl head: 3 words (dmin, dmax, error)
     const uint32_t *raster_ctl;   // RasterControl
     uint32_t *dst;                // [0, 3) sort head, [4, 4 + sizeof(RasterControl) / 4) raster control; nullptr = no snapshot
+    // multi-GPU peers: the frame pointer is rank 0's allocation; *half_src (0 / 1, RasterControl::peer_parity) selects its half
+    const uint32_t *half_src;
+    unsigned long long half_bytes;
 };
 
 template <int FORMAT, int S, int ROUNDS, bool TMA>
 __global__ void __launch_bounds__(128 * S * S, S == 1 ? 8 : 2)
 k_blend2(const uint2 *__restrict__ ranges, const unsigned long long *__restrict__ list, const SplatRecord *__restrict__ rec, int tiles_x,
-         int tiles_y, int coarse_x, uint32_t rank, uint32_t world, int width, int height, int flip_y, void *__restrict__ frame, const uint32_t *__restrict__ tile_order,
+         int tiles_y, int coarse_x, uint32_t rank, uint32_t world, int width, int height, int flip_y, void *__restrict__ frame_base, const uint32_t *__restrict__ tile_order,
          StatusSnapshot snap) {
     pdl_enter();
+    void *__restrict__ frame = snap.half_src ? (void *)((unsigned char *)frame_base + (size_t)(*snap.half_src & 1u) * snap.half_bytes) : frame_base;
     // Everything the host reads back about a frame (sort error bits, instance / visibility counters, overflow flag) is final before the
     // blend starts; CTA 0 copies it into a per-frame-buffer slot so that the read-back can run on the copy stream, off this stream.
     if (snap.dst && blockIdx.x == 0) {
@@ -1381,6 +1390,8 @@ struct RasterState {
     RBuf<ProjParams> projp;     // per-frame projection parameters (device copy read by k_project)
     RBuf<unsigned char> frame;
     RBuf<unsigned char> frame_alt;   // second device frame: pipelined frames (gs_frame_begin) alternate so a D2H copy can overlap the next frame
+    unsigned char *frame_half2 = nullptr;   // multi-GPU rank 0 with a double-size exported frame allocation: its second half (instead of frame_alt)
+    size_t frame_half_bytes = 0;
     int frame_parity = 0;
     // status snapshot taken by the blend kernel (see StatusSnapshot): destination slots [parity * snap_stride], source sort control
     uint32_t *snap_base = nullptr;
@@ -1493,7 +1504,8 @@ static int raster_upload(RasterState &rs, const gs_config &c, const gs_splat_dat
     return GS_OK;
 }
 
-static void *raster_frame_ptr(RasterState &rs, int) { return (rs.frame_parity && rs.frame_alt.p) ? rs.frame_alt.p : rs.frame.p; }
+static unsigned char *raster_second_frame(RasterState &rs) { return rs.frame_alt.p ? rs.frame_alt.p : rs.frame_half2; }
+static void *raster_frame_ptr(RasterState &rs, int) { return (rs.frame_parity && raster_second_frame(rs)) ? raster_second_frame(rs) : rs.frame.p; }
 
 template <bool COVF16>
 static void launch_project(RasterState &rs, uint32_t count, cudaStream_t st) {
@@ -1572,7 +1584,7 @@ static int raster_render(RasterState &rs, const gs_config &c, const gs_uniforms 
         prof.mark("k_raster_init", st);
         // rank 0 frees its frame buffer for the peers' stores right at the START of the frame (everything that consumed the previous
         // picture is earlier in stream order), so their blends never wait for rank 0's own sort + binning
-        if (world > 1 && rs.peer_root) { k_peer_release<<<1, 1, 0, st>>>(rs.peer_sync, rs.rctl.p); ++launches; }
+        if (world > 1 && rs.peer_root) { k_peer_release<<<1, 1, 0, st>>>(rs.peer_sync, rs.rctl.p, (uint32_t)(rs.frame_parity && rs.frame_half2)); ++launches; }
         const uint32_t count = rs.uploaded;
         if (rs.cov_format == GS_COV_F16) launch_project<true>(rs, count, st); else launch_project<false>(rs, count, st);
         ++launches;
@@ -1631,8 +1643,10 @@ static int raster_render(RasterState &rs, const gs_config &c, const gs_uniforms 
         }
         const uint32_t grid = ncoarse * kFinePerCoarse;
         if (rs.blend_version >= 2 || tshift != kTileShift) {
+            const bool to_peer = peer_mode && rs.peer_attached;
             const StatusSnapshot snap{rs.snap_sort_ctl, reinterpret_cast<const uint32_t *>(rs.rctl.p),
-                                      (rs.snap_base && rs.snap_sort_ctl) ? rs.snap_base + (size_t)rs.frame_parity * rs.snap_stride : nullptr};
+                                      (rs.snap_base && rs.snap_sort_ctl) ? rs.snap_base + (size_t)rs.frame_parity * rs.snap_stride : nullptr,
+                                      to_peer ? &rs.rctl.p->peer_parity : nullptr, to_peer ? (unsigned long long)rs.frame.n : 0ull};
             rs.snapshot_taken = snap.dst != nullptr;
 #define GS_BLEND2(FMT, SC, RD, TM) gs_launch(k_blend2<FMT, SC, RD, TM>, grid, 128 * SC * SC, 0, st, rs.ranges.p, rs.list.p, rs.records.p, tiles_x, tiles_y, coarse_x, rank, world, (int)p.width, (int)p.height, p.flip_y, target, rs.tile_order.p, snap)
 #define GS_BLEND2F(SC, RD, TM) do { if (p.frame_format == GS_FRAME_RGBA8) GS_BLEND2(GS_FRAME_RGBA8, SC, RD, TM); else GS_BLEND2(GS_FRAME_RGBA32F, SC, RD, TM); } while (0)

@@ -123,6 +123,49 @@ def _peer_worker(rank, world, port, q):
         if rank == 0:
             ok = ok and bool(np.array_equal(got, want))
     dist.barrier()
+    # Pipelined frames on rank 0 (gs_frame_begin / gs_frame_end, three in flight): rank 0's exported allocation holds TWO frames and the
+    # half a frame uses travels in the release word, so the peers store frame f+1 while frame f's picture crosses PCIe.  A moving camera:
+    # every delivered picture must be that frame's single-GPU picture, in order.
+    from gaussiansplats3d_b200 import _native as N
+    e = v.engine
+    cams, wants = [], []
+    for k in range(7):
+        v.camera.position = np.asarray(v.initialCameraPosition) + np.array([0.12 * k, -0.04 * k, 0.08 * k])
+        v.camera.look_at(v.initialCameraLookAt)
+        v.camera.update(); v.updateSplatMesh()
+        cams.append(e.prepare_frame(v.mvp_matrix().astype(np.float32), v.uniforms(), w, h, n, frame_format=N.GS_FRAME_RGBA8, flip_y=True))
+    if rank == 0:
+        v1 = Viewer(opts)
+        v1.addSplatScene(raw)
+        for k in range(7):
+            v1.camera.position = np.asarray(v1.initialCameraPosition) + np.array([0.12 * k, -0.04 * k, 0.08 * k])
+            v1.camera.look_at(v1.initialCameraLookAt)
+            v1.camera.update(); v1.updateSplatMesh()
+            out = N.pinned_empty((h, w, 4), np.uint8)
+            v1.engine.frame_prepared(v1.engine.prepare_frame(v1.mvp_matrix().astype(np.float32), v1.uniforms(), w, h, n, frame_format=N.GS_FRAME_RGBA8, flip_y=True), out)
+            wants.append(out.copy())
+        v1.dispose()
+        assert not np.array_equal(wants[0], wants[-1])
+    dist.barrier()
+    for rep in range(2):
+        if rank == 0:
+            bufs = [N.pinned_empty((h, w, 4), np.uint8) for _ in range(3)]
+            e.frame_begin(cams[0], bufs[0]); e.frame_begin(cams[1], bufs[1])
+            for i in range(7):
+                if i + 2 < 7:
+                    e.frame_begin(cams[i + 2], bufs[(i + 2) % 3])
+                e.frame_end()
+                ok = ok and bool(np.array_equal(bufs[i % 3], wants[i]))
+        else:
+            for i in range(7):
+                e.frame_async(None, None, w, h, n, prepared=cams[i])
+            e.synchronize()
+        dist.barrier()
+        # and a blocking frame afterwards (half 0 again, whatever half the last pipelined frame used)
+        got = v.frame(frame_format=gs._native.GS_FRAME_RGBA8, flip_y=True)
+        if rank == 0:
+            ok = ok and bool(np.array_equal(got, wants[6]))
+        dist.barrier()
     q.put((rank, ok))
     v.dispose()
     dist.destroy_process_group()

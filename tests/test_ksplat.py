@@ -50,15 +50,16 @@ def test_to_half_three_truncates():
     assert h[3] == 65504.0 and h[4] == 65504.0 and h[7] == 0.0 and h[8] == -2.5
 
 
+# integer sorter centres for every (level, degree); the float-centre variant on a subset
+_DECODE_CASES = [(lv, dg, True) for lv, dg in LEVELS_DEGREES] + [(lv, dg, False) for lv, dg in LEVELS_DEGREES if (lv, dg) in ((0, 0), (1, 2), (2, 1))]
+
+
 @pytest.mark.gpu
-@pytest.mark.parametrize("level,deg", LEVELS_DEGREES)
-@pytest.mark.parametrize("integer", [True, False])
+@pytest.mark.parametrize("level,deg,integer", _DECODE_CASES)
 def test_gpu_decode_matches_splatbuffer_semantics(gs, level, deg, integer):
     from gaussiansplats3d_b200 import ksplat as K
     from gaussiansplats3d_b200 import _native as N
     from oracle import ksplat_oracle as KO
-    if not integer and (level, deg) not in ((0, 0), (1, 2), (2, 1)):
-        pytest.skip("float-centre variant checked on a subset")
     raw, sh = _scene(n=20000, seed=4 + level, deg=deg)
     half_cov = (level == 1)
     data = K.write(raw.centers, raw.scales, raw.rotations, raw.colors, sh, deg, compression_level=level, bucket_size=100 if level else K.BUCKET_SIZE)

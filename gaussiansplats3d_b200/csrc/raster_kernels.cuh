@@ -756,14 +756,15 @@ template <int CFG>
 __global__ void __launch_bounds__(Bin2Cfg<CFG>::kWarps * 32)
 k_bin_place(const uint32_t *__restrict__ order, uint32_t render_count_host, const unsigned long long *__restrict__ n_dev, const ushort4 *__restrict__ rect_by_rank,
             int coarse_x, uint32_t nt, const uint32_t *__restrict__ offsets, uint32_t stride, unsigned long long *__restrict__ list, unsigned long long capacity,
-            RasterControl *rctl, OwnMask own, int sharded) {
+            RasterControl *rctl, OwnMask own, int sharded, int pack_ok) {
     pdl_enter();
     constexpr int W = Bin2Cfg<CFG>::kWarps, ITEMS = Bin2Cfg<CFG>::kItems, NT = kBinTiles;
     const uint32_t n = n_dev ? (uint32_t)*n_dev : render_count_host;
     const uint32_t base = blockIdx.x * (uint32_t)(W * 32 * ITEMS);
     if (base >= n) return;
     __shared__ uint32_t s_pre[W][NT];      // instances of this warp per tile, then: END of the slots this warp has handed out in the tile's list
-    __shared__ uint32_t s_mask[W][NT];     // lanes of the current round that touch the tile
+    __shared__ __align__(8) uint32_t s_mask[W][NT];     // lanes of the current round that touch the tile (first: staging of the compaction)
+    constexpr bool kCanCompact = NT * 4 >= 32 * ITEMS * 8;   // the mask row of a warp doubles as the staging buffer of its compacted items
     for (uint32_t i = threadIdx.x; i < (uint32_t)(W * NT); i += W * 32) (&s_pre[0][0])[i] = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -777,9 +778,45 @@ k_bin_place(const uint32_t *__restrict__ order, uint32_t render_count_host, cons
         rc[k] = p < n ? rect_by_rank[p] : make_ushort4(1, 1, 0, 0);
     }
     uint32_t *my_pre = s_pre[warp], *my_mask = s_mask[warp];
+    // Culled splats (empty rect) and, on a sharded frame, splats that reach none of this rank's tiles leave most lanes idle in the
+    // rounds below (ncu: 9-13 of 32 lanes active).  The warp's 32 * ITEMS items are therefore compacted first, order preserved
+    // (item k of lane l is draw rank run + 32 k + l, so (k, lane) order is draw order): fewer rounds, full lanes.  A compacted item is
+    // 8 bytes, {rect as 4 x u8, splat id}, which needs the frame to be at most 256 tiles wide and high (pack_ok).
+    uint32_t nvalid = 32u * ITEMS;
+    if (kCanCompact && pack_ok) {
+        const uint32_t lt = lanemask_lt();
+        unsigned long long *stage = reinterpret_cast<unsigned long long *>(my_mask);
+        uint32_t before = 0;
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k) {
+            const bool keep = sid[k] != 0xffffffffu && (sharded ? rect_touches_owned(rc[k], own) : (rc[k].z >= rc[k].x && rc[k].w >= rc[k].y));
+            const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+            if (keep) stage[before + __popc(bal & lt)] = ((unsigned long long)((uint32_t)rc[k].x | ((uint32_t)rc[k].y << 8) | ((uint32_t)rc[k].z << 16) | ((uint32_t)rc[k].w << 24)) << 32) | sid[k];
+            before += __popc(bal);
+        }
+        nvalid = before;
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k) {
+            const uint32_t j = (uint32_t)k * 32u + (uint32_t)lane;
+            sid[k] = 0xffffffffu;
+            rc[k] = make_ushort4(1, 1, 0, 0);
+            if (j < nvalid) {
+                const unsigned long long v = stage[j];
+                const uint32_t pr = (uint32_t)(v >> 32);
+                sid[k] = (uint32_t)v;
+                rc[k] = make_ushort4((unsigned short)(pr & 255u), (unsigned short)((pr >> 8) & 255u), (unsigned short)((pr >> 16) & 255u), (unsigned short)(pr >> 24));
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < NT / 32; ++i) my_mask[i * 32 + lane] = 0u;      // (rounds clear it again; keeps the buffer's two uses apart)
+        __syncwarp();
+    }
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k)
-        round_instances(sid[k] != 0xffffffffu, sid[k], rc[k], coarse_x, own, sharded != 0, [&](int, uint32_t, int t, uint32_t) { atomicAdd(&my_pre[t], 1u); });
+        if ((uint32_t)k * 32u < nvalid)      // warp-uniform
+            round_instances(sid[k] != 0xffffffffu, sid[k], rc[k], coarse_x, own, sharded != 0, [&](int, uint32_t, int t, uint32_t) { atomicAdd(&my_pre[t], 1u); });
     __syncthreads();
     for (uint32_t t = threadIdx.x; t < nt; t += W * 32) {   // counts -> first slot of each warp (chunk offset + earlier warps)
         uint32_t at = offsets[(size_t)t * stride + blockIdx.x];
@@ -794,6 +831,7 @@ k_bin_place(const uint32_t *__restrict__ order, uint32_t render_count_host, cons
     bool overflow = false;
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k) {
+        if ((uint32_t)k * 32u >= nvalid) break;      // warp-uniform: the compacted items fill the first rounds
         const bool valid = sid[k] != 0xffffffffu;
         // a round: (1) clear the warp's lane masks, (2) every instance sets its owner's bit in its tile's mask and takes one slot of the
         // tile's list, (3) with all bits in place, the instance of lane l sits popc(mask & lanes below l) after the round's first slot,
@@ -1384,6 +1422,7 @@ struct RasterState {
     RBuf<uint32_t> bin_totals;  // binning v2: instances per coarse tile (1024 words, zeroed by k_raster_init)
     uint32_t bin_stride = 0;
     int bin_cfg = 0;
+    int bin_compact = 1;        // GS_BIN_COMPACT=0: k_bin_place without the warp-level compaction of culled splats (A/B)
     int bin_version = 2, blend_version = 2;   // GS_BIN / GS_BLEND = 1 selects the round-1 kernels (A/B measurements)
     int blend_tma = 0, blend_rounds = 4;      // GS_BLEND_TMA = 1: bulk-async list prefetch; GS_BLEND_ROUNDS = 2 / 4 (16-px tiles)
     RBuf<DynamicUniforms> dyn;
@@ -1448,6 +1487,7 @@ static int raster_init(RasterState &rs, const gs_config &c, int sm_count) {
         RCU(rs.tile_hist.ensure(radix_tile_hist_words(rs.instance_capacity, 2, &rs.hist_stride)));
         if (const char *v = getenv("GS_BIN")) rs.bin_version = atoi(v);
         if (const char *v = getenv("GS_BLEND")) rs.blend_version = atoi(v);
+        if (const char *v = getenv("GS_BIN_COMPACT")) rs.bin_compact = atoi(v);
         if (const char *v = getenv("GS_BLEND_TMA")) rs.blend_tma = atoi(v);
         if (const char *v = getenv("GS_BLEND_ROUNDS")) rs.blend_rounds = atoi(v);
         if (const char *v = getenv("GS_BINCFG")) rs.bin_cfg = atoi(v);
@@ -1599,7 +1639,7 @@ static int raster_render(RasterState &rs, const gs_config &c, const gs_uniforms 
         const int sharded = world > 1 ? 1 : 0;
         const uint32_t chunks = (p.render_count + kBinRanks - 1u) / kBinRanks;
 #define GS_BIN_COUNT(C) gs_launch(k_bin_count<C>, chunks, Bin2Cfg<C>::kWarps * 32, 0, st, d_order, p.render_count, order_count_dev, rs.rects.p, coarse_x, ncoarse, rs.bin_hist.p, rs.bin_stride, rs.bin_totals.p, rs.rect_by_rank.p, own, sharded)
-#define GS_BIN_PLACE(C) gs_launch(k_bin_place<C>, chunks, Bin2Cfg<C>::kWarps * 32, 0, st, d_order, p.render_count, order_count_dev, rs.rect_by_rank.p, coarse_x, ncoarse, rs.bin_hist.p, rs.bin_stride, rs.list.p, rs.instance_capacity, rs.rctl.p, own, sharded)
+#define GS_BIN_PLACE(C) gs_launch(k_bin_place<C>, chunks, Bin2Cfg<C>::kWarps * 32, 0, st, d_order, p.render_count, order_count_dev, rs.rect_by_rank.p, coarse_x, ncoarse, rs.bin_hist.p, rs.bin_stride, rs.list.p, rs.instance_capacity, rs.rctl.p, own, sharded, (rs.bin_compact && tiles_x <= 256 && tiles_y <= 256) ? 1 : 0)
         if (rs.bin_cfg == 0) GS_BIN_COUNT(0); else GS_BIN_COUNT(1);
         ++launches;
         prof.mark("k_bin_count", st);

@@ -498,7 +498,8 @@ def run_ours(args):
                    + "; tile gather = " + (gather_kind or "none"))
         line = {
             "metric": "frames_per_sec", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "ms_per_step": total_ms / K, "ms_per_step_median": float(np.median(step_ms)), "ms_per_step_max": float(step_ms.max()),
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "int32 sort keys / f32 raster", "data": "synthetic",
             "config": {"workload": workload_label(args.workload), "l2": "flushed between steps (192 MiB write)", "parallelism": par,
                        "distance_map_range": 65536, "gather": gather_kind},

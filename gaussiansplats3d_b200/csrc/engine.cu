@@ -944,6 +944,7 @@ extern "C" int gs_render(gs_engine *e, const gs_uniforms *u, const gs_render_par
     int rc = check_engine(e);
     if (rc) return rc;
     if (!u || !p) return fail(GS_ERR_BAD_ARG, "gs_render: null argument");
+    if (e->pipe_inflight()) return fail(GS_ERR_NOT_READY, "gs_render: pipelined frames are in flight (gs_frame_end first)");
     const uint32_t *d_order = nullptr;
     e->last_frame_was_graph = false;
     if ((rc = stage_order(e, p, &d_order))) return rc;
@@ -1101,6 +1102,7 @@ extern "C" int gs_frame_async(gs_engine *e, const gs_sort_params *s, const gs_un
     int rc = check_engine(e);
     if (rc) return rc;
     if (!s || !u || !p) return fail(GS_ERR_BAD_ARG, "gs_frame_async: null argument");
+    if (e->pipe_inflight()) return fail(GS_ERR_NOT_READY, "gs_frame_async: pipelined frames are in flight (gs_frame_end first): their pictures are still being copied out of the frame buffers");
     gs_sort_params q; gs_render_params rp;
     if ((rc = enqueue_frame(e, s, u, p, q, rp))) return rc;
     e->pending_async = true;

@@ -368,6 +368,8 @@ def test_pipelined_frames_equal_blocking_frames(gs):
     e.frame_begin(cams[0], bufs[0]); e.frame_begin(cams[1], bufs[1]); e.frame_begin(cams[2], bufs[2])
     with pytest.raises(RuntimeError):
         e.frame_begin(cams[3], bufs[0])                 # a fourth frame in flight is refused
+    with pytest.raises(RuntimeError):
+        e.frame_async(None, None, w, h, n, prepared=cams[3])   # so is anything else that would overwrite a frame buffer being copied out
     for _ in range(3):
         e.frame_end()
     v.dispose()

@@ -157,3 +157,37 @@ def test_viewer_sort_schedule_follows_reference_state_machine(gs):
         partial_seen = partial_seen or want < rc
     assert partial_seen, "the path must exercise the partial-sort queue"
     v.dispose()
+
+
+def test_cull_decision_against_an_angle_formulation():
+    """Independent check of the restated cull rule (Viewer.js:2010-2037): the reference tests dot products of normalised in-plane
+    projections against cos(fov/2) - 0.6; here the same geometry is decided with angles (atan2 / acos on numpy vectors, none of the
+    restatement's helpers).  A leaf survives unless it is farther away than its own diagonal AND outside the widened frustum in x or y."""
+    from gaussiansplats3d_b200.scenes import synthetic_scene
+    from gaussiansplats3d_b200.splat_tree import fov_cosines
+    import cases
+    raw = synthetic_scene(20000, seed=12, kind="bonsai")
+    leaves = TO.build_leaves(raw.centers, raw.colors[:, 3], 1, 8, 150)
+    cx, cy = fov_cosines(1280.0, 720.0, 50.0)
+    checked = culled = 0
+    for eye, target in (((1.5, 2.7, -6.4), (0.45, 1.95, 1.5)), ((0.2, 0.1, -0.3), (3.0, 0.5, 2.0)), ((-14.0, 0.0, 0.0), (-30.0, 0.0, 0.0))):
+        _, view, _ = cases.camera_mvp(eye=eye, target=target, up=(0.02, -0.76, -0.65))
+        out, n = TO.gather_for_sort(leaves, view, cx, cy)
+        kept_ids = set(out.tolist())
+        V = np.asarray(view, np.float64).reshape(4, 4).T
+        for mn, mx, _d, idx in leaves:
+            mn, mx = np.asarray(mn), np.asarray(mx)
+            t = V[:3, :3] @ ((mx - mn) * 0.5 + mn) + V[:3, 3]
+            dist, diag = np.linalg.norm(t), np.linalg.norm(mx - mn)
+            ang_x, ang_y = np.arctan2(abs(t[0]), -t[2]), np.arctan2(abs(t[1]), -t[2])          # angle from the view direction (0, 0, -1)
+            lim_x = np.arccos(np.clip(cx - 0.6, -1.0, 1.0)) if cx - 0.6 > -1.0 else np.inf
+            lim_y = np.arccos(np.clip(cy - 0.6, -1.0, 1.0)) if cy - 0.6 > -1.0 else np.inf
+            margins = [abs(ang_x - lim_x), abs(ang_y - lim_y), abs(dist - diag)]
+            if min(margins) < 1e-6:
+                continue                                          # on a threshold: rounding may decide either way
+            want_culled = (ang_x > lim_x or ang_y > lim_y) and dist > diag
+            is_kept = idx[0] in kept_ids
+            assert is_kept == (not want_culled), (eye, mn.tolist(), ang_x, lim_x, ang_y, lim_y, dist, diag)
+            checked += 1
+            culled += int(want_culled)
+    assert checked > 300 and 0 < culled < checked

@@ -275,7 +275,10 @@ GS_API int gs_synchronize(gs_engine *e);
 /* Fused tile gather (multi-GPU, one process per GPU).  Rank 0 exports CUDA-IPC handles of its frame buffer and of a small handshake
  * block; every other rank attaches, after which its blend kernel stores finished pixels STRAIGHT INTO RANK 0'S FRAME over NVLink
  * and rank 0's frame is complete when gs_frame / gs_synchronize returns -- no NCCL call, no staging copy.  All ranks must render
- * the same sequence of frames.  (Without these calls the ranks' frames are zero outside their own tiles and can be summed.)        */
+ * the same sequence of frames.  (Without these calls the ranks' frames are zero outside their own tiles and can be summed.)
+ * The exported allocation holds TWO frames (all ranks size it from the same gs_config): rank 0's pipelined frames (gs_frame_begin)
+ * alternate between the halves, the half in use travels in the handshake, so frame f+1 is assembled while frame f's picture is
+ * copied to the host.  Environment GS_PEER_DOUBLE=0 on rank 0 keeps a single frame.                                                */
 #define GS_IPC_HANDLE_BYTES 64
 GS_API int gs_peer_export(gs_engine *e, void *frame_handle /*64 B out*/, void *sync_handle /*64 B out*/);      /* rank 0     */
 GS_API int gs_peer_attach(gs_engine *e, const void *frame_handle, const void *sync_handle);                    /* ranks > 0  */

@@ -70,7 +70,8 @@ def orbit_position(cam: dict, k: int) -> np.ndarray:
 class ClockSampler:
     """nvidia-smi clocks + throttle reasons sampled every 200 ms while the timed regions run."""
 
-    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    # (no power.draw: that query is the slow one, and a sample that lands inside the ~50 ms timed window must not stall the GPU)
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, gpu_index: int):
         self.rows, self.proc, self.gpu, self.first = [], None, gpu_index, 0
@@ -104,7 +105,7 @@ class ClockSampler:
                 sm.append(float(r[0])); mx = max(mx, float(r[1]))
             except Exception:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
